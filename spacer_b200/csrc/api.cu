@@ -1,0 +1,42 @@
+// Error plumbing and device queries shared by every translation unit of libspacer_b200.so.
+#include "common.cuh"
+#include "spacer_b200.h"
+#include <cstdarg>
+#include <cstdio>
+
+namespace {
+thread_local char g_err[1024] = "";
+}
+
+void sb_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sb_check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    sb_set_error("%s: kernel launch failed: %s", what, cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+
+extern "C" const char* sb_last_error(void) { return g_err; }
+extern "C" int sb_abi_version(void) { return SB_ABI_VERSION; }
+
+extern "C" int sb_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  SB_CUDA(cudaGetDevice(&dev));
+  int sms = 0, maj = 0, mnr = 0;
+  SB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  SB_CUDA(cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev));
+  SB_CUDA(cudaDeviceGetAttribute(&mnr, cudaDevAttrComputeCapabilityMinor, dev));
+  if (sm_count) *sm_count = sms;
+  if (cc_major) *cc_major = maj;
+  if (cc_minor) *cc_minor = mnr;
+  SB_REQUIRE(maj == 10, "spacer_b200 kernels are built for sm_100a only; device is sm_%d%d", maj, mnr);
+  return 0;
+}
