@@ -72,6 +72,122 @@ int sb_gemm(const sb_gemm_args* args, sb_stream_t stream);
 /* number of non-empty K splits sb_gemm will use for (K, k_splits) */
 int sb_gemm_effective_splits(int K, int k_splits);
 
+/* ------------------------------------------------------------------------------------------------
+ * Bandwidth-bound kernels (fp32 math, bf16 storage)
+ * ------------------------------------------------------------------------------------------------ */
+/* pixel_values fp32 -> bf16 (the `.to(dtype)` at MQ2:306) */
+int sb_cast_f32_bf16(const float* src, void* dst, long long n, sb_stream_t stream);
+/* torch.nn.LayerNorm(E, eps) of the ViT blocks / merger (MQ2:464-465,317); mean/rstd [T] optional outputs */
+int sb_layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd, int T, int E,
+                     float eps, sb_stream_t stream);
+/* dx = [dres +] dLN(dy); dw/db are fp32 accumulators [E] (+=) */
+int sb_layernorm_bwd(const void* x, const void* w, const float* mean, const float* rstd, const void* dy,
+                     const void* dres, void* dx, float* dw, float* db, int T, int E, sb_stream_t stream);
+/* Qwen2VLRMSNorm (MQ2:117-131) */
+int sb_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int T, int H, float eps, sb_stream_t stream);
+int sb_rmsnorm_bwd(const void* x, const void* w, const float* rstd, const void* dy, const void* dres, void* dx,
+                   float* dw, int T, int H, sb_stream_t stream);
+/* apply_rotary_pos_emb_vision + rot_pos_emb (MQ2:257-268,725-752) in place on q,k of qkv [T, 3*heads*hd];
+ * grids_dev: int32 [n_grids][3] (t,h,w) on the device; inverse=1 applies the transpose rotation (backward) */
+int sb_rope_vit(void* qkv, int T, int heads, int head_dim, const int* grids_dev, int n_grids, int merge, int inverse,
+                sb_stream_t stream);
+/* apply_multimodal_rotary_pos_emb (MQ2:188-254) in place on q,k of qkv [T,(nh+2nkv)*hd]; pos int32 [3,T];
+ * optionally copies the rotated k and v into a KV cache (row stride kv_ld elements) */
+int sb_mrope(void* qkv, const int* pos, int T, int n_heads, int n_kv_heads, int head_dim, float theta, int sec_t,
+             int sec_h, int inverse, void* k_out, void* v_out, long long kv_ld, sb_stream_t stream);
+/* activation recompute / backward; mode 0 = quick_gelu (activations.py:117), 1 = gelu(erf) */
+int sb_act_fwd(const void* z, void* f, long long n, int mode, sb_stream_t stream);
+int sb_act_bwd(const void* z, const void* dy, void* dz, long long n, int mode, sb_stream_t stream);
+/* SwiGLU backward on the interleaved raw [gate|up] output: dgu from dact; optional recompute of act */
+int sb_swiglu_bwd(const void* gu, const void* dact, void* dgu, void* act, int T, int I, sb_stream_t stream);
+/* running index of placeholder (video/image) tokens: vis_idx[t] = k for the k-th placeholder, else -1 */
+int sb_vision_index(const int* ids, int* vis_idx, int T, int video_id, int image_id, int* count_out,
+                    sb_stream_t stream);
+/* embed_tokens lookup + masked_scatter of vision embeddings (MQ2:1255-1272) */
+int sb_embed_merge(const int* ids, const int* vis_idx, const void* embed, const void* vision, void* out, int T, int H,
+                   int n_vision, sb_stream_t stream);
+int sb_embed_bwd(const int* ids, const int* vis_idx, const void* dx, void* d_embed, void* d_vision, int T, int H,
+                 int n_vision, sb_stream_t stream);
+int sb_gather_rows(const void* src, const int* rows, void* dst, int R, int H, sb_stream_t stream);
+int sb_scatter_add_rows(const void* src, const int* rows, void* dst, int R, int H, sb_stream_t stream);
+/* out_f32[n] += sum_t dy[t][n]   (bias gradients) */
+int sb_colsum(const void* dy, float* out, int T, int N, long long ld, sb_stream_t stream);
+int sb_f32_to_bf16_2d(const float* src, void* dst, int T, int W, long long ldd, sb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Attention (flash-style, varlen/prefix mask).  replaces flash_attn_varlen_func / sdpa under MQ2:415-454
+ * (ViT, head_dim 80, block-diagonal) and MQ2:575-590 (Qwen2 causal GQA, head_dim 128).
+ * meta: int32 [T][4] = (prefix_len, seg_start, kv_end, 0): key j visible to query t iff
+ *       j < prefix_len || seg_start <= j < kv_end.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct sb_attn_args {
+  const void* q; const void* k; const void* v; /* bf16; head h at column h*head_dim (kv head for k, v)   */
+  long long ldq, ldk, ldv;
+  void* o; long long ldo;                      /* bf16 [T, n_heads*head_dim]                             */
+  float* lse;                                  /* fp32 [n_heads][T] (natural log); required for backward */
+  const int* meta;
+  int T, Tk;                                   /* queries / keys (Tk = 0 -> T)                           */
+  int n_heads, n_kv_heads, head_dim;
+  float scale;
+  /* backward only */
+  const void* d_o; long long lddo;
+  float* delta;                                /* fp32 [n_heads][T] scratch                              */
+  float* dq_acc;                               /* fp32 [T][n_heads*head_dim], zeroed by the caller (+=)  */
+  void* dk; void* dv; long long lddk, lddv;    /* bf16 outputs, kv head h at column h*head_dim           */
+} sb_attn_args;
+int sb_attn_fwd(const sb_attn_args* args, sb_stream_t stream);
+int sb_attn_bwd(const sb_attn_args* args, sb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Decode step (q_len = 1): consumers of the split-K GEMV partials parts[s][r][n]
+ * (element (s,r,n) at parts + s*stride_s + r*stride_r + n).  `step_ptr` is a device int (the number of
+ * completion tokens already in the cache) so that one captured CUDA graph serves every step.
+ * replaces the per-token iterations of GenerationMixin._sample (generation/utils.py:2743-2806) through
+ * Qwen2VLDecoderLayer (MQ2:597-662) and DynamicCache.update (cache_utils.py:102-120).
+ * ------------------------------------------------------------------------------------------------ */
+int sb_dec_embed(const int* tokens, const void* embed, void* x, int R, int H, sb_stream_t stream);
+int sb_dec_residual_rmsnorm(void* x, const float* parts, int S, long long stride_s, long long stride_r, const void* w,
+                            void* xn, int R, int H, float eps, sb_stream_t stream);
+int sb_dec_qkv_post(const float* parts, int S, long long stride_s, long long stride_r, const void* bias,
+                    const int* step_ptr, int rope_base, float theta, int n_heads, int n_kv_heads, int head_dim,
+                    void* q_out, void* k_cache, void* v_cache, long long cache_stride_r, int c_max, int R,
+                    sb_stream_t stream);
+/* split-KV attention over the shared prompt cache(s) [P][nkv*hd] (rows < rows_group0 use kp0/vp0, the rest
+ * kp1/vp1) plus each row's completion cache [c_max][nkv*hd]; out bf16 [R][n_heads*hd] */
+int sb_dec_attn(const void* q, const void* kp0, const void* vp0, const void* kp1, const void* vp1, int rows_group0,
+                int P, const void* k_cache, const void* v_cache, long long cache_stride_r, const int* step_ptr,
+                int n_heads, int n_kv_heads, int head_dim, float scale, int n_split, float* o_part, float* ml_part,
+                void* out, int R, sb_stream_t stream);
+int sb_dec_swiglu(const float* parts, int S, long long stride_s, long long stride_r, void* act, int R, int I,
+                  sb_stream_t stream);
+/* top-p sampling of one token per row from fp32 logits [R][ld]; TopPLogitsWarper + multinomial semantics
+ * (logits_process.py:521-533, generation/utils.py:2789-2797).  out_ids[r][*step_ptr] = token (optional) */
+int sb_sample_top_p(const float* logits, long long ld, int R, int V, float top_p, unsigned long long seed,
+                    const int* step_ptr, int* finished, int* out_tokens, int* out_ids, long long out_ld,
+                    float* out_logprob, int eos_id, int pad_id, int suppress_eos, sb_stream_t stream);
+int sb_step_advance(int* step_ptr, sb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GRPO loss tail, forward + backward (SG_RLVR_trainer.py:353-366, 489-494, 551-552, 632-643)
+ * inputs are the LMHEAD-epilogue partials of the lm_head GEMM over the G*C scoring rows.
+ * out2 = {loss, mean_kl}; coef_out = dLoss/dlogprob per token (0 outside the completion mask).
+ * ------------------------------------------------------------------------------------------------ */
+int sb_grpo_loss(const float* lse_part, int n_tiles, const float* tgt_logit, const int* comp_ids, int G, int C,
+                 int eos_id, const float* ref_lp, const float* adv, float beta, float* lp_out, float* lse_out,
+                 float* coef_out, int* mask_out, float* row_loss, float* row_kl, int* row_len, float* out2,
+                 sb_stream_t stream);
+int sb_logprob_from_partials(const float* lse_part, int n_tiles, const float* tgt_logit, float* lp_out, long long rows,
+                             sb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * AdamW + global-norm clip over flat arenas (run_SpaceR_SG_RLVR.sh:23-25,37; zero3.json:10-12)
+ * ------------------------------------------------------------------------------------------------ */
+int sb_grad_sumsq(const void* g, long long n, int grad_is_f32, float* total_sq, sb_stream_t stream);
+int sb_adamw_step(void* param_bf16, float* master, void* m, void* v, const void* grad, long long n, int grad_is_f32,
+                  int moments_are_bf16, const float* total_sq, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, int step, float max_norm, float grad_scale, sb_stream_t stream);
+int sb_bf16_to_f32(const void* src, float* dst, long long n, sb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

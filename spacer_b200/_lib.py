@@ -50,7 +50,7 @@ def load():
             "(spacer_b200 has no CPU/PyTorch fallback path)")
     lib = C.CDLL(str(_LIB_PATH), mode=os.RTLD_GLOBAL if hasattr(os, "RTLD_GLOBAL") else 0)
     lib.sb_last_error.restype = C.c_char_p
-    lib.sb_abi_version.restype = C.c_int
+    bind(lib)
     _lib = lib
     return lib
 
@@ -59,3 +59,61 @@ def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = load().sb_last_error().decode("utf-8", "replace")
         raise SpacerError(f"{what}: {msg}" if what else msg)
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p),
+        ("ldq", C.c_longlong), ("ldk", C.c_longlong), ("ldv", C.c_longlong),
+        ("o", C.c_void_p), ("ldo", C.c_longlong),
+        ("lse", C.c_void_p), ("meta", C.c_void_p),
+        ("T", C.c_int), ("Tk", C.c_int),
+        ("n_heads", C.c_int), ("n_kv_heads", C.c_int), ("head_dim", C.c_int),
+        ("scale", C.c_float),
+        ("d_o", C.c_void_p), ("lddo", C.c_longlong),
+        ("delta", C.c_void_p), ("dq_acc", C.c_void_p),
+        ("dk", C.c_void_p), ("dv", C.c_void_p), ("lddk", C.c_longlong), ("lddv", C.c_longlong),
+    ]
+
+
+_HEADER = Path(__file__).resolve().parent.parent / "include" / "spacer_b200.h"
+_CT = {"p": C.c_void_p, "i": C.c_int, "l": C.c_longlong, "f": C.c_float, "u": C.c_ulonglong, "s": C.c_void_p}
+
+
+def header_signatures() -> dict:
+    """Parse include/spacer_b200.h: {function name: type-code string} with p = pointer, i = int,
+    l = long long, f = float, u = unsigned long long, s = stream.  The header is the single source of truth
+    for the ABI; the ctypes argtypes are derived from it."""
+    import re
+    src = re.sub(r"/\*.*?\*/", "", _HEADER.read_text(), flags=re.S)
+    sigs = {}
+    for m in re.finditer(r"\bint\s+(sb_\w+)\s*\((.*?)\)\s*;", src, flags=re.S):
+        name, args = m.group(1), m.group(2).strip()
+        codes = ""
+        if args and args != "void":
+            for a in args.split(","):
+                a = a.strip()
+                if "sb_stream_t" in a:
+                    codes += "s"
+                elif "*" in a:
+                    codes += "p"
+                elif "unsigned long long" in a:
+                    codes += "u"
+                elif "long long" in a:
+                    codes += "l"
+                elif "float" in a:
+                    codes += "f"
+                elif "int" in a:
+                    codes += "i"
+                else:
+                    raise SpacerError(f"cannot parse argument '{a}' of {name} in {_HEADER}")
+        sigs[name] = codes
+    return sigs
+
+
+def bind(lib):
+    for name, sig in header_signatures().items():
+        fn = getattr(lib, name)
+        fn.argtypes = [_CT[c] for c in sig]
+        fn.restype = C.c_int
+    return lib

@@ -75,3 +75,121 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn=False, b_mn=False, out=None, 
             setattr(g, name, t.data_ptr())
     check(lib.sb_gemm(C.byref(g), _stream()), "sb_gemm")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# generic call: tensors -> device pointers, the current stream appended
+# ------------------------------------------------------------------------------------------------
+def call(name: str, *args):
+    lib = _lib.load()
+    fn = getattr(lib, name)
+    conv = []
+    for a in args:
+        if isinstance(a, torch.Tensor):
+            if not a.is_cuda:
+                raise SpacerError(f"{name}: CPU tensor passed to a device entry point")
+            conv.append(a.data_ptr())
+        else:
+            conv.append(a)
+    check(fn(*conv, torch.cuda.current_stream().cuda_stream), name)
+
+
+def cast_f32_bf16(src, dst=None):
+    _req(src, torch.float32, "src")
+    if dst is None:
+        dst = torch.empty(src.shape, device=src.device, dtype=torch.bfloat16)
+    call("sb_cast_f32_bf16", src, dst, src.numel())
+    return dst
+
+
+def layernorm_fwd(x, w, b, eps=1e-6, save_stats=False, out=None):
+    T, E = x.shape
+    y = out if out is not None else torch.empty_like(x)
+    mean = rstd = None
+    if save_stats:
+        mean = torch.empty(T, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(T, device=x.device, dtype=torch.float32)
+    call("sb_layernorm_fwd", x, w, b, y, mean, rstd, T, E, eps)
+    return (y, mean, rstd) if save_stats else y
+
+
+def layernorm_bwd(x, w, mean, rstd, dy, dw, db, dres=None, out=None):
+    T, E = x.shape
+    dx = out if out is not None else torch.empty_like(x)
+    call("sb_layernorm_bwd", x, w, mean, rstd, dy, dres, dx, dw, db, T, E)
+    return dx
+
+
+def rmsnorm_fwd(x, w, eps=1e-6, save_stats=False, out=None):
+    T, H = x.shape
+    y = out if out is not None else torch.empty_like(x)
+    rstd = torch.empty(T, device=x.device, dtype=torch.float32) if save_stats else None
+    call("sb_rmsnorm_fwd", x, w, y, rstd, T, H, eps)
+    return (y, rstd) if save_stats else y
+
+
+def rmsnorm_bwd(x, w, rstd, dy, dw, dres=None, out=None):
+    T, H = x.shape
+    dx = out if out is not None else torch.empty_like(x)
+    call("sb_rmsnorm_bwd", x, w, rstd, dy, dres, dx, dw, T, H)
+    return dx
+
+
+def rope_vit(qkv, heads, head_dim, grids_dev, merge=2, inverse=False):
+    call("sb_rope_vit", qkv, qkv.shape[0], heads, head_dim, grids_dev, grids_dev.shape[0], merge, int(inverse))
+
+
+def mrope(qkv, pos, n_heads, n_kv_heads, head_dim, theta, sections, inverse=False, k_out=None, v_out=None, kv_ld=0):
+    _req(pos, torch.int32, "pos")
+    call("sb_mrope", qkv, pos, qkv.shape[0], n_heads, n_kv_heads, head_dim, float(theta), sections[0], sections[1],
+         int(inverse), k_out, v_out, kv_ld)
+
+
+def attn_args(q, k, v, o, meta, n_heads, n_kv_heads, head_dim, scale, lse=None, T=None, Tk=0):
+    a = _lib.AttnArgs()
+    a.q, a.k, a.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
+    a.ldq, a.ldk, a.ldv = q.stride(0), k.stride(0), v.stride(0)
+    a.o, a.ldo = o.data_ptr(), o.stride(0)
+    a.lse = None if lse is None else lse.data_ptr()
+    a.meta = meta.data_ptr()
+    a.T = q.shape[0] if T is None else T
+    a.Tk = Tk
+    a.n_heads, a.n_kv_heads, a.head_dim, a.scale = n_heads, n_kv_heads, head_dim, float(scale)
+    return a
+
+
+def attn_fwd(q, k, v, meta, n_heads, n_kv_heads, head_dim, scale=None, out=None, save_lse=False):
+    """q/k/v are column views into a fused projection buffer (row stride = buffer width)."""
+    T = q.shape[0]
+    _req(meta, torch.int32, "meta")
+    scale = head_dim ** -0.5 if scale is None else scale
+    o = out if out is not None else torch.empty((T, n_heads * head_dim), device=q.device, dtype=torch.bfloat16)
+    lse = torch.empty((n_heads, T), device=q.device, dtype=torch.float32) if save_lse else None
+    a = attn_args(q, k, v, o, meta, n_heads, n_kv_heads, head_dim, scale, lse)
+    check(_lib.load().sb_attn_fwd(C.byref(a), _stream()), "sb_attn_fwd")
+    return (o, lse) if save_lse else o
+
+
+def attn_bwd(q, k, v, o, lse, d_o, meta, n_heads, n_kv_heads, head_dim, dq_out, dk_out, dv_out, scale=None,
+             dq_acc=None, delta=None):
+    """dq_out/dk_out/dv_out: bf16 column views (e.g. into a d_qkv buffer)."""
+    T = q.shape[0]
+    scale = head_dim ** -0.5 if scale is None else scale
+    if dq_acc is None:
+        dq_acc = torch.empty((T, n_heads * head_dim), device=q.device, dtype=torch.float32)
+    dq_acc.zero_()
+    if delta is None:
+        delta = torch.empty((n_heads, T), device=q.device, dtype=torch.float32)
+    a = attn_args(q, k, v, o, meta, n_heads, n_kv_heads, head_dim, scale, lse)
+    a.d_o, a.lddo = d_o.data_ptr(), d_o.stride(0)
+    a.delta, a.dq_acc = delta.data_ptr(), dq_acc.data_ptr()
+    a.dk, a.dv, a.lddk, a.lddv = dk_out.data_ptr(), dv_out.data_ptr(), dk_out.stride(0), dv_out.stride(0)
+    check(_lib.load().sb_attn_bwd(C.byref(a), _stream()), "sb_attn_bwd")
+    call("sb_f32_to_bf16_2d", dq_acc, dq_out, T, n_heads * head_dim, dq_out.stride(0))
+
+
+def make_meta(prefix_len, seg_start, kv_end, device="cuda"):
+    """int32 [T,4] visibility metadata from three equal-length integer sequences/tensors."""
+    m = torch.stack([torch.as_tensor(prefix_len), torch.as_tensor(seg_start), torch.as_tensor(kv_end),
+                     torch.zeros_like(torch.as_tensor(kv_end))], dim=1).to(torch.int32)
+    return m.contiguous().to(device)
