@@ -1,0 +1,604 @@
+"""Qwen2-VL on the spacer_b200 kernels: host-side orchestration of the SG-RLVR hot path.
+
+Mirrors the surface of the object the reference trainer drives:
+    model.generate(input_ids, pixel_values_videos=..., video_grid_thw=..., generation_config-like kwargs)
+        -> LongTensor [G, P + C']                              (SG_RLVR_trainer.py:463-467)
+    model.per_token_logps(...) / model.grpo_forward_backward(...)  (TRN:353-366, 526-547, 640-643)
+    model.state_dict() / load_state_dict() with HF parameter names
+Every FLOP runs in libspacer_b200.so (tcgen05 GEMMs, flash attention, fused norms/rope/loss); torch is used
+for device memory, streams and CUDA-graph capture only.
+
+Algorithmic differences from the reference's executed path (same mathematics):
+  * the ViT and the prompt prefill run ONCE per prompt, not once per sampled copy;
+  * scoring / training run on the packed sequence [prompt | completion_0 | ... | completion_{G-1}] with the
+    prompt shared through the attention mask (every completion token sees the whole prompt + its own
+    completion causally) -- identical to G independent causal sequences because the prompt rows are
+    identical across copies and no padding mask is passed (TRN:357, Appendix B.1-2);
+  * the [.,V] logits are never materialised: lm_head -> online logsumexp -> gather in the GEMM epilogue.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import torch
+
+from . import ops
+from .config import ModelDims
+from .ops import (EPI_DLOGITS, EPI_F32T, EPI_GELU, EPI_LMHEAD, EPI_QUICKGELU, EPI_STORE, EPI_SWIGLU,
+                  SpacerError)
+from .params import ParamStore
+
+I32 = torch.int32
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+# ------------------------------------------------------------------------------------------------
+# position ids (host integer work)
+# ------------------------------------------------------------------------------------------------
+def rope_index(input_ids: torch.Tensor, grid_thw, dims: ModelDims, convention: str = "classic"):
+    """3-stream M-RoPE position ids for ONE row: int64 [3, L] and the next free position.
+
+    "classic" is the formula of the transformers release the reference was written against and the released
+    Qwen2-VL weights were trained with (per-frame raster t/h/w); "hf55" reproduces transformers 5.5.0
+    (modeling_qwen2_vl.py:934-988).  See SURVEY.md 8(c) drift #2."""
+    ids = input_ids.reshape(-1).cpu()
+    L = ids.numel()
+    is_v = (ids == dims.video_token_id) | (ids == dims.image_token_id)
+    pos = torch.zeros(3, L, dtype=torch.long)
+    nxt, i, gi = 0, 0, 0
+    grids = [list(map(int, g)) for g in (grid_thw.tolist() if torch.is_tensor(grid_thw) else grid_thw)]
+    m = dims.merge
+    isv = is_v.tolist()
+    while i < L:
+        if isv[i]:
+            t, h, w = grids[min(gi, len(grids) - 1)]
+            gi += 1
+            gh, gw = h // m, w // m
+            n = t * gh * gw
+            if convention == "classic":
+                tt = torch.arange(t).view(-1, 1).expand(-1, gh * gw).flatten()
+                hh = torch.arange(gh).view(1, -1, 1).expand(t, -1, gw).flatten()
+                ww = torch.arange(gw).view(1, 1, -1).expand(t, gh, -1).flatten()
+                blk = torch.stack([tt, hh, ww]) + nxt
+            else:
+                ww = torch.arange(nxt, nxt + gw).repeat(gh * t)
+                hh = torch.arange(nxt, nxt + gh).repeat_interleave(gw * t)
+                tt = torch.full((n,), nxt, dtype=torch.long)
+                blk = torch.stack([tt, hh, ww])
+            if i + n > L:
+                raise SpacerError("placeholder tokens do not match video_grid_thw (truncated prompt?)")
+            pos[:, i:i + n] = blk
+            nxt = int(blk.max()) + 1
+            i += n
+        else:
+            # run of text tokens
+            j = i
+            while j < L and not isv[j]:
+                j += 1
+            pos[:, i:j] = torch.arange(nxt, nxt + (j - i))
+            nxt += j - i
+            i = j
+    return pos, nxt
+
+
+def slab_meta(grid_thw, device):
+    """Attention visibility for the ViT: one block-diagonal slab per temporal index (MQ2:772-780)."""
+    starts, ends = [], []
+    base = 0
+    for t, h, w in (grid_thw.tolist() if torch.is_tensor(grid_thw) else grid_thw):
+        for _ in range(int(t)):
+            n = int(h) * int(w)
+            starts += [base] * n
+            ends += [base + n] * n
+            base += n
+    z = torch.zeros(len(starts), dtype=torch.long)
+    return ops.make_meta(z, torch.tensor(starts), torch.tensor(ends), device)
+
+
+def causal_meta(T, device):
+    t = torch.arange(T)
+    return ops.make_meta(torch.zeros(T, dtype=torch.long), torch.zeros(T, dtype=torch.long), t + 1, device)
+
+
+@dataclass
+class PackedBatch:
+    """[prompt | completion_0 | ... | completion_{G-1}] with everything the kernels need."""
+    ids: torch.Tensor          # int32 [T]
+    pos: torch.Tensor          # int32 [3, T]
+    meta: torch.Tensor         # int32 [T, 4]
+    rows: torch.Tensor         # int32 [G*C]: hidden row that predicts completion token (g, c)
+    targets: torch.Tensor      # int32 [G*C]
+    comp_ids: torch.Tensor     # int32 [G, C]
+    P: int
+    G: int
+    C: int
+
+
+def pack_prompt_completions(prompt_ids, completion_ids, grid_thw, dims: ModelDims, device, convention="classic"):
+    prompt_ids = prompt_ids.reshape(-1).cpu().long()
+    comp = completion_ids.cpu().long()
+    P, (G, C) = prompt_ids.numel(), comp.shape
+    ppos, nxt = rope_index(prompt_ids, grid_thw, dims, convention)
+    cpos = (torch.arange(C) + nxt).repeat(G)
+    pos = torch.cat([ppos, cpos[None].expand(3, -1)], dim=1)
+    ids = torch.cat([prompt_ids, comp.reshape(-1)])
+    T = P + G * C
+    t = torch.arange(T)
+    seg = torch.where(t < P, torch.zeros_like(t), P + ((t - P) // C) * C)
+    pre = torch.where(t < P, torch.zeros_like(t), torch.full_like(t, P))
+    meta = ops.make_meta(pre, seg, t + 1, device)
+    starts = P + torch.arange(G) * C
+    rows = torch.cat([torch.full((G, 1), P - 1), starts[:, None] + torch.arange(C - 1)[None]], dim=1).reshape(-1)
+    return PackedBatch(ids=ids.to(I32).to(device), pos=pos.to(I32).contiguous().to(device), meta=meta,
+                       rows=rows.to(I32).to(device), targets=comp.reshape(-1).to(I32).to(device),
+                       comp_ids=comp.to(I32).contiguous().to(device), P=P, G=G, C=C)
+
+
+class GradStore:
+    """Gradient arenas: bf16 for matrices (written by GEMM epilogues), fp32 for norm weights / biases."""
+
+    def __init__(self, params: ParamStore):
+        self.params = params
+        self.mat = torch.zeros(params.sizes["mat"], device=params.device, dtype=BF16)
+        self.vec = torch.zeros(params.sizes["vec"], device=params.device, dtype=F32)
+        self.views = {n: params.view_of(n, self.mat, self.vec) for n in params.index}
+
+    def __getitem__(self, name):
+        if name == "lm_head" and self.params.dims.tie:
+            name = "embed"
+        return self.views[name]
+
+    def zero_for_step(self):
+        """Only accumulating destinations need zeroing: the fp32 vector arena and the embedding table."""
+        self.vec.zero_()
+        self.views["embed"].zero_()
+
+
+class Qwen2VLB200:
+    def __init__(self, dims: ModelDims, device="cuda", params: ParamStore | None = None,
+                 rope_convention: str = "classic"):
+        if not torch.cuda.is_available():
+            raise SpacerError("spacer_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        ops._lib.load()
+        self.dims = dims
+        self.device = torch.device(device)
+        self.params = params if params is not None else ParamStore(dims, device)
+        self.rope_convention = rope_convention
+        self.training = False
+        self._dec = None
+
+    # ---- HF-like surface -------------------------------------------------------------------------
+    def state_dict(self):
+        return self.params.state_dict()
+
+    def load_state_dict(self, sd, strict=True):
+        self.params.load_state_dict(sd)
+        return self
+
+    def train(self, mode=True):
+        self.training = mode
+        return self
+
+    def eval(self):
+        return self.train(False)
+
+    def parameters(self):
+        return [self.params.mat, self.params.vec]
+
+    # ---- vision tower ----------------------------------------------------------------------------
+    def vit_forward(self, pixel_values, grid_thw, tape: dict | None = None):
+        """Qwen2VisionTransformerPretrainedModel.forward (MQ2:757-795).  pixel_values [N_p, 1176] fp32/bf16."""
+        d, W = self.dims, self.params
+        grid_list = grid_thw.tolist() if torch.is_tensor(grid_thw) else grid_thw
+        pix = pixel_values if pixel_values.dtype == BF16 else ops.cast_f32_bf16(pixel_values.contiguous())
+        T = pix.shape[0]
+        if T != sum(int(t) * int(h) * int(w) for t, h, w in grid_list):
+            raise SpacerError("pixel_values rows do not match video_grid_thw")
+        grids_dev = torch.tensor(grid_list, dtype=I32, device=self.device)
+        meta = slab_meta(grid_list, self.device)
+        E, nh, hd = d.v_embed, d.v_heads, d.v_head_dim
+        x = ops.gemm(pix, W["v.patch_w"])
+        save = tape is not None
+        if save:
+            tape.update(pix=pix, grids=grids_dev, meta=meta, blocks=[])
+        for i in range(d.v_depth):
+            p = f"v.{i}."
+            r1 = ops.layernorm_fwd(x, W[p + "ln1_w"], W[p + "ln1_b"], save_stats=save)
+            h = r1[0] if save else r1
+            qkv = ops.gemm(h, W[p + "qkv_w"], bias=W[p + "qkv_b"])
+            ops.rope_vit(qkv, nh, hd, grids_dev, d.merge)
+            r2 = ops.attn_fwd(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], meta, nh, nh, hd, save_lse=save)
+            a = r2[0] if save else r2
+            x2 = ops.gemm(a, W[p + "proj_w"], bias=W[p + "proj_b"], residual=x)
+            r3 = ops.layernorm_fwd(x2, W[p + "ln2_w"], W[p + "ln2_b"], save_stats=save, out=h)
+            z = torch.empty((T, d.v_mlp), device=self.device, dtype=BF16) if save else None
+            f = ops.gemm(r3[0] if save else r3, W[p + "fc1_w"], bias=W[p + "fc1_b"], epilogue=EPI_QUICKGELU, aux=z)
+            x3 = ops.gemm(f, W[p + "fc2_w"], bias=W[p + "fc2_b"], residual=x2)
+            if save:
+                tape["blocks"].append(dict(x=x, m1=r1[1], s1=r1[2], qkv=qkv, a=a, lse=r2[1], x2=x2, m2=r3[1], s2=r3[2], z=z))
+            x = x3
+        rm = ops.layernorm_fwd(x, W["v.m.ln_w"], W["v.m.ln_b"], save_stats=save)
+        hm = (rm[0] if save else rm).view(T // (d.merge * d.merge), d.merge_dim)
+        zm = torch.empty_like(hm) if save else None
+        fm = ops.gemm(hm, W["v.m.fc0_w"], bias=W["v.m.fc0_b"], epilogue=EPI_GELU, aux=zm)
+        out = ops.gemm(fm, W["v.m.fc2_w"], bias=W["v.m.fc2_b"])
+        if save:
+            tape.update(x_last=x, mm=rm[1], sm=rm[2], zm=zm)
+        return out
+
+    def vit_backward(self, tape: dict, d_out, grads: GradStore):
+        d, W, G = self.dims, self.params, grads
+        E, nh, hd = d.v_embed, d.v_heads, d.v_head_dim
+        T = tape["pix"].shape[0]
+        mode_q, mode_g = 0, 1
+        # merger
+        fm = torch.empty_like(tape["zm"])
+        ops.call("sb_act_fwd", tape["zm"], fm, fm.numel(), mode_g)
+        ops.gemm(d_out, fm, a_mn=True, b_mn=True, out=G["v.m.fc2_w"])
+        ops.call("sb_colsum", d_out, G["v.m.fc2_b"], d_out.shape[0], d_out.shape[1], d_out.stride(0))
+        d_fm = ops.gemm(d_out, W["v.m.fc2_w"], b_mn=True)
+        d_zm = fm  # reuse
+        ops.call("sb_act_bwd", tape["zm"], d_fm, d_zm, d_zm.numel(), mode_g)
+        hm = ops.layernorm_fwd(tape["x_last"], W["v.m.ln_w"], W["v.m.ln_b"]).view(-1, d.merge_dim)
+        ops.gemm(d_zm, hm, a_mn=True, b_mn=True, out=G["v.m.fc0_w"])
+        ops.call("sb_colsum", d_zm, G["v.m.fc0_b"], d_zm.shape[0], d_zm.shape[1], d_zm.stride(0))
+        d_hm = ops.gemm(d_zm, W["v.m.fc0_w"], b_mn=True).view(T, E)
+        dx = ops.layernorm_bwd(tape["x_last"], W["v.m.ln_w"], tape["mm"], tape["sm"], d_hm, G["v.m.ln_w"], G["v.m.ln_b"])
+        del fm, d_fm, d_zm, hm, d_hm
+        for i in reversed(range(d.v_depth)):
+            p = f"v.{i}."
+            t = tape["blocks"][i]
+            f = torch.empty_like(t["z"])
+            ops.call("sb_act_fwd", t["z"], f, f.numel(), mode_q)
+            ops.gemm(dx, f, a_mn=True, b_mn=True, out=G[p + "fc2_w"])
+            ops.call("sb_colsum", dx, G[p + "fc2_b"], T, E, E)
+            d_f = ops.gemm(dx, W[p + "fc2_w"], b_mn=True)
+            d_z = f
+            ops.call("sb_act_bwd", t["z"], d_f, d_z, d_z.numel(), mode_q)
+            h2 = ops.layernorm_fwd(t["x2"], W[p + "ln2_w"], W[p + "ln2_b"])
+            ops.gemm(d_z, h2, a_mn=True, b_mn=True, out=G[p + "fc1_w"])
+            ops.call("sb_colsum", d_z, G[p + "fc1_b"], T, d.v_mlp, d.v_mlp)
+            d_h2 = ops.gemm(d_z, W[p + "fc1_w"], b_mn=True, out=h2)
+            dx2 = ops.layernorm_bwd(t["x2"], W[p + "ln2_w"], t["m2"], t["s2"], d_h2, G[p + "ln2_w"], G[p + "ln2_b"], dres=dx)
+            ops.gemm(dx2, t["a"], a_mn=True, b_mn=True, out=G[p + "proj_w"])
+            ops.call("sb_colsum", dx2, G[p + "proj_b"], T, E, E)
+            d_a = ops.gemm(dx2, W[p + "proj_w"], b_mn=True)
+            qkv = t["qkv"]
+            d_qkv = torch.empty_like(qkv)
+            ops.attn_bwd(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], t["a"], t["lse"], d_a, tape["meta"], nh, nh, hd,
+                         d_qkv[:, :E], d_qkv[:, E:2 * E], d_qkv[:, 2 * E:])
+            ops.rope_vit(d_qkv, nh, hd, tape["grids"], d.merge, inverse=True)
+            h = ops.layernorm_fwd(t["x"], W[p + "ln1_w"], W[p + "ln1_b"])
+            ops.gemm(d_qkv, h, a_mn=True, b_mn=True, out=G[p + "qkv_w"])
+            ops.call("sb_colsum", d_qkv, G[p + "qkv_b"], T, 3 * E, 3 * E)
+            d_h = ops.gemm(d_qkv, W[p + "qkv_w"], b_mn=True, out=h)
+            dx = ops.layernorm_bwd(t["x"], W[p + "ln1_w"], t["m1"], t["s1"], d_h, G[p + "ln1_w"], G[p + "ln1_b"], dres=dx2)
+            tape["blocks"][i] = None
+        ops.gemm(dx, tape["pix"], a_mn=True, b_mn=True, out=G["v.patch_w"])
+
+    # ---- language model --------------------------------------------------------------------------
+    def llm_forward(self, ids, vis, pos, meta, tape: dict | None = None, kv_out=None):
+        """Qwen2VLTextModel.forward on a packed token sequence (MQ2:597-662, 905).
+        ids int32 [T]; vis bf16 [N_v, H] or None; pos int32 [3, T]; meta int32 [T, 4].
+        kv_out: optional list (per layer) of (k_cache, v_cache) bf16 [T, nkv*hd] filled with rotated K and V."""
+        d, W = self.dims, self.params
+        T, H = ids.shape[0], d.hidden
+        nh, nkv, hd = d.heads, d.kv_heads, d.head_dim
+        nq, nk = nh * hd, nkv * hd
+        save = tape is not None
+        vis_idx = None
+        n_vis = 0
+        if vis is not None:
+            vis_idx = torch.empty(T, dtype=I32, device=self.device)
+            cnt = torch.zeros(1, dtype=I32, device=self.device)
+            ops.call("sb_vision_index", ids, vis_idx, T, d.video_token_id, d.image_token_id, cnt)
+            n_vis = vis.shape[0]
+        x = torch.empty((T, H), device=self.device, dtype=BF16)
+        ops.call("sb_embed_merge", ids, vis_idx, W["embed"], vis, x, T, H, n_vis)
+        if save:
+            tape.update(ids=ids, vis_idx=vis_idx, n_vis=n_vis, pos=pos, meta=meta, layers=[])
+        h = torch.empty_like(x)
+        for i in range(d.layers):
+            p = f"l.{i}."
+            r1 = ops.rmsnorm_fwd(x, W[p + "ln1_w"], d.rms_eps, save_stats=save, out=h)
+            qkv = ops.gemm(h, W[p + "qkv_w"], bias=W[p + "qkv_b"])
+            ko, vo = kv_out[i] if kv_out is not None else (None, None)
+            ops.mrope(qkv, pos, nh, nkv, hd, d.rope_theta, d.mrope_section, k_out=ko, v_out=vo, kv_ld=nk)
+            r2 = ops.attn_fwd(qkv[:, :nq], qkv[:, nq:nq + nk], qkv[:, nq + nk:], meta, nh, nkv, hd, save_lse=save)
+            a = r2[0] if save else r2
+            x2 = ops.gemm(a, W[p + "o_w"], residual=x)
+            r3 = ops.rmsnorm_fwd(x2, W[p + "ln2_w"], d.rms_eps, save_stats=save, out=h)
+            gu = torch.empty((T, 2 * d.inter), device=self.device, dtype=BF16) if save else None
+            act = ops.gemm(h, W[p + "gu_w"], epilogue=EPI_SWIGLU, aux=gu)
+            x3 = ops.gemm(act, W[p + "down_w"], residual=x2)
+            if save:
+                tape["layers"].append(dict(x=x, s1=r1[1], qkv=qkv, a=a, lse=r2[1], x2=x2, s2=r3[1], gu=gu))
+            x = x3
+            del act
+        rf = ops.rmsnorm_fwd(x, W["norm_w"], d.rms_eps, save_stats=save)
+        if save:
+            tape.update(x_last=x, sf=rf[1])
+            return rf[0]
+        return rf
+
+    def llm_backward(self, tape: dict, d_hf, grads: GradStore, want_d_vis=True):
+        d, W, G = self.dims, self.params, grads
+        T, H, I = tape["ids"].shape[0], d.hidden, d.inter
+        nh, nkv, hd = d.heads, d.kv_heads, d.head_dim
+        nq, nk = nh * hd, nkv * hd
+        dx = ops.rmsnorm_bwd(tape["x_last"], W["norm_w"], tape["sf"], d_hf, G["norm_w"])
+        d_act = torch.empty((T, I), device=self.device, dtype=BF16)
+        d_gu = torch.empty((T, 2 * I), device=self.device, dtype=BF16)
+        act = torch.empty((T, I), device=self.device, dtype=BF16)
+        h = torch.empty((T, H), device=self.device, dtype=BF16)
+        d_h = torch.empty((T, H), device=self.device, dtype=BF16)
+        d_a = torch.empty((T, nq), device=self.device, dtype=BF16)
+        d_qkv = torch.empty((T, d.qkv_dim), device=self.device, dtype=BF16)
+        dq_acc = torch.empty((T, nq), device=self.device, dtype=F32)
+        delta = torch.empty((nh, T), device=self.device, dtype=F32)
+        for i in reversed(range(d.layers)):
+            p = f"l.{i}."
+            t = tape["layers"][i]
+            ops.gemm(dx, W[p + "down_w"], b_mn=True, out=d_act)
+            ops.call("sb_swiglu_bwd", t["gu"], d_act, d_gu, act, T, I)
+            ops.gemm(dx, act, a_mn=True, b_mn=True, out=G[p + "down_w"])
+            ops.rmsnorm_fwd(t["x2"], W[p + "ln2_w"], d.rms_eps, out=h)
+            ops.gemm(d_gu, h, a_mn=True, b_mn=True, out=G[p + "gu_w"])
+            ops.gemm(d_gu, W[p + "gu_w"], b_mn=True, out=d_h)
+            dx2 = ops.rmsnorm_bwd(t["x2"], W[p + "ln2_w"], t["s2"], d_h, G[p + "ln2_w"], dres=dx)
+            ops.gemm(dx2, W[p + "o_w"], b_mn=True, out=d_a)
+            ops.gemm(dx2, t["a"], a_mn=True, b_mn=True, out=G[p + "o_w"])
+            qkv = t["qkv"]
+            ops.attn_bwd(qkv[:, :nq], qkv[:, nq:nq + nk], qkv[:, nq + nk:], t["a"], t["lse"], d_a, tape["meta"], nh, nkv,
+                         hd, d_qkv[:, :nq], d_qkv[:, nq:nq + nk], d_qkv[:, nq + nk:], dq_acc=dq_acc, delta=delta)
+            ops.mrope(d_qkv, tape["pos"], nh, nkv, hd, d.rope_theta, d.mrope_section, inverse=True)
+            ops.call("sb_colsum", d_qkv, G[p + "qkv_b"], T, d.qkv_dim, d.qkv_dim)
+            ops.rmsnorm_fwd(t["x"], W[p + "ln1_w"], d.rms_eps, out=h)
+            ops.gemm(d_qkv, h, a_mn=True, b_mn=True, out=G[p + "qkv_w"])
+            ops.gemm(d_qkv, W[p + "qkv_w"], b_mn=True, out=d_h)
+            dx = ops.rmsnorm_bwd(t["x"], W[p + "ln1_w"], t["s1"], d_h, G[p + "ln1_w"], dres=dx2)
+            tape["layers"][i] = None
+            del dx2
+        d_vis = None
+        if tape["n_vis"] > 0 and want_d_vis:
+            d_vis = torch.zeros((tape["n_vis"], H), device=self.device, dtype=BF16)
+        ops.call("sb_embed_bwd", tape["ids"], tape["vis_idx"], dx, G["embed"], d_vis, T, H, tape["n_vis"])
+        return d_vis
+
+    # ---- scoring -----------------------------------------------------------------------------------
+    def _lmhead_partials(self, hsel, targets):
+        d = self.dims
+        R = hsel.shape[0]
+        nt = (d.vocab + 255) // 256
+        part = torch.empty((R, nt, 2), device=self.device, dtype=F32)
+        tl = torch.zeros(R, device=self.device, dtype=F32)
+        ops.gemm(hsel, self.params["lm_head"], epilogue=EPI_LMHEAD, targets=targets, lse_part=part, tgt_logit=tl)
+        return part, tl, nt
+
+    @torch.no_grad()
+    def per_token_logps(self, batch: PackedBatch, pixel_values, grid_thw):
+        """[G, C] log-probs of the completion tokens (the slice `[:, P-1:]` of TRN:353-366, 526-528)."""
+        vis = self.vit_forward(pixel_values, grid_thw) if pixel_values is not None else None
+        hf = self.llm_forward(batch.ids, vis, batch.pos, batch.meta)
+        R = batch.rows.shape[0]
+        hsel = torch.empty((R, self.dims.hidden), device=self.device, dtype=BF16)
+        ops.call("sb_gather_rows", hf, batch.rows, hsel, R, self.dims.hidden)
+        part, tl, nt = self._lmhead_partials(hsel, batch.targets)
+        lp = torch.empty(R, device=self.device, dtype=F32)
+        ops.call("sb_logprob_from_partials", part, nt, tl, lp, R)
+        return lp.view(batch.G, batch.C)
+
+    def grpo_forward_backward(self, batch: PackedBatch, pixel_values, grid_thw, ref_logps, advantages, beta,
+                              grads: GradStore, lm_chunk: int = 4096):
+        """One GRPO forward/backward (TRN:526-528, 551-552, 640-643 + autograd's backward).
+        Returns dict(loss, mean_kl, logps [G,C], mask [G,C], lengths [G]); gradients land in `grads`."""
+        d = self.dims
+        H = d.hidden
+        G_, C = batch.G, batch.C
+        R = G_ * C
+        vtape, ltape = {}, {}
+        vis = self.vit_forward(pixel_values, grid_thw, vtape) if pixel_values is not None else None
+        hf = self.llm_forward(batch.ids, vis, batch.pos, batch.meta, ltape)
+        hsel = torch.empty((R, H), device=self.device, dtype=BF16)
+        ops.call("sb_gather_rows", hf, batch.rows, hsel, R, H)
+        part, tl, nt = self._lmhead_partials(hsel, batch.targets)
+        lp = torch.empty(R, device=self.device, dtype=F32)
+        lse = torch.empty(R, device=self.device, dtype=F32)
+        coef = torch.empty(R, device=self.device, dtype=F32)
+        mask = torch.empty(R, device=self.device, dtype=I32)
+        row_loss = torch.empty(G_, device=self.device, dtype=F32)
+        row_kl = torch.empty(G_, device=self.device, dtype=F32)
+        row_len = torch.empty(G_, device=self.device, dtype=I32)
+        out2 = torch.empty(2, device=self.device, dtype=F32)
+        adv = advantages.to(self.device, F32).contiguous()
+        ref = None if ref_logps is None else ref_logps.to(self.device, F32).contiguous()
+        ops.call("sb_grpo_loss", part, nt, tl, batch.comp_ids, G_, C, d.eos_id, ref, adv, float(beta), lp, lse, coef,
+                 mask, row_loss, row_kl, row_len, out2)
+        del part
+        # backward through lm_head: recompute logits tile by tile, emit dlogits, two GEMMs
+        grads.zero_for_step()
+        d_hsel = torch.empty((R, H), device=self.device, dtype=BF16)
+        g_lm = grads["lm_head"]
+        first = True
+        for r0 in range(0, R, lm_chunk):
+            r1 = min(r0 + lm_chunk, R)
+            dl = ops.gemm(hsel[r0:r1], self.params["lm_head"], epilogue=EPI_DLOGITS, targets=batch.targets[r0:r1],
+                          lse=lse[r0:r1], coef=coef[r0:r1])
+            ops.gemm(dl, self.params["lm_head"], b_mn=True, out=d_hsel[r0:r1])
+            ops.gemm(dl, hsel[r0:r1], a_mn=True, b_mn=True, out=g_lm, residual=None if (first and not d.tie) else g_lm)
+            first = False
+            del dl
+        d_hf = torch.zeros_like(hf)
+        ops.call("sb_scatter_add_rows", d_hsel, batch.rows, d_hf, R, H)
+        del hsel, d_hsel, hf
+        d_vis = self.llm_backward(ltape, d_hf, grads)
+        del ltape, d_hf
+        if vis is not None:
+            self.vit_backward(vtape, d_vis, grads)
+        return dict(loss=out2[0], mean_kl=out2[1], logps=lp.view(G_, C), mask=mask.view(G_, C), lengths=row_len)
+
+    # ---- rollout -----------------------------------------------------------------------------------
+    def _gemv(self, w, x16, out_parts, splits):
+        """parts[s][r][n] = x16[r] . w[n] over K split s   (swap-AB tcgen05 GEMM, weights streamed once)."""
+        ops.gemm(w, x16, out=out_parts, epilogue=EPI_F32T, k_splits=splits)
+
+    def _splits_for(self, n_out, k):
+        m_tiles = (n_out + 127) // 128
+        if m_tiles >= 148:
+            return 1
+        s = max(1, 148 // m_tiles)
+        return min(s, max(1, (k + 63) // 64))
+
+    def _alloc_decode(self, R, P, c_max, n_prompts):
+        d, dev = self.dims, self.device
+        H, I, nk = d.hidden, d.inter, d.kv_heads * d.head_dim
+        RP = 16 if R <= 16 else 32
+        lib = ops._lib.load()
+        S = {}
+        for name, (n_out, k) in dict(qkv=(d.qkv_dim, H), o=(H, d.heads * d.head_dim), gu=(2 * I, H), down=(H, I),
+                                     lm=(d.vocab, H)).items():
+            S[name] = 1 if name == "lm" else lib.sb_gemm_effective_splits(k, self._splits_for(n_out, k))
+        st = dict(
+            R=R, RP=RP, P=P, c_max=c_max, S=S,
+            x=torch.zeros((RP, H), device=dev, dtype=BF16), xn=torch.zeros((RP, H), device=dev, dtype=BF16),
+            q=torch.zeros((RP, d.heads * d.head_dim), device=dev, dtype=BF16),
+            attn=torch.zeros((RP, d.heads * d.head_dim), device=dev, dtype=BF16),
+            act=torch.zeros((RP, I), device=dev, dtype=BF16),
+            p_qkv=torch.empty((S["qkv"], RP, d.qkv_dim), device=dev, dtype=F32),
+            p_o=torch.empty((S["o"], RP, H), device=dev, dtype=F32),
+            p_gu=torch.empty((S["gu"], RP, 2 * I), device=dev, dtype=F32),
+            p_down=torch.empty((S["down"], RP, H), device=dev, dtype=F32),
+            logits=torch.empty((S["lm"], RP, d.vocab), device=dev, dtype=F32),
+            kc=torch.zeros((d.layers, R, c_max, nk), device=dev, dtype=BF16),
+            vc=torch.zeros((d.layers, R, c_max, nk), device=dev, dtype=BF16),
+            kp=[torch.empty((d.layers, P, nk), device=dev, dtype=BF16) for _ in range(n_prompts)],
+            vp=[torch.empty((d.layers, P, nk), device=dev, dtype=BF16) for _ in range(n_prompts)],
+            step=torch.zeros(1, device=dev, dtype=I32), tokens=torch.zeros(RP, device=dev, dtype=I32),
+            finished=torch.zeros(RP, device=dev, dtype=I32),
+            out_ids=torch.zeros((R, c_max), device=dev, dtype=I32),
+            n_split=4,
+        )
+        rep = d.heads // d.kv_heads
+        st["o_part"] = torch.empty((R, d.kv_heads, st["n_split"], rep, d.head_dim), device=dev, dtype=F32)
+        st["ml_part"] = torch.empty((R, d.kv_heads, st["n_split"], rep, 2), device=dev, dtype=F32)
+        return st
+
+    def _decode_step(self, st, rope_base, rows_group0, top_p, seed, suppress_eos):
+        """Enqueue one decode step (feeds tokens at slot *step, samples the next token into slot *step + 1)."""
+        d, W = self.dims, self.params
+        R, RP, P, S = st["R"], st["RP"], st["P"], st["S"]
+        H, I = d.hidden, d.inter
+        nh, nkv, hd = d.heads, d.kv_heads, d.head_dim
+        ops.call("sb_dec_embed", st["tokens"], W["embed"], st["x"], R, H)
+        parts, sp = None, 0
+        for i in range(d.layers):
+            p = f"l.{i}."
+            ops.call("sb_dec_residual_rmsnorm", st["x"], parts, sp, RP * H, H, W[p + "ln1_w"], st["xn"], R, H, d.rms_eps)
+            self._gemv(W[p + "qkv_w"], st["xn"], st["p_qkv"], S["qkv"])
+            ops.call("sb_dec_qkv_post", st["p_qkv"], S["qkv"], RP * d.qkv_dim, d.qkv_dim, W[p + "qkv_b"], st["step"],
+                     rope_base, float(d.rope_theta), nh, nkv, hd, st["q"], st["kc"][i], st["vc"][i],
+                     st["c_max"] * nkv * hd, st["c_max"], R)
+            kp1 = st["kp"][1][i] if len(st["kp"]) > 1 else None
+            vp1 = st["vp"][1][i] if len(st["vp"]) > 1 else None
+            ops.call("sb_dec_attn", st["q"], st["kp"][0][i], st["vp"][0][i], kp1, vp1, rows_group0, P, st["kc"][i],
+                     st["vc"][i], st["c_max"] * nkv * hd, st["step"], nh, nkv, hd, hd ** -0.5, st["n_split"],
+                     st["o_part"], st["ml_part"], st["attn"], R)
+            self._gemv(W[p + "o_w"], st["attn"], st["p_o"], S["o"])
+            ops.call("sb_dec_residual_rmsnorm", st["x"], st["p_o"], S["o"], RP * H, H, W[p + "ln2_w"], st["xn"], R, H,
+                     d.rms_eps)
+            self._gemv(W[p + "gu_w"], st["xn"], st["p_gu"], S["gu"])
+            ops.call("sb_dec_swiglu", st["p_gu"], S["gu"], RP * 2 * I, 2 * I, st["act"], R, I)
+            self._gemv(W[p + "down_w"], st["act"], st["p_down"], S["down"])
+            parts, sp = st["p_down"], S["down"]
+        ops.call("sb_dec_residual_rmsnorm", st["x"], parts, sp, RP * H, H, W["norm_w"], st["xn"], R, H, d.rms_eps)
+        self._gemv(W["lm_head"], st["xn"], st["logits"], 1)
+        ops.call("sb_step_advance", st["step"])
+        ops.call("sb_sample_top_p", st["logits"], d.vocab, R, d.vocab, float(top_p), int(seed), st["step"],
+                 st["finished"], st["tokens"], st["out_ids"], st["c_max"], None, d.eos_id, d.pad_id, int(suppress_eos))
+
+    @torch.no_grad()
+    def generate(self, input_ids, pixel_values_videos=None, video_grid_thw=None, *, max_new_tokens=1024,
+                 num_return_sequences=1, top_p=0.95, temperature=1.0, do_sample=True, seed=0, min_new_tokens=0,
+                 pixel_values_videos_2=None, num_return_sequences_2=0, use_graph=True, attention_mask=None,
+                 return_stats=False, **unused):
+        """Sampled rollout: `num_return_sequences` completions of ONE prompt (TRN:463-467; generate() with
+        do_sample, top_p, temperature 1).  Returns LongTensor [G, P + C'] (prompt echoed, finished rows padded).
+
+        `pixel_values_videos_2` / `num_return_sequences_2` add a second group decoded in the same batch from
+        the same text with another video (T-GRPO's frame-shuffled rollout, TRN:442-458, 469-475); the result is
+        then a tuple (ids_main, ids_second)."""
+        d = self.dims
+        if not do_sample or temperature != 1.0:
+            raise SpacerError("generate: only do_sample=True with temperature 1 (the reference's configuration)")
+        if min_new_tokens not in (0, max_new_tokens):
+            raise SpacerError("generate: min_new_tokens must be 0 or max_new_tokens")
+        ids = input_ids.reshape(-1)
+        P = ids.numel()
+        G1, G2 = int(num_return_sequences), int(num_return_sequences_2 if pixel_values_videos_2 is not None else 0)
+        R = G1 + G2
+        if R > 32:
+            raise SpacerError("generate: at most 32 rows per prompt")
+        ids_dev = ids.to(self.device, I32)
+        pos, nxt = rope_index(ids, video_grid_thw, d, self.rope_convention)
+        pos_dev = pos.to(I32).contiguous().to(self.device)
+        meta = causal_meta(P, self.device)
+        pixel_sets = [pixel_values_videos] + ([pixel_values_videos_2] if G2 > 0 else [])
+        st = self._alloc_decode(R, P, max_new_tokens, len(pixel_sets))
+        H = d.hidden
+        last_h = []
+        for k, pix in enumerate(pixel_sets):
+            vis = self.vit_forward(pix, video_grid_thw) if pix is not None else None
+            kv = [(st["kp"][k][i], st["vp"][k][i]) for i in range(d.layers)]
+            hf = self.llm_forward(ids_dev, vis, pos_dev, meta, kv_out=kv)
+            last_h.append(hf[P - 1])
+            del hf, vis
+        # first token: same distribution for every row of a group, independent draws
+        for r in range(R):
+            st["xn"][r].copy_(last_h[0] if r < G1 else last_h[1])
+        self._gemv(self.params["lm_head"], st["xn"], st["logits"], 1)
+        suppress = min_new_tokens > 0
+        ops.call("sb_sample_top_p", st["logits"], d.vocab, R, d.vocab, float(top_p), int(seed), st["step"],
+                 st["finished"], st["tokens"], st["out_ids"], st["c_max"], None, d.eos_id, d.pad_id, int(suppress))
+        n_steps = max_new_tokens - 1
+        graph = None
+        if n_steps > 0:
+            if use_graph:
+                # warm-up step outside capture (first-call attribute setup), then rewind the state it touched
+                snap = (st["step"].clone(), st["tokens"].clone(), st["finished"].clone(), st["out_ids"].clone())
+                self._decode_step(st, nxt, G1, top_p, seed, suppress)
+                torch.cuda.synchronize()
+                st["step"].copy_(snap[0]); st["tokens"].copy_(snap[1]); st["finished"].copy_(snap[2]); st["out_ids"].copy_(snap[3])
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self._decode_step(st, nxt, G1, top_p, seed, suppress)
+            done = 0
+            while done < n_steps:
+                burst = min(32, n_steps - done)
+                for _ in range(burst):
+                    if graph is not None:
+                        graph.replay()
+                    else:
+                        self._decode_step(st, nxt, G1, top_p, seed, suppress)
+                done += burst
+                if not suppress and done < n_steps and bool(st["finished"][:R].all().item()):
+                    break
+        out = st["out_ids"].long()
+        if not suppress:
+            is_eos = out == d.eos_id
+            first = torch.where(is_eos.any(1), is_eos.int().argmax(1), torch.full((R,), out.shape[1] - 1, device=self.device))
+            width = int(first.max().item()) + 1
+            width = min(width, int(st["step"].item()) + 1)
+            out = out[:, :width]
+            # rows that finished early are padded (generation/utils.py:2797)
+            col = torch.arange(width, device=self.device)[None]
+            out = torch.where(col > first[:, None], torch.full_like(out, d.pad_id), out)
+        prompt = ids.to(self.device).long()[None]
+        res1 = torch.cat([prompt.expand(G1, -1), out[:G1]], dim=1)
+        stats = dict(decode_steps=int(st["step"].item()), rows=R)
+        self._last_decode_state = st   # kept for the parity tests (logits of the final step)
+        if G2 > 0:
+            res2 = torch.cat([prompt.expand(G2, -1), out[G1:]], dim=1)
+            return (res1, res2, stats) if return_stats else (res1, res2)
+        return (res1, stats) if return_stats else res1

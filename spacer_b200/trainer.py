@@ -1,0 +1,262 @@
+"""GRPO step of SG-RLVR on the spacer_b200 engine -- host-side mirror of `SGRLVRTrainer.compute_loss`
+(/root/reference/SpaceR-SG-RLVR/src/r1-v/src/open_r1/trainer/SG_RLVR_trainer.py:384-686, "TRN") plus the
+`training_step` tail HF `Trainer` adds around it (backward, clip, AdamW, cosine LR).
+
+Same step order, constants and metric names as the reference; the compute underneath is the CUDA library.
+Deviations (all documented in DESIGN.md): the scoring-forward exception fallback of TRN:529-547 is not
+reproduced (errors raise); tensors are created on the model's device instead of a hard-coded 'cuda'.
+"""
+from __future__ import annotations
+
+import math
+from collections import defaultdict
+from dataclasses import dataclass
+from typing import Callable, Sequence
+
+import torch
+
+from . import ops
+from .model import GradStore, Qwen2VLB200, pack_prompt_completions
+from .params import ParamStore
+
+# hard-coded constants of the reference, named
+TOP_P = 0.95                 # TRN:277-284
+KL_CLAMP = 10.0              # TRN:551 (inside the fused loss kernel)
+TEMPORAL_RATIO = 0.8         # TRN:604
+TEMPORAL_BONUS = 0.3         # TRN:606
+ACC_THRESHOLD = 0.1          # TRN:605, 622
+LEN_WINDOW = (320, 512)      # TRN:628
+LEN_BONUS = 0.2              # TRN:629
+STD_EPS = 1e-4               # TRN:638
+
+
+@dataclass
+class GRPOConfig:
+    """The subset of trl.GRPOConfig / GRPOScriptArguments the hot path reads (run_SpaceR_SG_RLVR.sh:16-39)."""
+    num_generations: int = 8
+    max_prompt_length: int = 16384
+    max_completion_length: int = 1024
+    beta: float = 0.04
+    temporal: bool = True
+    len_control: bool = True
+    learning_rate: float = 1e-6
+    weight_decay: float = 0.01
+    adam_beta1: float = 0.9
+    adam_beta2: float = 0.999
+    adam_eps: float = 1e-8
+    max_grad_norm: float = 5.0
+    lr_scheduler_type: str = "cosine"
+    max_steps: int = 1000
+    warmup_steps: int = 0
+    seed: int = 42
+    moments_bf16: bool = False      # fp32 moments like DeepSpeed unless memory forces otherwise
+    min_new_tokens: int = 0         # = max_completion_length disables EOS (timing runs)
+
+
+class AdamW:
+    """AdamW over the flat arenas with fp32 master weights + global-norm clip (zero3.json:10-12 semantics)."""
+
+    def __init__(self, params: ParamStore, cfg: GRPOConfig):
+        self.p, self.cfg = params, cfg
+        mdt = torch.bfloat16 if cfg.moments_bf16 else torch.float32
+        dev = params.device
+        self.master = [torch.empty(params.sizes[k], device=dev, dtype=torch.float32) for k in ("mat", "vec")]
+        ops.call("sb_bf16_to_f32", params.mat, self.master[0], params.mat.numel())
+        ops.call("sb_bf16_to_f32", params.vec, self.master[1], params.vec.numel())
+        self.m = [torch.zeros(params.sizes[k], device=dev, dtype=mdt) for k in ("mat", "vec")]
+        self.v = [torch.zeros(params.sizes[k], device=dev, dtype=mdt) for k in ("mat", "vec")]
+        self.total_sq = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.t = 0
+
+    def lr_at(self, step: int) -> float:
+        c = self.cfg
+        if step < c.warmup_steps:
+            return c.learning_rate * step / max(1, c.warmup_steps)
+        if c.lr_scheduler_type == "cosine":
+            prog = (step - c.warmup_steps) / max(1, c.max_steps - c.warmup_steps)
+            return c.learning_rate * max(0.0, 0.5 * (1.0 + math.cos(math.pi * min(1.0, prog))))
+        return c.learning_rate
+
+    def grad_sumsq(self, grads: GradStore):
+        self.total_sq.zero_()
+        ops.call("sb_grad_sumsq", grads.mat, grads.mat.numel(), 0, self.total_sq)
+        ops.call("sb_grad_sumsq", grads.vec, grads.vec.numel(), 1, self.total_sq)
+        return self.total_sq
+
+    def step(self, grads: GradStore, grad_scale: float = 1.0, sumsq_ready: bool = False):
+        c = self.cfg
+        if not sumsq_ready:
+            self.grad_sumsq(grads)
+        lr = self.lr_at(self.t)
+        self.t += 1
+        mb = int(c.moments_bf16)
+        ops.call("sb_adamw_step", self.p.mat, self.master[0], self.m[0], self.v[0], grads.mat, self.p.mat.numel(), 0,
+                 mb, self.total_sq, lr, c.adam_beta1, c.adam_beta2, c.adam_eps, c.weight_decay, self.t,
+                 c.max_grad_norm, grad_scale)
+        ops.call("sb_adamw_step", self.p.vec, self.master[1], self.m[1], self.v[1], grads.vec, self.p.vec.numel(), 1,
+                 mb, self.total_sq, lr, c.adam_beta1, c.adam_beta2, c.adam_eps, 0.0, self.t, c.max_grad_norm,
+                 grad_scale)
+        return lr
+
+
+class SGRLVRTrainerB200:
+    """One prompt per rank per step -> G sampled completions (+ G/2 from the frame-shuffled video) -> rewards ->
+    group-relative advantages -> one GRPO update.  Data-parallel over ranks: gradients are summed with one NCCL
+    all-reduce per arena (torch.distributed), nothing else crosses ranks on the data path."""
+
+    def __init__(self, model: Qwen2VLB200, ref_model: Qwen2VLB200 | None, reward_funcs: Sequence[Callable],
+                 cfg: GRPOConfig, decode_completions: Callable[[torch.Tensor], list[str]],
+                 process_group=None):
+        self.model, self.ref_model, self.reward_funcs, self.cfg = model, ref_model, list(reward_funcs), cfg
+        self.decode_completions = decode_completions
+        self.grads = GradStore(model.params)
+        self.opt = AdamW(model.params, cfg)
+        self.pg = process_group
+        self._metrics = defaultdict(list)
+        self.global_step = 0
+
+    # -- distributed helpers ---------------------------------------------------------------------------
+    def _world(self):
+        import torch.distributed as dist
+        return dist.get_world_size(self.pg) if (dist.is_available() and dist.is_initialized()) else 1
+
+    def _allreduce_grads(self):
+        import torch.distributed as dist
+        if self._world() > 1:
+            dist.all_reduce(self.grads.mat, group=self.pg)
+            dist.all_reduce(self.grads.vec, group=self.pg)
+
+    def _gather(self, t: torch.Tensor) -> torch.Tensor:
+        import torch.distributed as dist
+        w = self._world()
+        if w == 1:
+            return t
+        out = [torch.empty_like(t) for _ in range(w)]
+        dist.all_gather(out, t.contiguous(), group=self.pg)
+        return torch.cat(out)
+
+    # -- the step --------------------------------------------------------------------------------------
+    def rollout(self, example, seed):
+        """TRN:442-481: G completions of the prompt (+ G/2 of the frame-shuffled video when temporal)."""
+        c = self.cfg
+        G = c.num_generations
+        pix = example["pixel_values_videos"]
+        grid = example["video_grid_thw"]
+        ids = example["input_ids"]
+        if c.max_prompt_length is not None and ids.shape[-1] > c.max_prompt_length:
+            ids = ids[..., -c.max_prompt_length:]                    # TRN:432-440
+        kw = dict(max_new_tokens=c.max_completion_length, top_p=TOP_P, seed=seed, min_new_tokens=c.min_new_tokens)
+        if c.temporal and pix is not None:
+            pix2 = self.shuffle_frames(pix, grid, seed)
+            main, shuf = self.model.generate(ids, pix, grid, num_return_sequences=G, pixel_values_videos_2=pix2,
+                                             num_return_sequences_2=G // 2, **kw)
+            return ids, main, shuf
+        main = self.model.generate(ids, pix, grid, num_return_sequences=G, **kw)
+        return ids, main, None
+
+    @staticmethod
+    def shuffle_frames(pixel_values, grid_thw, seed):
+        """TRN:442-458 permutes the decoded FRAMES and re-runs the processor.  Normalisation is per pixel, so on
+        the patch matrix this is an index permutation of the per-frame halves of the patch rows."""
+        grid = grid_thw.tolist() if torch.is_tensor(grid_thw) else grid_thw
+        t, h, w = map(int, grid[0])
+        hw = h * w
+        c2 = pixel_values.shape[1] // 2          # channels * patch * patch per frame of the temporal pair
+        n_ch = 3
+        pp = c2 // n_ch
+        g = torch.Generator(device="cpu").manual_seed(int(seed) + 7919)
+        perm = torch.randperm(2 * t, generator=g).to(pixel_values.device)
+        # rows are [C, Tp=2, 14, 14] flattened: bring the frame index out, permute frames, fold back
+        x = pixel_values.view(t, hw, n_ch, 2, pp).permute(0, 3, 1, 2, 4).reshape(2 * t, hw, n_ch, pp)
+        x = x[perm]
+        return x.view(t, 2, hw, n_ch, pp).permute(0, 2, 3, 1, 4).reshape(pixel_values.shape).contiguous()
+
+    def compute_rewards(self, completions_text, example, G):
+        prompts = [example.get("prompt")] * G
+        completions = [[{"role": "assistant", "content": s}] for s in completions_text]
+        per_func = torch.zeros(G, len(self.reward_funcs), device=self.model.device)
+        extra = {k: [example[k]] * G for k in example
+                 if k not in ("prompt", "completion", "input_ids", "pixel_values_videos", "video_grid_thw", "path")}
+        for i, fn in enumerate(self.reward_funcs):
+            out = fn(prompts=prompts, completions=completions, path=[example.get("path", "")] * G, **extra)  # TRN:592
+            per_func[:, i] = torch.tensor([float(x) for x in out], device=self.model.device)
+        return per_func
+
+    def training_step(self, example) -> dict:
+        c, m = self.cfg, self.model
+        G = c.num_generations
+        seed = c.seed + 1000003 * self.global_step
+        prompt_ids, main, shuf = self.rollout(example, seed)
+        P = prompt_ids.reshape(-1).numel()
+        completion_ids = main[:, P:]
+        pix, grid = example["pixel_values_videos"], example["video_grid_thw"]
+        batch = pack_prompt_completions(prompt_ids, completion_ids, grid, m.dims, m.device, m.rope_convention)
+        # reference-policy log-probs (TRN:534-547); beta = 0 skips it
+        ref_lp = None
+        if self.ref_model is not None and c.beta != 0.0:
+            ref_lp = self.ref_model.per_token_logps(batch, pix, grid)
+        # rewards on decoded text (TRN:555-593)
+        rewards_per_func = self.compute_rewards(self.decode_completions(completion_ids), example, G)
+        temporal_rewards = 0.5
+        summed = rewards_per_func
+        if c.temporal and shuf is not None:
+            shuf_rpf = self.compute_rewards(self.decode_completions(shuf[:, P:]), example, G // 2)
+            summed = rewards_per_func.clone()                                       # TRN:598-611
+            if summed[:, 0].mean() >= TEMPORAL_RATIO * shuf_rpf[:, 0].mean():
+                sel = summed[:, 0] > ACC_THRESHOLD
+                summed[sel, 0] = summed[sel, 0] + TEMPORAL_BONUS
+                temporal_rewards = 1.0
+            else:
+                temporal_rewards = 0.0
+        rewards = summed.sum(dim=1)                                                 # TRN:613-617
+        # completion mask lengths are needed for the length bonus before the loss kernel runs (TRN:489-494, 620-629)
+        is_eos = completion_ids == m.dims.eos_id
+        C = completion_ids.shape[1]
+        eos_idx = torch.where(is_eos.any(1), is_eos.int().argmax(1), torch.full((G,), C, device=m.device))
+        lengths = torch.clamp(eos_idx + 1, max=C)
+        if c.len_control:
+            sel = torch.nonzero(rewards_per_func[:, 0] > ACC_THRESHOLD, as_tuple=True)[0].tolist()
+            if len(sel) > 1:
+                ll = lengths.tolist()
+                for i in sel:
+                    if LEN_WINDOW[0] <= ll[i] <= LEN_WINDOW[1]:
+                        rewards[i] += LEN_BONUS
+        mean = rewards.mean()
+        std = rewards.std()                                                         # unbiased, TRN:633
+        adv = (rewards - mean) / (std + STD_EPS)                                    # TRN:638
+        out = m.grpo_forward_backward(batch, pix, grid, ref_lp, adv, c.beta, self.grads)
+        # data parallel: sum gradients over ranks, average inside the optimizer
+        self._allreduce_grads()
+        lr = self.opt.step(self.grads, grad_scale=1.0 / self._world())
+        self.global_step += 1
+        # metrics (TRN:650-683), one gather per quantity like the reference but on a packed struct
+        packed = torch.cat([lengths.float(), rewards_per_func.reshape(-1), rewards,
+                            torch.stack([std, out["mean_kl"], torch.tensor(temporal_rewards, device=m.device)])])
+        allp = self._gather(packed).view(-1, packed.numel())
+        nf = len(self.reward_funcs)
+        gl = allp[:, :G]
+        grpf = allp[:, G:G + G * nf].reshape(-1, nf)
+        grew = allp[:, G + G * nf:G + G * nf + G]
+        tail = allp[:, -3:]
+        mt = {"completion_length": gl.mean().item()}
+        for i, fn in enumerate(self.reward_funcs):
+            mt[f"rewards/{fn.__name__}"] = grpf[:, i].mean().item()
+        mt["all_wrong"] = (grew <= 1).all(dim=1).float().mean().item()
+        mt["all_correct"] = (grew >= 2).all(dim=1).float().mean().item()
+        if c.temporal:
+            mt["temporal_rewards"] = tail[:, 2].mean().item()
+        mt["reward"] = grew.mean().item()
+        mt["reward_std"] = tail[:, 0].mean().item()
+        mt["kl"] = tail[:, 1].mean().item()
+        mt["loss"] = out["loss"].item()
+        mt["learning_rate"] = lr
+        for k, v in mt.items():
+            self._metrics[k].append(v)
+        mt["generated_tokens"] = int(completion_ids.numel() + (shuf[:, P:].numel() if shuf is not None else 0))
+        return mt
+
+    def log(self):
+        """TRN:688-695: average and clear."""
+        out = {k: sum(v) / len(v) for k, v in self._metrics.items() if v}
+        self._metrics.clear()
+        return out

@@ -1,0 +1,264 @@
+"""GPU parity of the decode-step kernels, the sampler, the fused GRPO loss and AdamW against torch / the oracle."""
+import math
+import os
+import sys
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+pytestmark = pytest.mark.gpu
+
+
+def rnd(shape, seed, scale=1.0, dtype=torch.bfloat16):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dtype).cuda()
+
+
+def close(a, b, tol=2e-2, name=""):
+    a, b = a.float(), b.float()
+    err = (a - b).abs().max().item()
+    den = b.abs().max().item() + 1e-6
+    assert err / den < tol, f"{name}: max abs err {err} vs scale {den}"
+
+
+def test_dec_residual_rmsnorm_and_swiglu():
+    from spacer_b200 import ops
+    R, H, S = 12, 3584, 4
+    x = rnd((16, H), 1)
+    parts = rnd((S, 16, H), 2, 0.3, torch.float32)
+    w = 1 + rnd((H,), 3, 0.1)
+    xn = torch.zeros((16, H), device="cuda", dtype=torch.bfloat16)
+    x2 = x.clone()
+    ops.call("sb_dec_residual_rmsnorm", x2, parts, S, 16 * H, H, w, xn, R, H, 1e-6)
+    ref_x = (parts.sum(0).bfloat16().float() + x.float()).bfloat16()
+    assert torch.equal(x2[:R], ref_x[:R]) and torch.equal(x2[R:], x[R:])
+    xf = ref_x.float()
+    ref_n = w.float() * (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6)).bfloat16().float()
+    close(xn[:R], ref_n[:R], 1e-2)
+    I = 512
+    pg = rnd((S, 16, 2 * I), 4, 0.5, torch.float32)
+    act = torch.zeros((16, I), device="cuda", dtype=torch.bfloat16)
+    ops.call("sb_dec_swiglu", pg, S, 16 * 2 * I, 2 * I, act, R, I)
+    gu = pg.sum(0).bfloat16().float().view(16, I // 64, 2, 64)
+    ref = (F.silu(gu[:, :, 0]).bfloat16().float() * gu[:, :, 1]).reshape(16, I)
+    close(act[:R], ref[:R], 1e-2)
+
+
+def test_dec_qkv_post_and_attention():
+    from oracle import qwen2vl_ref as Rf
+    from spacer_b200 import ops
+    R, nh, nkv, hd, S, P, Cmax = 6, 14, 2, 128, 3, 150, 40
+    W = (nh + 2 * nkv) * hd
+    step = 17
+    rope_base = 93
+    parts = rnd((S, 16, W), 1, 0.4, torch.float32)
+    bias = rnd((W,), 2, 0.1)
+    step_t = torch.tensor([step], dtype=torch.int32, device="cuda")
+    q_out = torch.zeros((16, nh * hd), device="cuda", dtype=torch.bfloat16)
+    kc = rnd((R, Cmax, nkv * hd), 3, 0.5)
+    vc = rnd((R, Cmax, nkv * hd), 4, 0.5)
+    kc0, vc0 = kc.clone(), vc.clone()
+    ops.call("sb_dec_qkv_post", parts, S, 16 * W, W, bias, step_t, rope_base, 1e6, nh, nkv, hd, q_out, kc, vc,
+             Cmax * nkv * hd, Cmax, R)
+    qkv = (parts.sum(0) + bias.float()).bfloat16().float()[:R]
+    d = Rf.Dims(heads=nh, kv_heads=nkv)
+    pos = torch.full((3, 1, 1), rope_base + step)
+    cos, sin = Rf.mrope_cos_sin(pos, d)
+    cos, sin = cos[0, 0].cuda().bfloat16().float(), sin[0, 0].cuda().bfloat16().float()
+    rot = lambda x: torch.cat((-x[..., hd // 2:], x[..., :hd // 2]), -1)
+    q = qkv[:, :nh * hd].view(R, nh, hd)
+    k = qkv[:, nh * hd:(nh + nkv) * hd].view(R, nkv, hd)
+    v = qkv[:, (nh + nkv) * hd:]
+    qr, kr = q * cos + rot(q) * sin, k * cos + rot(k) * sin
+    close(q_out[:R], qr.reshape(R, -1), 1e-2, "q")
+    close(kc[:, step], kr.reshape(R, -1), 1e-2, "k slot")
+    close(vc[:, step], v, 1e-2, "v slot")
+    mask = torch.ones(Cmax, dtype=torch.bool)
+    mask[step] = False
+    assert torch.equal(kc[:, mask], kc0[:, mask]) and torch.equal(vc[:, mask], vc0[:, mask])
+    # attention over two prompt caches + completion cache
+    kp0, vp0, kp1, vp1 = (rnd((P, nkv * hd), s, 0.5) for s in (5, 6, 7, 8))
+    n_split = 4
+    rep = nh // nkv
+    o_part = torch.empty((R, nkv, n_split, rep, hd), device="cuda", dtype=torch.float32)
+    ml = torch.empty((R, nkv, n_split, rep, 2), device="cuda", dtype=torch.float32)
+    out = torch.zeros((16, nh * hd), device="cuda", dtype=torch.bfloat16)
+    g0 = 4
+    ops.call("sb_dec_attn", q_out, kp0, vp0, kp1, vp1, g0, P, kc, vc, Cmax * nkv * hd, step_t, nh, nkv, hd,
+             hd ** -0.5, n_split, o_part, ml, out, R)
+    for r in range(R):
+        kp, vp = (kp0, vp0) if r < g0 else (kp1, vp1)
+        K = torch.cat([kp, kc[r, :step + 1]]).float().view(-1, nkv, hd).repeat_interleave(rep, 1)
+        V = torch.cat([vp, vc[r, :step + 1]]).float().view(-1, nkv, hd).repeat_interleave(rep, 1)
+        qq = q_out[r].float().view(nh, hd)
+        s = torch.einsum("hd,jhd->hj", qq, K) * hd ** -0.5
+        ref = torch.einsum("hj,jhd->hd", torch.softmax(s, -1), V).reshape(-1)
+        close(out[r], ref, 1e-2, f"attn row {r}")
+
+
+def _expected_dist(logits, top_p, suppress=None):
+    from oracle import qwen2vl_ref as Rf
+    l = logits.bfloat16().float().cpu()
+    if suppress is not None:
+        l[:, suppress] = float("-inf")
+    return torch.softmax(Rf.top_p_filter(l, top_p), dim=-1)
+
+
+@pytest.mark.parametrize("V,scale", [(2048, 3.0), (152064, 1.0), (5003, 6.0)])
+def test_sampler_distribution(V, scale):
+    """Kept set == the TopPLogitsWarper kept set; empirical frequencies match the filtered softmax
+    (total-variation distance over many Philox draws)."""
+    from spacer_b200 import ops
+    R = 4
+    logits = rnd((R, V), 21, scale, torch.float32)
+    if V == 2048:
+        logits[1, :] = 0.0          # all tied
+        logits[2, 7] = 30.0         # one dominant token: top-1 always kept
+    exp = _expected_dist(logits, 0.95)
+    n_draws = 4000
+    step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    toks = torch.empty(R, dtype=torch.int32, device="cuda")
+    ids = torch.zeros((R, n_draws), dtype=torch.int32, device="cuda")
+    lp = torch.empty(R, dtype=torch.float32, device="cuda")
+    for i in range(n_draws):
+        ops.call("sb_sample_top_p", logits, V, R, V, 0.95, 1234, step, None, toks, ids, n_draws, lp, -1, 0, 0)
+        ops.call("sb_step_advance", step)
+    torch.cuda.synchronize()
+    ids = ids.cpu().long()
+    lv = logits.bfloat16().float().cpu()
+    for r in range(R):
+        # Which members of a tie group at the cut are dropped depends on the sort's tie order (implementation
+        # defined in torch), so compare per distinct logit VALUE: mass of every value group must match.
+        vals, inv = torch.unique(lv[r], return_inverse=True)
+        exp_g = torch.zeros(len(vals)).index_add_(0, inv, exp[r])
+        got_g = torch.bincount(inv[ids[r]], minlength=len(vals)).float() / n_draws
+        assert (exp_g[inv[ids[r]]] > 0).all(), f"row {r}: sampled a value group the reference warper removes"
+        kept_groups = int((exp_g > 0).sum())
+        tv = 0.5 * (got_g - exp_g).abs().sum().item()
+        assert tv < 3 * math.sqrt(kept_groups / (2 * math.pi * n_draws)) + 0.02, f"row {r}: TV {tv}, groups {kept_groups}"
+        # within the cut tie group the number of distinct survivors cannot exceed the reference's count
+        cut = int(torch.nonzero(exp_g > 0)[0])
+        n_keep_ref = int(((inv == cut) & (exp[r] > 0)).sum())
+        n_keep_got = len(set(ids[r][inv[ids[r]] == cut].tolist()))
+        assert n_keep_got <= n_keep_ref, f"row {r}: {n_keep_got} distinct survivors in the cut group, reference keeps {n_keep_ref}"
+    # different seeds / rows give different streams, same seed reproduces
+    a = torch.empty(R, dtype=torch.int32, device="cuda")
+    b = torch.empty(R, dtype=torch.int32, device="cuda")
+    step.zero_()
+    ops.call("sb_sample_top_p", logits, V, R, V, 0.95, 99, step, None, a, None, 0, None, -1, 0, 0)
+    ops.call("sb_sample_top_p", logits, V, R, V, 0.95, 99, step, None, b, None, 0, None, -1, 0, 0)
+    assert torch.equal(a, b)
+
+
+def test_sampler_kept_set_exact():
+    """Draw many samples from a small vocabulary: the support must equal the reference kept set exactly."""
+    from spacer_b200 import ops
+    V, R = 64, 8
+    logits = rnd((R, V), 5, 2.0, torch.float32)
+    exp = _expected_dist(logits, 0.95)
+    n = 3000
+    step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    toks = torch.empty(R, dtype=torch.int32, device="cuda")
+    ids = torch.zeros((R, n), dtype=torch.int32, device="cuda")
+    for i in range(n):
+        ops.call("sb_sample_top_p", logits, V, R, V, 0.95, 7, step, None, toks, ids, n, None, -1, 0, 0)
+        ops.call("sb_step_advance", step)
+    ids = ids.cpu().long()
+    lv = logits.bfloat16().float().cpu()
+    for r in range(R):
+        support = set(ids[r].tolist())
+        kept = set(torch.nonzero(exp[r] > 0).flatten().tolist())
+        vmin = lv[r][sorted(kept)].min()
+        # strictly-above-the-cut tokens are unambiguous; ties at the cut value may differ by sort order
+        assert all(lv[r][t] >= vmin for t in support)
+        big = {i for i in kept if exp[r][i] > 5e-3 and lv[r][i] > vmin}
+        assert big <= support
+
+
+def test_sampler_eos_and_finished():
+    from spacer_b200 import ops
+    V, R = 512, 3
+    logits = torch.full((R, V), -20.0, device="cuda")
+    logits[:, 5] = 20.0     # always samples token 5
+    step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    fin = torch.tensor([0, 1, 0], dtype=torch.int32, device="cuda")
+    toks = torch.empty(R, dtype=torch.int32, device="cuda")
+    ops.call("sb_sample_top_p", logits, V, R, V, 0.95, 1, step, fin, toks, None, 0, None, 5, 9, 0)
+    assert toks.tolist() == [5, 9, 5] and fin.tolist() == [1, 1, 1]
+    ops.call("sb_sample_top_p", logits, V, R, V, 0.95, 1, step, fin, toks, None, 0, None, 5, 9, 0)
+    assert toks.tolist() == [9, 9, 9]
+    fin.zero_()
+    logits[:, 6] = 19.0
+    ops.call("sb_sample_top_p", logits, V, R, V, 0.95, 1, step, fin, toks, None, 0, None, 5, 9, 1)  # EOS suppressed
+    assert toks.tolist() == [6, 6, 6] and fin.tolist() == [0, 0, 0]
+
+
+def test_grpo_loss_matches_oracle():
+    from oracle import grpo_ref as GR
+    from spacer_b200 import ops
+    G, C, V, K, eos = 4, 37, 1000, 128, 77
+    H, Wm = rnd((G * C, K), 1), rnd((V, K), 2, 0.2)
+    comp = torch.randint(0, V, (G, C))
+    comp[comp == eos] = 0
+    comp[1, 10] = eos
+    comp[2, C - 1] = eos
+    tg = comp.reshape(-1).to(torch.int32).cuda()
+    nt = (V + 255) // 256
+    part = torch.empty((G * C, nt, 2), device="cuda", dtype=torch.float32)
+    tl = torch.zeros(G * C, device="cuda")
+    ops.gemm(H, Wm, epilogue=ops.EPI_LMHEAD, targets=tg, lse_part=part, tgt_logit=tl)
+    logits = (H.float() @ Wm.float().t()).bfloat16().float().cpu()
+    lp_ref = torch.log_softmax(logits, -1).gather(1, comp.reshape(-1, 1)).view(G, C)
+    ref_lp = lp_ref + torch.randn(G, C) * 0.5
+    ref_lp[0, 3] = lp_ref[0, 3] + 25.0   # exercise the clamp
+    adv = torch.tensor([0.7, -1.2, 0.1, 0.4])
+    mask = GR.completion_mask(comp, eos)
+    lp_t = lp_ref.clone().requires_grad_()
+    loss, kl = GR.grpo_loss(lp_t, ref_lp, adv, mask, 0.04)
+    loss.backward()
+    outs = [torch.empty(G * C, device="cuda") for _ in range(3)]
+    mask_o = torch.empty(G * C, dtype=torch.int32, device="cuda")
+    rl, rk = torch.empty(G, device="cuda"), torch.empty(G, device="cuda")
+    rlen = torch.empty(G, dtype=torch.int32, device="cuda")
+    out2 = torch.empty(2, device="cuda")
+    ops.call("sb_grpo_loss", part, nt, tl, comp.to(torch.int32).cuda(), G, C, eos, ref_lp.cuda().contiguous(),
+             adv.cuda(), 0.04, outs[0], outs[1], outs[2], mask_o, rl, rk, rlen, out2)
+    assert (outs[0].cpu().view(G, C) - lp_ref).abs().max() < 2e-3
+    assert torch.equal(mask_o.cpu().view(G, C), mask)
+    assert rlen.tolist() == mask.sum(1).tolist()
+    assert abs(out2[0].item() - loss.item()) < 1e-4 * max(1.0, abs(loss.item()))
+    assert abs(out2[1].item() - kl.item()) < 1e-3 * max(1.0, abs(kl.item()))
+    g_ref = GR.grpo_loss_grad(outs[0].cpu().view(G, C), ref_lp, adv, mask, 0.04)
+    assert (outs[2].cpu().view(G, C) - g_ref).abs().max() < 1e-5
+    assert (lp_t.grad - g_ref).abs().max() < 1e-3
+    lp2 = torch.empty(G * C, device="cuda")
+    ops.call("sb_logprob_from_partials", part, nt, tl, lp2, G * C)
+    assert torch.allclose(lp2, outs[0])
+
+
+@pytest.mark.parametrize("grad_f32,mom_bf16", [(0, 0), (1, 0), (0, 1)])
+def test_adamw_matches_torch(grad_f32, mom_bf16):
+    from spacer_b200 import ops
+    n = 100003
+    p0 = rnd((n,), 1, 0.02)
+    master = p0.float().clone()
+    mdt = torch.bfloat16 if mom_bf16 else torch.float32
+    m, v = torch.zeros(n, device="cuda", dtype=mdt), torch.zeros(n, device="cuda", dtype=mdt)
+    ref_p = torch.nn.Parameter(p0.float().clone())
+    opt = torch.optim.AdamW([ref_p], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+    p = p0.clone()
+    for step in range(1, 4):
+        g = rnd((n,), 10 + step, 3.0, torch.float32 if grad_f32 else torch.bfloat16)
+        ref_p.grad = g.float().clone()
+        torch.nn.utils.clip_grad_norm_([ref_p], 5.0)
+        opt.step()
+        tot = torch.zeros(1, device="cuda")
+        ops.call("sb_grad_sumsq", g, n, grad_f32, tot)
+        assert abs(tot.item() - g.float().pow(2).sum().item()) < 1e-3 * tot.item()
+        ops.call("sb_adamw_step", p, master, m, v, g, n, grad_f32, mom_bf16, tot, 1e-3, 0.9, 0.999, 1e-8, 0.01, step,
+                 5.0, 1.0)
+    tol = 2e-3 if mom_bf16 else 1e-5
+    assert (master - ref_p.data).abs().max().item() < tol
+    assert torch.equal(p, master.bfloat16())
