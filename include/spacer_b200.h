@@ -33,6 +33,9 @@ const char* sb_last_error(void);
 int sb_abi_version(void);
 /* fills SM count and compute capability of the current device; error if it is not sm_100 */
 int sb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* number of kernels this library has launched (successfully enqueued) since the last reset; a launch recorded
+ * into a CUDA graph during stream capture counts once -- replays are the caller's to add.  count_host may be NULL. */
+int sb_launch_counter(long long* count_host, int reset);
 
 /* ------------------------------------------------------------------------------------------------
  * GEMM  D[M,N] = epi(A[M,K] * B[N,K]^T)   (tcgen05 + TMEM + TMA)

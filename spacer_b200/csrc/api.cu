@@ -4,8 +4,11 @@
 #include <cstdarg>
 #include <cstdio>
 
+#include <atomic>
+
 namespace {
 thread_local char g_err[1024] = "";
+std::atomic<long long> g_launches{0};
 }
 
 void sb_set_error(const char* fmt, ...) {
@@ -21,6 +24,13 @@ int sb_check_launch(const char* what) {
     sb_set_error("%s: kernel launch failed: %s", what, cudaGetErrorString(e));
     return 1;
   }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+extern "C" int sb_launch_counter(long long* count_host, int reset) {
+  if (count_host) *count_host = g_launches.load(std::memory_order_relaxed);
+  if (reset) g_launches.store(0, std::memory_order_relaxed);
   return 0;
 }
 

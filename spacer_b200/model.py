@@ -440,6 +440,43 @@ class Qwen2VLB200:
         return dict(loss=out2[0], mean_kl=out2[1], logps=lp.view(G_, C), mask=mask.view(G_, C), lengths=row_len)
 
     # ---- rollout -----------------------------------------------------------------------------------
+    def decode_weight_bytes(self) -> int:
+        """bf16 bytes of the weights one decode step must stream: 28 x (qkv, o, gate|up, down) + lm_head."""
+        d = self.dims
+        per_layer = d.qkv_dim * d.hidden + d.hidden * d.heads * d.head_dim + 3 * d.inter * d.hidden
+        return 2 * (d.layers * per_layer + d.vocab * d.hidden)
+
+    @torch.no_grad()
+    def profile_decode_gemv(self, rows: int, reps: int = 3):
+        """Time the weight-streaming GEMVs of one decode step (4 per layer + lm_head, the kernels that move >97 % of
+        a step's bytes) back to back with CUDA events; returns achieved GB/s on their algorithmic bytes."""
+        d, W = self.dims, self.params
+        st = self._alloc_decode(rows, 8, 8, 1)
+        S = st["S"]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+        def sweep():
+            for i in range(d.layers):
+                p = f"l.{i}."
+                self._gemv(W[p + "qkv_w"], st["xn"], st["p_qkv"], S["qkv"])
+                self._gemv(W[p + "o_w"], st["attn"], st["p_o"], S["o"])
+                self._gemv(W[p + "gu_w"], st["xn"], st["p_gu"], S["gu"])
+                self._gemv(W[p + "down_w"], st["act"], st["p_down"], S["down"])
+            self._gemv(W["lm_head"], st["xn"], st["logits"], 1)
+
+        sweep()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            sweep()
+        e1.record()
+        torch.cuda.synchronize()
+        launches = 4 * d.layers + 1
+        ms = e0.elapsed_time(e1) / reps
+        byts = self.decode_weight_bytes()
+        return dict(gbs=byts / (ms * 1e-3) / 1e9, bytes_per_launch=byts / launches, avg_us=ms * 1e3 / launches,
+                    launches=launches, ms_per_sweep=ms)
+
     def _gemv(self, w, x16, out_parts, splits):
         """parts[s][r][n] = x16[r] . w[n] over K split s   (swap-AB tcgen05 GEMM, weights streamed once)."""
         ops.gemm(w, x16, out=out_parts, epilogue=EPI_F32T, k_splits=splits)
@@ -540,6 +577,8 @@ class Qwen2VLB200:
         R = G1 + G2
         if R > 32:
             raise SpacerError("generate: at most 32 rows per prompt")
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
         ids_dev = ids.to(self.device, I32)
         pos, nxt = rope_index(ids, video_grid_thw, d, self.rope_convention)
         pos_dev = pos.to(I32).contiguous().to(self.device)
@@ -563,27 +602,35 @@ class Qwen2VLB200:
                  st["finished"], st["tokens"], st["out_ids"], st["c_max"], None, d.eos_id, d.pad_id, int(suppress))
         n_steps = max_new_tokens - 1
         graph = None
-        if n_steps > 0:
-            if use_graph:
-                # warm-up step outside capture (first-call attribute setup), then rewind the state it touched
-                snap = (st["step"].clone(), st["tokens"].clone(), st["finished"].clone(), st["out_ids"].clone())
+        graph_nodes = 0
+        replays = 0
+        if n_steps > 0 and use_graph:
+            # warm-up step outside capture (first-call attribute setup), then rewind the state it touched
+            snap = (st["step"].clone(), st["tokens"].clone(), st["finished"].clone(), st["out_ids"].clone())
+            self._decode_step(st, nxt, G1, top_p, seed, suppress)
+            torch.cuda.synchronize()
+            st["step"].copy_(snap[0]); st["tokens"].copy_(snap[1]); st["finished"].copy_(snap[2]); st["out_ids"].copy_(snap[3])
+            graph = torch.cuda.CUDAGraph()
+            n0 = ops.direct_launch_count()
+            with torch.cuda.graph(graph):
                 self._decode_step(st, nxt, G1, top_p, seed, suppress)
-                torch.cuda.synchronize()
-                st["step"].copy_(snap[0]); st["tokens"].copy_(snap[1]); st["finished"].copy_(snap[2]); st["out_ids"].copy_(snap[3])
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
-                    self._decode_step(st, nxt, G1, top_p, seed, suppress)
-            done = 0
+            graph_nodes = ops.direct_launch_count() - n0
+        ev[1].record()
+        done = 0
+        if n_steps > 0:
             while done < n_steps:
                 burst = min(32, n_steps - done)
                 for _ in range(burst):
                     if graph is not None:
                         graph.replay()
+                        replays += 1
                     else:
                         self._decode_step(st, nxt, G1, top_p, seed, suppress)
                 done += burst
                 if not suppress and done < n_steps and bool(st["finished"][:R].all().item()):
                     break
+            ops.note_graph_replay(graph_nodes * replays)
+        ev[2].record()
         out = st["out_ids"].long()
         if not suppress:
             is_eos = out == d.eos_id
@@ -596,7 +643,20 @@ class Qwen2VLB200:
             out = torch.where(col > first[:, None], torch.full_like(out, d.pad_id), out)
         prompt = ids.to(self.device).long()[None]
         res1 = torch.cat([prompt.expand(G1, -1), out[:G1]], dim=1)
-        stats = dict(decode_steps=int(st["step"].item()), rows=R)
+        steps_done = int(st["step"].item())      # host sync: everything above has completed
+        dec_ms = ev[1].elapsed_time(ev[2])
+        n_loop = max(1, done)
+        # algorithmic HBM bytes of one decode step: every LLM-layer weight + lm_head once, the shared
+        # prompt KV once per group, each row's own completion KV (average over the loop)
+        kv_tok = 2 * d.layers * d.kv_heads * d.head_dim * 2
+        w_bytes = self.decode_weight_bytes()
+        kv_bytes = len(pixel_sets) * P * kv_tok + R * (n_loop / 2.0) * kv_tok
+        stats = dict(decode_steps=steps_done, rows=R, prompt_len=P, rollout_ms=ev[0].elapsed_time(ev[2]),
+                     prefill_ms=ev[0].elapsed_time(ev[1]), decode_ms=dec_ms, decode_ms_per_step=dec_ms / n_loop,
+                     decode_bytes_per_step=w_bytes + kv_bytes,
+                     decode_gbs=(w_bytes + kv_bytes) * n_loop / (dec_ms * 1e-3) / 1e9 if dec_ms > 0 else None,
+                     graph_nodes=graph_nodes, graph_replays=replays)
+        self.last_generate_stats = stats
         self._last_decode_state = st   # kept for the parity tests (logits of the final step)
         if G2 > 0:
             res2 = torch.cat([prompt.expand(G2, -1), out[G1:]], dim=1)

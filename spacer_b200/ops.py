@@ -14,6 +14,34 @@ from ._lib import (EPI_DLOGITS, EPI_F32T, EPI_GELU, EPI_LMHEAD, EPI_QUICKGELU, E
                    EPI_SWIGLU, GemmArgs, SpacerError, check)
 
 
+# ------------------------------------------------------------------------------------------------
+# kernel-launch accounting (bench.py's `gpu_launches`): the library counts every launch it enqueues;
+# CUDA-graph replays re-launch the captured kernels, so model.py adds (graph nodes x replays) here.
+# ------------------------------------------------------------------------------------------------
+_graph_replayed = 0
+
+
+def reset_launch_count() -> None:
+    global _graph_replayed
+    _lib.load().sb_launch_counter(None, 1)
+    _graph_replayed = 0
+
+
+def direct_launch_count() -> int:
+    n = C.c_longlong(0)
+    _lib.load().sb_launch_counter(C.byref(n), 0)
+    return int(n.value)
+
+
+def note_graph_replay(kernels: int) -> None:
+    global _graph_replayed
+    _graph_replayed += int(kernels)
+
+
+def launch_count() -> int:
+    return direct_launch_count() + _graph_replayed
+
+
 def _stream() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 

@@ -114,6 +114,7 @@ class SGRLVRTrainerB200:
         self.pg = process_group
         self._metrics = defaultdict(list)
         self.global_step = 0
+        self.last_rollout_stats = None
 
     # -- distributed helpers ---------------------------------------------------------------------------
     def _world(self):
@@ -150,8 +151,10 @@ class SGRLVRTrainerB200:
             pix2 = self.shuffle_frames(pix, grid, seed)
             main, shuf = self.model.generate(ids, pix, grid, num_return_sequences=G, pixel_values_videos_2=pix2,
                                              num_return_sequences_2=G // 2, **kw)
+            self.last_rollout_stats = self.model.last_generate_stats
             return ids, main, shuf
         main = self.model.generate(ids, pix, grid, num_return_sequences=G, **kw)
+        self.last_rollout_stats = self.model.last_generate_stats
         return ids, main, None
 
     @staticmethod
@@ -186,7 +189,16 @@ class SGRLVRTrainerB200:
         c, m = self.cfg, self.model
         G = c.num_generations
         seed = c.seed + 1000003 * self.global_step
+        marks = []
+
+        def mark(name):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            marks.append((name, e))
+
+        mark("start")
         prompt_ids, main, shuf = self.rollout(example, seed)
+        mark("rollout")
         P = prompt_ids.reshape(-1).numel()
         completion_ids = main[:, P:]
         pix, grid = example["pixel_values_videos"], example["video_grid_thw"]
@@ -195,6 +207,7 @@ class SGRLVRTrainerB200:
         ref_lp = None
         if self.ref_model is not None and c.beta != 0.0:
             ref_lp = self.ref_model.per_token_logps(batch, pix, grid)
+        mark("ref_scoring")
         # rewards on decoded text (TRN:555-593)
         rewards_per_func = self.compute_rewards(self.decode_completions(completion_ids), example, G)
         temporal_rewards = 0.5
@@ -224,10 +237,14 @@ class SGRLVRTrainerB200:
         mean = rewards.mean()
         std = rewards.std()                                                         # unbiased, TRN:633
         adv = (rewards - mean) / (std + STD_EPS)                                    # TRN:638
+        mark("rewards")
         out = m.grpo_forward_backward(batch, pix, grid, ref_lp, adv, c.beta, self.grads)
+        mark("policy_fwd_bwd")
         # data parallel: sum gradients over ranks, average inside the optimizer
         self._allreduce_grads()
+        mark("grad_allreduce")
         lr = self.opt.step(self.grads, grad_scale=1.0 / self._world())
+        mark("adamw")
         self.global_step += 1
         # metrics (TRN:650-683), one gather per quantity like the reference but on a packed struct
         packed = torch.cat([lengths.float(), rewards_per_func.reshape(-1), rewards,
@@ -252,6 +269,7 @@ class SGRLVRTrainerB200:
         mt["learning_rate"] = lr
         for k, v in mt.items():
             self._metrics[k].append(v)
+        self.last_phase_ms = {marks[i][0]: marks[i - 1][1].elapsed_time(marks[i][1]) for i in range(1, len(marks))}
         mt["generated_tokens"] = int(completion_ids.numel() + (shuf[:, P:].numel() if shuf is not None else 0))
         return mt
 
