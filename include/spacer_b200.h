@@ -155,19 +155,24 @@ int sb_dec_qkv_post(const float* parts, int S, long long stride_s, long long str
                     const int* step_ptr, int rope_base, float theta, int n_heads, int n_kv_heads, int head_dim,
                     void* q_out, void* k_cache, void* v_cache, long long cache_stride_r, int c_max, int R,
                     sb_stream_t stream);
-/* split-KV attention over the shared prompt cache(s) [P][nkv*hd] (rows < rows_group0 use kp0/vp0, the rest
- * kp1/vp1) plus each row's completion cache [c_max][nkv*hd]; out bf16 [R][n_heads*hd] */
+/* prefix-shared flash decoding: rows < rows_group0 share prompt cache kp0/vp0 [P][nkv*hd], the rest kp1/vp1; every
+ * row also attends to its own completion cache [c_max][nkv*hd] slots 0..*step_ptr.  The shared prompt K/V is read once
+ * per group (queries of all its rows batched on tensor cores).  workspace: fp32 scratch of at least
+ * sb_dec_attn_workspace() floats.  out bf16 [R][n_heads*hd] */
+int sb_dec_attn_workspace(int R, int rows_group0, int P, int c_max, int n_heads, int n_kv_heads, long long* floats_out);
 int sb_dec_attn(const void* q, const void* kp0, const void* vp0, const void* kp1, const void* vp1, int rows_group0,
-                int P, const void* k_cache, const void* v_cache, long long cache_stride_r, const int* step_ptr,
-                int n_heads, int n_kv_heads, int head_dim, float scale, int n_split, float* o_part, float* ml_part,
-                void* out, int R, sb_stream_t stream);
+                int P, const void* k_cache, const void* v_cache, long long cache_stride_r, int c_max,
+                const int* step_ptr, int n_heads, int n_kv_heads, int head_dim, float scale, float* workspace,
+                long long workspace_floats, void* out, int R, sb_stream_t stream);
 int sb_dec_swiglu(const float* parts, int S, long long stride_s, long long stride_r, void* act, int R, int I,
                   sb_stream_t stream);
 /* top-p sampling of one token per row from fp32 logits [R][ld]; TopPLogitsWarper + multinomial semantics
- * (logits_process.py:521-533, generation/utils.py:2789-2797).  out_ids[r][*step_ptr] = token (optional) */
+ * (logits_process.py:521-533, generation/utils.py:2789-2797).  out_ids[r][*step_ptr] = token (optional).
+ * seed_dev (optional device scalar) overrides `seed`, so that a captured CUDA graph can be replayed with new seeds */
 int sb_sample_top_p(const float* logits, long long ld, int R, int V, float top_p, unsigned long long seed,
                     const int* step_ptr, int* finished, int* out_tokens, int* out_ids, long long out_ld,
-                    float* out_logprob, int eos_id, int pad_id, int suppress_eos, sb_stream_t stream);
+                    float* out_logprob, int eos_id, int pad_id, int suppress_eos, const long long* seed_dev,
+                    sb_stream_t stream);
 int sb_step_advance(int* step_ptr, sb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -45,6 +45,7 @@ struct SampleParams {
   const float* logits; long long ld; int V;
   float top_p;
   unsigned long long seed;
+  const long long* seed_dev;  // optional: overrides `seed` (lets one captured CUDA graph serve every rollout)
   const int* step_ptr;
   int* finished;            // [R] in/out
   int* out_tokens;          // [R]
@@ -266,7 +267,8 @@ sample_kernel(const SampleParams p) {
   // ---- phase E: draw u, locate the token in index order
   const int step = *p.step_ptr;
   uint32_t rnd[4];
-  philox4x32_10((uint32_t)step, (uint32_t)row, 0x5BACE200u, 0u, (uint32_t)p.seed, (uint32_t)(p.seed >> 32), rnd);
+  const unsigned long long seed = p.seed_dev ? (unsigned long long)*p.seed_dev : p.seed;
+  philox4x32_10((uint32_t)step, (uint32_t)row, 0x5BACE200u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), rnd);
   const float u = ((rnd[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
   const float target = u * kept_total;
   // the CTA whose kept-mass interval holds target owns the draw; the last CTA with mass absorbs round-off
@@ -312,11 +314,12 @@ __global__ void step_advance_kernel(int* step_ptr) { *step_ptr += 1; }
 
 extern "C" int sb_sample_top_p(const float* logits, long long ld, int R, int V, float top_p, unsigned long long seed,
                                const int* step_ptr, int* finished, int* out_tokens, int* out_ids, long long out_ld,
-                               float* out_logprob, int eos_id, int pad_id, int suppress_eos, sb_stream_t stream) {
+                               float* out_logprob, int eos_id, int pad_id, int suppress_eos, const long long* seed_dev,
+                               sb_stream_t stream) {
   SB_REQUIRE(logits && step_ptr && out_tokens && R > 0 && V > 0, "sb_sample_top_p: bad arguments");
   SB_REQUIRE(top_p > 0.f && top_p <= 1.f, "sb_sample_top_p: top_p must be in (0,1], got %f", top_p);
   SampleParams p;
-  p.logits = logits; p.ld = ld; p.V = V; p.top_p = top_p; p.seed = seed; p.step_ptr = step_ptr;
+  p.logits = logits; p.ld = ld; p.V = V; p.top_p = top_p; p.seed = seed; p.seed_dev = seed_dev; p.step_ptr = step_ptr;
   p.finished = finished; p.out_tokens = out_tokens; p.out_ids = out_ids; p.out_ld = out_ld;
   p.out_logprob = out_logprob; p.eos_id = eos_id; p.pad_id = pad_id; p.suppress_eos = suppress_eos;
   p.slice = ((V + CL - 1) / CL + 3) & ~3;

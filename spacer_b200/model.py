@@ -451,7 +451,7 @@ class Qwen2VLB200:
         """Time the weight-streaming GEMVs of one decode step (4 per layer + lm_head, the kernels that move >97 % of
         a step's bytes) back to back with CUDA events; returns achieved GB/s on their algorithmic bytes."""
         d, W = self.dims, self.params
-        st = self._alloc_decode(rows, 8, 8, 1)
+        st = self._alloc_decode(rows, 8, 8, 1)      # private scratch state, not the cached rollout state
         S = st["S"]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
@@ -515,19 +515,40 @@ class Qwen2VLB200:
             step=torch.zeros(1, device=dev, dtype=I32), tokens=torch.zeros(RP, device=dev, dtype=I32),
             finished=torch.zeros(RP, device=dev, dtype=I32),
             out_ids=torch.zeros((R, c_max), device=dev, dtype=I32),
-            n_split=4,
+            seed=torch.zeros(1, device=dev, dtype=torch.int64),
+            graphs={},
         )
-        rep = d.heads // d.kv_heads
-        st["o_part"] = torch.empty((R, d.kv_heads, st["n_split"], rep, d.head_dim), device=dev, dtype=F32)
-        st["ml_part"] = torch.empty((R, d.kv_heads, st["n_split"], rep, 2), device=dev, dtype=F32)
+        st["attn_ws"] = None      # sized on first use (depends on the group split)
         return st
 
-    def _decode_step(self, st, rope_base, rows_group0, top_p, seed, suppress_eos):
+    def _attn_workspace(self, st, rows_group0):
+        import ctypes
+        d = self.dims
+        n = ctypes.c_longlong(0)
+        ops._lib.check(ops._lib.load().sb_dec_attn_workspace(st["R"], rows_group0, st["P"], st["c_max"], d.heads,
+                                                             d.kv_heads, ctypes.byref(n)), "sb_dec_attn_workspace")
+        if st["attn_ws"] is None or st["attn_ws"].numel() < n.value:
+            st["attn_ws"] = torch.empty(n.value, device=self.device, dtype=F32)
+        return st["attn_ws"]
+
+    def _decode_state(self, R, P, c_max, n_prompts):
+        """Decode buffers (KV caches, split-K partials, sampler state) are allocated once per shape and reused by every
+        rollout, so the CUDA graph captured over them stays valid from step to step."""
+        key = (R, P, c_max, n_prompts)
+        if self._dec is None or self._dec[0] != key:
+            self._dec = None                  # free the old buffers before allocating the new ones
+            self._dec = (key, self._alloc_decode(R, P, c_max, n_prompts))
+        st = self._dec[1]
+        st["step"].zero_(); st["finished"].zero_(); st["tokens"].zero_(); st["out_ids"].zero_()
+        return st
+
+    def _decode_step(self, st, rope_base, rows_group0, top_p, suppress_eos):
         """Enqueue one decode step (feeds tokens at slot *step, samples the next token into slot *step + 1)."""
         d, W = self.dims, self.params
         R, RP, P, S = st["R"], st["RP"], st["P"], st["S"]
         H, I = d.hidden, d.inter
         nh, nkv, hd = d.heads, d.kv_heads, d.head_dim
+        ws = self._attn_workspace(st, rows_group0)
         ops.call("sb_dec_embed", st["tokens"], W["embed"], st["x"], R, H)
         parts, sp = None, 0
         for i in range(d.layers):
@@ -540,8 +561,8 @@ class Qwen2VLB200:
             kp1 = st["kp"][1][i] if len(st["kp"]) > 1 else None
             vp1 = st["vp"][1][i] if len(st["vp"]) > 1 else None
             ops.call("sb_dec_attn", st["q"], st["kp"][0][i], st["vp"][0][i], kp1, vp1, rows_group0, P, st["kc"][i],
-                     st["vc"][i], st["c_max"] * nkv * hd, st["step"], nh, nkv, hd, hd ** -0.5, st["n_split"],
-                     st["o_part"], st["ml_part"], st["attn"], R)
+                     st["vc"][i], st["c_max"] * nkv * hd, st["c_max"], st["step"], nh, nkv, hd, hd ** -0.5, ws,
+                     ws.numel(), st["attn"], R)
             self._gemv(W[p + "o_w"], st["attn"], st["p_o"], S["o"])
             ops.call("sb_dec_residual_rmsnorm", st["x"], st["p_o"], S["o"], RP * H, H, W[p + "ln2_w"], st["xn"], R, H,
                      d.rms_eps)
@@ -552,8 +573,35 @@ class Qwen2VLB200:
         ops.call("sb_dec_residual_rmsnorm", st["x"], parts, sp, RP * H, H, W["norm_w"], st["xn"], R, H, d.rms_eps)
         self._gemv(W["lm_head"], st["xn"], st["logits"], 1)
         ops.call("sb_step_advance", st["step"])
-        ops.call("sb_sample_top_p", st["logits"], d.vocab, R, d.vocab, float(top_p), int(seed), st["step"],
-                 st["finished"], st["tokens"], st["out_ids"], st["c_max"], None, d.eos_id, d.pad_id, int(suppress_eos))
+        ops.call("sb_sample_top_p", st["logits"], d.vocab, R, d.vocab, float(top_p), 0, st["step"], st["finished"],
+                 st["tokens"], st["out_ids"], st["c_max"], None, d.eos_id, d.pad_id, int(suppress_eos), st["seed"])
+
+    def _decode_graph(self, st, rope_base, rows_group0, top_p, suppress_eos):
+        """Capture one decode step into a CUDA graph (cached per decode state and step arguments).  Captured with the
+        raw CUDAGraph API: the `torch.cuda.graph` context manager would empty the caching allocator, which makes
+        every later phase of the training step re-map its memory."""
+        key = (int(rope_base), int(rows_group0), float(top_p), bool(suppress_eos))
+        hit = st["graphs"].get(key)
+        if hit is not None:
+            return hit
+        snap = (st["step"].clone(), st["tokens"].clone(), st["finished"].clone(), st["out_ids"].clone())
+        self._decode_step(st, rope_base, rows_group0, top_p, suppress_eos)   # warm-up outside capture (func attributes)
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(cur)
+        graph = torch.cuda.CUDAGraph()
+        n0 = ops.direct_launch_count()
+        with torch.cuda.stream(side):
+            graph.capture_begin()
+            try:
+                self._decode_step(st, rope_base, rows_group0, top_p, suppress_eos)
+            finally:
+                graph.capture_end()
+        nodes = ops.direct_launch_count() - n0
+        cur.wait_stream(side)
+        st["step"].copy_(snap[0]); st["tokens"].copy_(snap[1]); st["finished"].copy_(snap[2]); st["out_ids"].copy_(snap[3])
+        st["graphs"][key] = (graph, nodes)
+        return graph, nodes
 
     @torch.no_grad()
     def generate(self, input_ids, pixel_values_videos=None, video_grid_thw=None, *, max_new_tokens=1024,
@@ -584,52 +632,38 @@ class Qwen2VLB200:
         pos_dev = pos.to(I32).contiguous().to(self.device)
         meta = causal_meta(P, self.device)
         pixel_sets = [pixel_values_videos] + ([pixel_values_videos_2] if G2 > 0 else [])
-        st = self._alloc_decode(R, P, max_new_tokens, len(pixel_sets))
-        H = d.hidden
-        last_h = []
+        st = self._decode_state(R, P, max_new_tokens, len(pixel_sets))
+        st["seed"].fill_(int(seed))
         for k, pix in enumerate(pixel_sets):
             vis = self.vit_forward(pix, video_grid_thw) if pix is not None else None
             kv = [(st["kp"][k][i], st["vp"][k][i]) for i in range(d.layers)]
             hf = self.llm_forward(ids_dev, vis, pos_dev, meta, kv_out=kv)
-            last_h.append(hf[P - 1])
+            # first token: same distribution for every row of a group, independent draws
+            r0, r1 = (0, G1) if k == 0 else (G1, R)
+            st["xn"][r0:r1].copy_(hf[P - 1][None].expand(r1 - r0, -1))
             del hf, vis
-        # first token: same distribution for every row of a group, independent draws
-        for r in range(R):
-            st["xn"][r].copy_(last_h[0] if r < G1 else last_h[1])
         self._gemv(self.params["lm_head"], st["xn"], st["logits"], 1)
         suppress = min_new_tokens > 0
-        ops.call("sb_sample_top_p", st["logits"], d.vocab, R, d.vocab, float(top_p), int(seed), st["step"],
-                 st["finished"], st["tokens"], st["out_ids"], st["c_max"], None, d.eos_id, d.pad_id, int(suppress))
+        ops.call("sb_sample_top_p", st["logits"], d.vocab, R, d.vocab, float(top_p), 0, st["step"], st["finished"],
+                 st["tokens"], st["out_ids"], st["c_max"], None, d.eos_id, d.pad_id, int(suppress), st["seed"])
         n_steps = max_new_tokens - 1
-        graph = None
-        graph_nodes = 0
-        replays = 0
+        graph, graph_nodes, replays = None, 0, 0
         if n_steps > 0 and use_graph:
-            # warm-up step outside capture (first-call attribute setup), then rewind the state it touched
-            snap = (st["step"].clone(), st["tokens"].clone(), st["finished"].clone(), st["out_ids"].clone())
-            self._decode_step(st, nxt, G1, top_p, seed, suppress)
-            torch.cuda.synchronize()
-            st["step"].copy_(snap[0]); st["tokens"].copy_(snap[1]); st["finished"].copy_(snap[2]); st["out_ids"].copy_(snap[3])
-            graph = torch.cuda.CUDAGraph()
-            n0 = ops.direct_launch_count()
-            with torch.cuda.graph(graph):
-                self._decode_step(st, nxt, G1, top_p, seed, suppress)
-            graph_nodes = ops.direct_launch_count() - n0
+            graph, graph_nodes = self._decode_graph(st, nxt, G1, top_p, suppress)
         ev[1].record()
         done = 0
-        if n_steps > 0:
-            while done < n_steps:
-                burst = min(32, n_steps - done)
-                for _ in range(burst):
-                    if graph is not None:
-                        graph.replay()
-                        replays += 1
-                    else:
-                        self._decode_step(st, nxt, G1, top_p, seed, suppress)
-                done += burst
-                if not suppress and done < n_steps and bool(st["finished"][:R].all().item()):
-                    break
-            ops.note_graph_replay(graph_nodes * replays)
+        while done < n_steps:
+            burst = min(32, n_steps - done)
+            for _ in range(burst):
+                if graph is not None:
+                    graph.replay()
+                    replays += 1
+                else:
+                    self._decode_step(st, nxt, G1, top_p, suppress)
+            done += burst
+            if not suppress and done < n_steps and bool(st["finished"][:R].all().item()):
+                break
+        ops.note_graph_replay(graph_nodes * replays)
         ev[2].record()
         out = st["out_ids"].long()
         if not suppress:
@@ -657,7 +691,7 @@ class Qwen2VLB200:
                      decode_gbs=(w_bytes + kv_bytes) * n_loop / (dec_ms * 1e-3) / 1e9 if dec_ms > 0 else None,
                      graph_nodes=graph_nodes, graph_replays=replays)
         self.last_generate_stats = stats
-        self._last_decode_state = st   # kept for the parity tests (logits of the final step)
+        self._last_decode_state = st   # the cached decode state (parity tests read the final step's logits)
         if G2 > 0:
             res2 = torch.cat([prompt.expand(G2, -1), out[G1:]], dim=1)
             return (res1, res2, stats) if return_stats else (res1, res2)

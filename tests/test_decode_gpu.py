@@ -80,14 +80,15 @@ def test_dec_qkv_post_and_attention():
     assert torch.equal(kc[:, mask], kc0[:, mask]) and torch.equal(vc[:, mask], vc0[:, mask])
     # attention over two prompt caches + completion cache
     kp0, vp0, kp1, vp1 = (rnd((P, nkv * hd), s, 0.5) for s in (5, 6, 7, 8))
-    n_split = 4
+    import ctypes
     rep = nh // nkv
-    o_part = torch.empty((R, nkv, n_split, rep, hd), device="cuda", dtype=torch.float32)
-    ml = torch.empty((R, nkv, n_split, rep, 2), device="cuda", dtype=torch.float32)
     out = torch.zeros((16, nh * hd), device="cuda", dtype=torch.bfloat16)
     g0 = 4
-    ops.call("sb_dec_attn", q_out, kp0, vp0, kp1, vp1, g0, P, kc, vc, Cmax * nkv * hd, step_t, nh, nkv, hd,
-             hd ** -0.5, n_split, o_part, ml, out, R)
+    nws = ctypes.c_longlong(0)
+    assert ops._lib.load().sb_dec_attn_workspace(R, g0, P, Cmax, nh, nkv, ctypes.byref(nws)) == 0
+    ws = torch.empty(nws.value, device="cuda", dtype=torch.float32)
+    ops.call("sb_dec_attn", q_out, kp0, vp0, kp1, vp1, g0, P, kc, vc, Cmax * nkv * hd, Cmax, step_t, nh, nkv, hd,
+             hd ** -0.5, ws, ws.numel(), out, R)
     for r in range(R):
         kp, vp = (kp0, vp0) if r < g0 else (kp1, vp1)
         K = torch.cat([kp, kc[r, :step + 1]]).float().view(-1, nkv, hd).repeat_interleave(rep, 1)
@@ -96,6 +97,41 @@ def test_dec_qkv_post_and_attention():
         s = torch.einsum("hd,jhd->hj", qq, K) * hd ** -0.5
         ref = torch.einsum("hj,jhd->hd", torch.softmax(s, -1), V).reshape(-1)
         close(out[r], ref, 1e-2, f"attn row {r}")
+
+
+@pytest.mark.parametrize("R,g0,nh,nkv,P,Cmax,step", [
+    (12, 8, 28, 4, 2304, 512, 255),     # cfg3 shape: 8 + 4 rows, 7 q heads per kv head, 18 prompt splits
+    (12, 8, 28, 4, 2304, 512, 0),       # first decode step: one completion key
+    (12, 8, 28, 4, 2304, 512, 511),     # last slot
+    (24, 16, 12, 2, 832, 1024, 700),    # G=16 (+8): two 64-query blocks per (group, kv head), 8 completion splits
+    (3, 3, 4, 4, 70, 40, 5),            # one group, rep 1, ragged prompt tile
+    (5, 0, 8, 2, 130, 64, 63),          # every row in the second group
+])
+def test_dec_attention_shapes(R, g0, nh, nkv, P, Cmax, step):
+    import ctypes
+    from spacer_b200 import ops
+    hd = 128
+    rep = nh // nkv
+    RP = 16 if R <= 16 else 32
+    q = rnd((RP, nh * hd), 11, 1.0)
+    kp0, vp0, kp1, vp1 = (rnd((P, nkv * hd), s, 0.7) for s in (5, 6, 7, 8))
+    kc = rnd((R, Cmax, nkv * hd), 3, 0.7)
+    vc = rnd((R, Cmax, nkv * hd), 4, 0.7)
+    step_t = torch.tensor([step], dtype=torch.int32, device="cuda")
+    nws = ctypes.c_longlong(0)
+    assert ops._lib.load().sb_dec_attn_workspace(R, g0, P, Cmax, nh, nkv, ctypes.byref(nws)) == 0
+    ws = torch.full((nws.value,), float("nan"), device="cuda", dtype=torch.float32)
+    out = torch.zeros((RP, nh * hd), device="cuda", dtype=torch.bfloat16)
+    ops.call("sb_dec_attn", q, kp0, vp0, kp1, vp1, g0, P, kc, vc, Cmax * nkv * hd, Cmax, step_t, nh, nkv, hd,
+             hd ** -0.5, ws, ws.numel(), out, R)
+    for r in range(R):
+        kp, vp = (kp0, vp0) if r < g0 else (kp1, vp1)
+        K = torch.cat([kp, kc[r, :step + 1]]).float().view(-1, nkv, hd).repeat_interleave(rep, 1)
+        V = torch.cat([vp, vc[r, :step + 1]]).float().view(-1, nkv, hd).repeat_interleave(rep, 1)
+        s = torch.einsum("hd,jhd->hj", q[r].float().view(nh, hd), K) * hd ** -0.5
+        ref = torch.einsum("hj,jhd->hd", torch.softmax(s, -1), V).reshape(-1)
+        close(out[r], ref, 1e-2, f"attn row {r}")
+    assert torch.equal(out[R:], torch.zeros_like(out[R:]))
 
 
 def _expected_dist(logits, top_p, suppress=None):
@@ -123,7 +159,7 @@ def test_sampler_distribution(V, scale):
     ids = torch.zeros((R, n_draws), dtype=torch.int32, device="cuda")
     lp = torch.empty(R, dtype=torch.float32, device="cuda")
     for i in range(n_draws):
-        ops.call("sb_sample_top_p", logits, V, R, V, 0.95, 1234, step, None, toks, ids, n_draws, lp, -1, 0, 0)
+        ops.call("sb_sample_top_p", logits, V, R, V, 0.95, 1234, step, None, toks, ids, n_draws, lp, -1, 0, 0, None)
         ops.call("sb_step_advance", step)
     torch.cuda.synchronize()
     ids = ids.cpu().long()
@@ -147,8 +183,8 @@ def test_sampler_distribution(V, scale):
     a = torch.empty(R, dtype=torch.int32, device="cuda")
     b = torch.empty(R, dtype=torch.int32, device="cuda")
     step.zero_()
-    ops.call("sb_sample_top_p", logits, V, R, V, 0.95, 99, step, None, a, None, 0, None, -1, 0, 0)
-    ops.call("sb_sample_top_p", logits, V, R, V, 0.95, 99, step, None, b, None, 0, None, -1, 0, 0)
+    ops.call("sb_sample_top_p", logits, V, R, V, 0.95, 99, step, None, a, None, 0, None, -1, 0, 0, None)
+    ops.call("sb_sample_top_p", logits, V, R, V, 0.95, 99, step, None, b, None, 0, None, -1, 0, 0, None)
     assert torch.equal(a, b)
 
 
@@ -163,7 +199,7 @@ def test_sampler_kept_set_exact():
     toks = torch.empty(R, dtype=torch.int32, device="cuda")
     ids = torch.zeros((R, n), dtype=torch.int32, device="cuda")
     for i in range(n):
-        ops.call("sb_sample_top_p", logits, V, R, V, 0.95, 7, step, None, toks, ids, n, None, -1, 0, 0)
+        ops.call("sb_sample_top_p", logits, V, R, V, 0.95, 7, step, None, toks, ids, n, None, -1, 0, 0, None)
         ops.call("sb_step_advance", step)
     ids = ids.cpu().long()
     lv = logits.bfloat16().float().cpu()
@@ -185,13 +221,13 @@ def test_sampler_eos_and_finished():
     step = torch.zeros(1, dtype=torch.int32, device="cuda")
     fin = torch.tensor([0, 1, 0], dtype=torch.int32, device="cuda")
     toks = torch.empty(R, dtype=torch.int32, device="cuda")
-    ops.call("sb_sample_top_p", logits, V, R, V, 0.95, 1, step, fin, toks, None, 0, None, 5, 9, 0)
+    ops.call("sb_sample_top_p", logits, V, R, V, 0.95, 1, step, fin, toks, None, 0, None, 5, 9, 0, None)
     assert toks.tolist() == [5, 9, 5] and fin.tolist() == [1, 1, 1]
-    ops.call("sb_sample_top_p", logits, V, R, V, 0.95, 1, step, fin, toks, None, 0, None, 5, 9, 0)
+    ops.call("sb_sample_top_p", logits, V, R, V, 0.95, 1, step, fin, toks, None, 0, None, 5, 9, 0, None)
     assert toks.tolist() == [9, 9, 9]
     fin.zero_()
     logits[:, 6] = 19.0
-    ops.call("sb_sample_top_p", logits, V, R, V, 0.95, 1, step, fin, toks, None, 0, None, 5, 9, 1)  # EOS suppressed
+    ops.call("sb_sample_top_p", logits, V, R, V, 0.95, 1, step, fin, toks, None, 0, None, 5, 9, 1, None)  # EOS suppressed
     assert toks.tolist() == [6, 6, 6] and fin.tolist() == [0, 0, 0]
 
 
