@@ -135,11 +135,16 @@ typedef struct sb_attn_args {
   /* backward only */
   const void* d_o; long long lddo;
   float* delta;                                /* fp32 [n_heads][T] scratch                              */
-  float* dq_acc;                               /* fp32 [T][n_heads*head_dim], zeroed by the caller (+=)  */
+  void* dq; long long lddq;                    /* bf16 output, head h at column h*head_dim               */
   void* dk; void* dv; long long lddk, lddv;    /* bf16 outputs, kv head h at column h*head_dim           */
+  void* gqa_ws;                                /* bf16 scratch, sb_attn_bwd_workspace() elements (GQA)   */
+  int* tile_ws;                                /* int32 scratch, sb_attn_bwd_workspace() ints            */
 } sb_attn_args;
 int sb_attn_fwd(const sb_attn_args* args, sb_stream_t stream);
+/* deterministic (no atomics): a key-tile-major kernel produces dK, dV, a query-tile-major kernel produces dQ */
 int sb_attn_bwd(const sb_attn_args* args, sb_stream_t stream);
+int sb_attn_bwd_workspace(int T, int Tk, int n_heads, int n_kv_heads, int head_dim, long long* gqa_ws_elems,
+                          long long* tile_ws_ints);
 
 /* ------------------------------------------------------------------------------------------------
  * Decode step (q_len = 1): consumers of the split-K GEMV partials parts[s][r][n]

@@ -71,8 +71,10 @@ class AttnArgs(C.Structure):
         ("n_heads", C.c_int), ("n_kv_heads", C.c_int), ("head_dim", C.c_int),
         ("scale", C.c_float),
         ("d_o", C.c_void_p), ("lddo", C.c_longlong),
-        ("delta", C.c_void_p), ("dq_acc", C.c_void_p),
+        ("delta", C.c_void_p),
+        ("dq", C.c_void_p), ("lddq", C.c_longlong),
         ("dk", C.c_void_p), ("dv", C.c_void_p), ("lddk", C.c_longlong), ("lddv", C.c_longlong),
+        ("gqa_ws", C.c_void_p), ("tile_ws", C.c_void_p),
     ]
 
 

@@ -50,7 +50,6 @@ struct AttnParams {
   // backward
   const bf16* d_o; long long lddo;
   const float* delta;         // [n_heads][T]
-  float* dq_acc;              // fp32 [T][n_heads*HD]
   bf16* dk; bf16* dv; long long lddk, lddv;
 };
 
@@ -290,31 +289,63 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ o, long long ldo, con
   if (lane == 0) delta[(long long)h * T + t] = s;
 }
 
-// One CTA owns a 64-key tile of one kv head; it loops over the q heads of the group and over every
-// 32-query tile that can see the keys.  Each warp owns 16 keys: S^T = K Q^T, dV += P^T dO,
-// dP^T = V dO^T, dS^T = P^T o (dP^T - delta), dK += dS^T Q; dQ += dS K goes through smem + fp32 atomics.
-constexpr int BQB = 32;  // query rows per backward iteration
+// Backward in two kernels (no atomics, deterministic):
+//   attn_bwd_dkdv_kernel : one CTA per (64-key tile, q head); loops over the 64-query tiles that can see the keys.
+//                          Each warp owns 16 keys:  S^T = K Q^T,  P^T = exp(S^T - lse),  dV += P^T dO,
+//                          dP^T = V dO^T,  dS^T = P^T o (dP^T - delta),  dK += dS^T Q.
+//                          With GQA the per-q-head dK/dV go to an expanded [T][n_heads*HD] scratch and are summed
+//                          over the group by attn_gqa_reduce_kernel.
+//   attn_bwd_dq_kernel   : one CTA per (64-query tile, q head); loops over the visible key tiles like the forward:
+//                          S = Q K^T, P, dP = dO V^T, dS, dQ += dS K  (S and dP are recomputed: +2 GEMMs instead of
+//                          64x128 fp32 atomics per tile pair).
+// Visibility of a (query tile, key tile) pair is decided from per-query-tile bounds computed once per call.
+struct QTileBounds { int pmin, pmax, smin, smax, emin, emax, pad0, pad1; };
+
+__global__ void attn_qtile_bounds_kernel(const int4* __restrict__ meta, int T, QTileBounds* __restrict__ out) {
+  const int qt = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int q0 = qt * BQ;
+  if (q0 >= T) return;
+  const int lane = threadIdx.x & 31;
+  int pmin = 1 << 30, pmax = 0, smin = 1 << 30, smax = 0, emin = 1 << 30, emax = 0;
+  for (int i = lane; i < BQ && q0 + i < T; i += 32) {
+    const int4 m = meta[q0 + i];
+    pmin = min(pmin, m.x); pmax = max(pmax, m.x);
+    if (m.z > m.y) { smin = min(smin, m.y); emax = max(emax, m.z); }
+    smax = max(smax, m.y); emin = min(emin, m.z);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    pmin = min(pmin, __shfl_xor_sync(0xffffffffu, pmin, o)); pmax = max(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
+    smin = min(smin, __shfl_xor_sync(0xffffffffu, smin, o)); smax = max(smax, __shfl_xor_sync(0xffffffffu, smax, o));
+    emin = min(emin, __shfl_xor_sync(0xffffffffu, emin, o)); emax = max(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+  }
+  if (lane == 0) {
+    QTileBounds b;
+    b.pmin = pmin; b.pmax = pmax; b.smin = smin; b.smax = smax; b.emin = emin; b.emax = emax; b.pad0 = b.pad1 = 0;
+    out[qt] = b;
+  }
+}
 
 template <int HD>
 __global__ void __launch_bounds__(ATT_THREADS)
-attn_bwd_kernel(const AttnParams p) {
+attn_bwd_dkdv_kernel(const AttnParams p, const QTileBounds* __restrict__ qtb, bf16* __restrict__ dk_out,
+                     bf16* __restrict__ dv_out, long long ld_dk, long long ld_dv) {
   using S = Smem<HD>;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   bf16* sK = reinterpret_cast<bf16*>(smem_raw);          // [64][LD]
   bf16* sV = sK + S::TILE;                               // [64][LD]
-  bf16* sQ = sV + S::TILE;                               // 2 x [32][LD]
-  bf16* sdO = sQ + 2 * BQB * S::LD;                      // 2 x [32][LD]
-  bf16* sdS = sdO + 2 * BQB * S::LD;                     // [32 q][64+8 keys]
-  float* sLse = reinterpret_cast<float*>(sdS + BQB * 72);  // 2 x 32
-  float* sDelta = sLse + 2 * BQB;                         // 2 x 32
-  int* sMeta = reinterpret_cast<int*>(sDelta + 2 * BQB);  // 2 x 3 x 32
+  bf16* sQ = sV + S::TILE;                               // 2 x [64][LD]
+  bf16* sdO = sQ + 2 * S::TILE;                          // 2 x [64][LD]
+  float* sLse = reinterpret_cast<float*>(sdO + 2 * S::TILE);  // 2 x 64 (log2 domain)
+  float* sDelta = sLse + 2 * BQ;                          // 2 x 64
+  int* sMeta = reinterpret_cast<int*>(sDelta + 2 * BQ);   // 2 x 3 x 64
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t4 = lane & 3;
   const int j0 = blockIdx.x * BKV;
-  const int kvh = blockIdx.y;
-  const int rep = p.n_heads / p.n_kv_heads;
-  const float sc = p.scale;
+  const int hh = blockIdx.y;
+  const int kvh = hh / (p.n_heads / p.n_kv_heads);
+  const float sc2 = p.scale * 1.4426950408889634f;
 
   load_tile<HD>(smem_u32(sK), p.k + (long long)kvh * HD, p.ldk, j0, p.Tk, tid);
   load_tile<HD>(smem_u32(sV), p.v + (long long)kvh * HD, p.ldv, j0, p.Tk, tid);
@@ -328,197 +359,305 @@ attn_bwd_kernel(const AttnParams p) {
     dk_acc[i][0] = dk_acc[i][1] = dk_acc[i][2] = dk_acc[i][3] = 0.f;
     dv_acc[i][0] = dv_acc[i][1] = dv_acc[i][2] = dv_acc[i][3] = 0.f;
   }
+  const int n_qt = (p.T + BQ - 1) / BQ;
 
-  const int n_qt = (p.T + BQB - 1) / BQB;
-  const int total = n_qt * rep;   // iteration space: (q tile, head in group); q tile outer
-
-  auto issue = [&](int it, int b) {
-    const int qt = it / rep, hh = kvh * rep + it % rep;
-    const int q0 = qt * BQB;
-    constexpr int CH = HD / 8;
-    for (int i = tid; i < BQB * CH; i += ATT_THREADS) {
-      const int r = i / CH, c = i % CH;
-      const bool ok = (q0 + r) < p.T;
-      const long long row = ok ? (q0 + r) : 0;
-      cp_async16(smem_u32(sQ + b * BQB * S::LD + r * S::LD + c * 8), p.q + row * p.ldq + (long long)hh * HD + c * 8, ok);
-      cp_async16(smem_u32(sdO + b * BQB * S::LD + r * S::LD + c * 8), p.d_o + row * p.lddo + (long long)hh * HD + c * 8, ok);
-    }
-    if (tid < BQB) {
+  auto issue = [&](int qt, int b) {
+    const int q0 = qt * BQ;
+    load_tile<HD>(smem_u32(sQ + b * S::TILE), p.q + (long long)hh * HD, p.ldq, q0, p.T, tid);
+    load_tile<HD>(smem_u32(sdO + b * S::TILE), p.d_o + (long long)hh * HD, p.lddo, q0, p.T, tid);
+    if (tid < BQ) {
       const bool ok = (q0 + tid) < p.T;
-      sLse[b * BQB + tid] = ok ? p.lse[(long long)hh * p.T + q0 + tid] : 0.f;
-      sDelta[b * BQB + tid] = ok ? p.delta[(long long)hh * p.T + q0 + tid] : 0.f;
+      sLse[b * BQ + tid] = ok ? p.lse[(long long)hh * p.T + q0 + tid] * 1.4426950408889634f : 0.f;
+      sDelta[b * BQ + tid] = ok ? p.delta[(long long)hh * p.T + q0 + tid] : 0.f;
       int4 m = make_int4(0, 0, 0, 0);
       if (ok) m = p.meta[q0 + tid];
-      sMeta[b * 96 + tid] = m.x; sMeta[b * 96 + 32 + tid] = m.y; sMeta[b * 96 + 64 + tid] = m.z;
+      sMeta[b * 192 + tid] = m.x; sMeta[b * 192 + 64 + tid] = m.y; sMeta[b * 192 + 128 + tid] = m.z;
     }
   };
-  // a q tile can see this key tile iff some row has prefix_len > j0 or an own range intersecting it.
-  // Cheap conservative host-free test using the tile's first/last rows is not enough for general metas,
-  // so the relevance test reads the meta of all 32 rows (L2-resident, tiny).
-  auto relevant = [&](int qt) -> bool {
-    const int q0 = qt * BQB;
-    bool r = false;
-    for (int i = 0; i < BQB && q0 + i < p.T; ++i) {
-      const int4 m = p.meta[q0 + i];
-      r |= (j0 < m.x) || (j0 + BKV > m.y && j0 < m.z && m.z > m.y);
+  auto next_qt = [&](int qt) -> int {
+    while (qt < n_qt) {
+      const QTileBounds b = qtb[qt];
+      if ((j0 < b.pmax) || (j0 + BKV > b.smin && j0 < b.emax)) return qt;
+      ++qt;
     }
-    return r;
-  };
-  auto next_it = [&](int it) -> int {
-    while (it < total) {
-      if (relevant(it / rep)) return it;
-      it = (it / rep + 1) * rep;  // skip the whole q tile
-    }
-    return total;
+    return n_qt;
   };
 
-  int it = next_it(0);
+  int qt = next_qt(0);
   int buf = 0;
-  if (it < total) issue(it, 0);
+  if (qt < n_qt) issue(qt, 0);
   cp_async_commit();
 
-  while (it < total) {
-    const int itn = ((it + 1) % rep == 0) ? next_it(it + 1) : it + 1;
-    if (itn < total) issue(itn, buf ^ 1);
+  while (qt < n_qt) {
+    const int qn = next_qt(qt + 1);
+    if (qn < n_qt) issue(qn, buf ^ 1);
     cp_async_commit();
     cp_async_wait<1>();
     __syncthreads();
 
-    const int qt = it / rep, hh = kvh * rep + it % rep;
-    const int q0 = qt * BQB;
-    const bf16* cQ = sQ + buf * BQB * S::LD;
-    const bf16* cdO = sdO + buf * BQB * S::LD;
-    const float* cL = sLse + buf * BQB;
-    const float* cD = sDelta + buf * BQB;
-    const int* cM = sMeta + buf * 96;
+    const int q0 = qt * BQ;
+    const bf16* cQ = sQ + buf * S::TILE;
+    const bf16* cdO = sdO + buf * S::TILE;
+    const float* cL = sLse + buf * BQ;
+    const float* cD = sDelta + buf * BQ;
+    const int* cM = sMeta + buf * 192;
+    const QTileBounds tb = qtb[qt];
+    const bool full = ((j0 + BKV <= tb.pmin) || (j0 >= tb.smax && j0 + BKV <= tb.emin)) && (j0 + BKV <= p.Tk) &&
+                      (q0 + BQ <= p.T);
 
-    // S^T [16 keys x 32 q] = K_w Q^T ; dP^T = V_w dO^T
-    float st[4][4], dp[4][4];
+#pragma unroll 1
+    for (int hf = 0; hf < 2; ++hf) {   // two halves of 32 queries: keeps S^T / dP^T at 16 registers each
+      const int qh = hf * 32;
+      float st[4][4], dp[4][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f;
-      dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
-    }
-#pragma unroll
-    for (int ks = 0; ks < KS; ++ks) {
-      uint32_t ka[4], va[4];
-      const int arow = warp * 16 + (lane & 15), acol = ks * 16 + (lane >> 4) * 8;
-      ldsm_x4(smem_u32(sK + arow * S::LD + acol), ka[0], ka[1], ka[2], ka[3]);
-      ldsm_x4(smem_u32(sV + arow * S::LD + acol), va[0], va[1], va[2], va[3]);
-#pragma unroll
-      for (int np = 0; np < 2; ++np) {
-        uint32_t b0, b1, b2, b3;
-        const int brow = np * 16 + (lane & 7) + (lane >> 4) * 8, bcol = ks * 16 + ((lane >> 3) & 1) * 8;
-        ldsm_x4(smem_u32(cQ + brow * S::LD + bcol), b0, b1, b2, b3);
-        mma16816(st[np * 2], ka, b0, b1);
-        mma16816(st[np * 2 + 1], ka, b2, b3);
-        ldsm_x4(smem_u32(cdO + brow * S::LD + bcol), b0, b1, b2, b3);
-        mma16816(dp[np * 2], va, b0, b1);
-        mma16816(dp[np * 2 + 1], va, b2, b3);
+      for (int i = 0; i < 4; ++i) {
+        st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f;
+        dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
       }
-    }
-    // P^T, dS^T
-    uint32_t pf[2][4], dsf[2][4];
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      float pv[4], dsv[4];
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t ka[4], va[4];
+        const int arow = warp * 16 + (lane & 15), acol = ks * 16 + (lane >> 4) * 8;
+        ldsm_x4(smem_u32(sK + arow * S::LD + acol), ka[0], ka[1], ka[2], ka[3]);
+        ldsm_x4(smem_u32(sV + arow * S::LD + acol), va[0], va[1], va[2], va[3]);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int ql = nt * 8 + t4 * 2 + (e & 1);       // query within tile
-        const int key = j0 + warp * 16 + g + (e >= 2 ? 8 : 0);
-        const int pre = cM[ql], s0 = cM[32 + ql], en = cM[64 + ql];
-        const bool vis = (q0 + ql < p.T) && (key < p.Tk) && ((key < pre) || (key >= s0 && key < en));
-        const float pr = vis ? __expf(st[nt][e] * sc - cL[ql]) : 0.f;
-        pv[e] = pr;
-        dsv[e] = pr * (dp[nt][e] - cD[ql]);
-      }
-      // accumulator (rows = keys g/g+8, cols = q) -> A fragment of a 16(keys) x 16(q) block
-      pf[nt >> 1][(nt & 1) * 2] = pack_bf16(pv[0], pv[1]);
-      pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(pv[2], pv[3]);
-      dsf[nt >> 1][(nt & 1) * 2] = pack_bf16(dsv[0], dsv[1]);
-      dsf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(dsv[2], dsv[3]);
-      // dS (not transposed) to smem for the dQ product: sdS[q][key]
-      const int kl = warp * 16 + g;
-      sdS[(nt * 8 + t4 * 2) * 72 + kl] = __float2bfloat16_rn(dsv[0]);
-      sdS[(nt * 8 + t4 * 2 + 1) * 72 + kl] = __float2bfloat16_rn(dsv[1]);
-      sdS[(nt * 8 + t4 * 2) * 72 + kl + 8] = __float2bfloat16_rn(dsv[2]);
-      sdS[(nt * 8 + t4 * 2 + 1) * 72 + kl + 8] = __float2bfloat16_rn(dsv[3]);
-    }
-    // dV += P^T dO ; dK += dS^T Q     (k = 32 queries = 2 k-steps; B from [q][d] smem via .trans)
-#pragma unroll
-    for (int kk = 0; kk < 2; ++kk) {
-#pragma unroll
-      for (int dpair = 0; dpair < ND / 2; ++dpair) {
-        uint32_t b0, b1, b2, b3;
-        const int brow = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, bcol = dpair * 16 + (lane >> 4) * 8;
-        ldsm_x4_t(smem_u32(cdO + brow * S::LD + bcol), b0, b1, b2, b3);
-        mma16816(dv_acc[dpair * 2], pf[kk], b0, b1);
-        mma16816(dv_acc[dpair * 2 + 1], pf[kk], b2, b3);
-        ldsm_x4_t(smem_u32(cQ + brow * S::LD + bcol), b0, b1, b2, b3);
-        mma16816(dk_acc[dpair * 2], dsf[kk], b0, b1);
-        mma16816(dk_acc[dpair * 2 + 1], dsf[kk], b2, b3);
-      }
-    }
-    __syncthreads();  // sdS complete
-    // dQ [32 q x HD] += dS [32 x 64 keys] K [64 x HD]; warp w: q rows (w&1)*16.., head-dim half (w>>1)
-    {
-      const int qr = (warp & 1) * 16;
-      constexpr int NH = ND / 2;            // n-tiles per head-dim half
-      const int dbase = (warp >> 1) * (HD / 2);
-      float dq[NH][4];
-#pragma unroll
-      for (int i = 0; i < NH; ++i) { dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f; }
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        uint32_t a[4];
-        ldsm_x4(smem_u32(sdS + (qr + (lane & 15)) * 72 + kk * 16 + (lane >> 4) * 8), a[0], a[1], a[2], a[3]);
-#pragma unroll
-        for (int i = 0; i < NH; i += 2) {
+        for (int np = 0; np < 2; ++np) {
           uint32_t b0, b1, b2, b3;
-          const int brow = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, bcol = dbase + i * 8 + (lane >> 4) * 8;
-          if (i + 1 < NH) {
-            ldsm_x4_t(smem_u32(sK + brow * S::LD + bcol), b0, b1, b2, b3);
-            mma16816(dq[i], a, b0, b1);
-            mma16816(dq[i + 1], a, b2, b3);
-          } else {
-            // odd tail (HD=80: 5 n-tiles per half): x4 load would run past the half; use the first pair only
-            ldsm_x4_t(smem_u32(sK + brow * S::LD + (bcol - (lane >> 4) * 8)), b0, b1, b2, b3);
-            mma16816(dq[i], a, b0, b1);
-          }
+          const int brow = qh + np * 16 + (lane & 7) + (lane >> 4) * 8, bcol = ks * 16 + ((lane >> 3) & 1) * 8;
+          ldsm_x4(smem_u32(cQ + brow * S::LD + bcol), b0, b1, b2, b3);
+          mma16816(st[np * 2], ka, b0, b1);
+          mma16816(st[np * 2 + 1], ka, b2, b3);
+          ldsm_x4(smem_u32(cdO + brow * S::LD + bcol), b0, b1, b2, b3);
+          mma16816(dp[np * 2], va, b0, b1);
+          mma16816(dp[np * 2 + 1], va, b2, b3);
         }
       }
+      uint32_t pf[2][4], dsf[2][4];
 #pragma unroll
-      for (int i = 0; i < NH; ++i) {
-        const int col = hh * HD + dbase + i * 8 + t4 * 2;
-        const int r_lo = q0 + qr + g, r_hi = r_lo + 8;
-        if (r_lo < p.T) {
-          atomicAdd(p.dq_acc + (long long)r_lo * p.n_heads * HD + col, dq[i][0] * sc);
-          atomicAdd(p.dq_acc + (long long)r_lo * p.n_heads * HD + col + 1, dq[i][1] * sc);
+      for (int nt = 0; nt < 4; ++nt) {
+        float pv[4], dsv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int ql = qh + nt * 8 + t4 * 2 + (e & 1);
+          bool vis = true;
+          if (!full) {
+            const int key = j0 + warp * 16 + g + (e >= 2 ? 8 : 0);
+            const int pre = cM[ql], s0 = cM[64 + ql], en = cM[128 + ql];
+            vis = (q0 + ql < p.T) && (key < p.Tk) && ((key < pre) || (key >= s0 && key < en));
+          }
+          const float pr = vis ? exp2f(st[nt][e] * sc2 - cL[ql]) : 0.f;
+          pv[e] = pr;
+          dsv[e] = pr * (dp[nt][e] - cD[ql]);
         }
-        if (r_hi < p.T) {
-          atomicAdd(p.dq_acc + (long long)r_hi * p.n_heads * HD + col, dq[i][2] * sc);
-          atomicAdd(p.dq_acc + (long long)r_hi * p.n_heads * HD + col + 1, dq[i][3] * sc);
+        pf[nt >> 1][(nt & 1) * 2] = pack_bf16(pv[0], pv[1]);
+        pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(pv[2], pv[3]);
+        dsf[nt >> 1][(nt & 1) * 2] = pack_bf16(dsv[0], dsv[1]);
+        dsf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(dsv[2], dsv[3]);
+      }
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll
+        for (int dpair = 0; dpair < ND / 2; ++dpair) {
+          uint32_t b0, b1, b2, b3;
+          const int brow = qh + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, bcol = dpair * 16 + (lane >> 4) * 8;
+          ldsm_x4_t(smem_u32(cdO + brow * S::LD + bcol), b0, b1, b2, b3);
+          mma16816(dv_acc[dpair * 2], pf[kk], b0, b1);
+          mma16816(dv_acc[dpair * 2 + 1], pf[kk], b2, b3);
+          ldsm_x4_t(smem_u32(cQ + brow * S::LD + bcol), b0, b1, b2, b3);
+          mma16816(dk_acc[dpair * 2], dsf[kk], b0, b1);
+          mma16816(dk_acc[dpair * 2 + 1], dsf[kk], b2, b3);
         }
       }
     }
     __syncthreads();
     buf ^= 1;
-    it = itn;
+    qt = qn;
   }
   cp_async_wait<0>();
 
   const int k_lo = j0 + warp * 16 + g, k_hi = k_lo + 8;
 #pragma unroll
   for (int i = 0; i < ND; ++i) {
-    const int col = kvh * HD + i * 8 + t4 * 2;
+    const int col = hh * HD + i * 8 + t4 * 2;   // q-head column (== kv-head column when there is no GQA)
     if (k_lo < p.Tk) {
-      *reinterpret_cast<uint32_t*>(p.dk + (long long)k_lo * p.lddk + col) = pack_bf16(dk_acc[i][0] * sc, dk_acc[i][1] * sc);
-      *reinterpret_cast<uint32_t*>(p.dv + (long long)k_lo * p.lddv + col) = pack_bf16(dv_acc[i][0], dv_acc[i][1]);
+      *reinterpret_cast<uint32_t*>(dk_out + (long long)k_lo * ld_dk + col) = pack_bf16(dk_acc[i][0] * p.scale, dk_acc[i][1] * p.scale);
+      *reinterpret_cast<uint32_t*>(dv_out + (long long)k_lo * ld_dv + col) = pack_bf16(dv_acc[i][0], dv_acc[i][1]);
     }
     if (k_hi < p.Tk) {
-      *reinterpret_cast<uint32_t*>(p.dk + (long long)k_hi * p.lddk + col) = pack_bf16(dk_acc[i][2] * sc, dk_acc[i][3] * sc);
-      *reinterpret_cast<uint32_t*>(p.dv + (long long)k_hi * p.lddv + col) = pack_bf16(dv_acc[i][2], dv_acc[i][3]);
+      *reinterpret_cast<uint32_t*>(dk_out + (long long)k_hi * ld_dk + col) = pack_bf16(dk_acc[i][2] * p.scale, dk_acc[i][3] * p.scale);
+      *reinterpret_cast<uint32_t*>(dv_out + (long long)k_hi * ld_dv + col) = pack_bf16(dv_acc[i][2], dv_acc[i][3]);
     }
+  }
+}
+
+// dk[t][kvh*HD + d] = sum over the q heads of the group of the expanded per-head gradients (fp32 sum)
+template <int HD>
+__global__ void attn_gqa_reduce_kernel(const bf16* __restrict__ xk, const bf16* __restrict__ xv, long long ldx, int rep,
+                                       bf16* __restrict__ dk, bf16* __restrict__ dv, long long lddk, long long lddv,
+                                       int Tk, int nkv) {
+  constexpr int CH = HD / 8;
+  const long long total = (long long)Tk * nkv * CH;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = idx % CH;
+    const int kvh = (idx / CH) % nkv;
+    const long long t = idx / ((long long)CH * nkv);
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      const bf16* src = (which ? xv : xk) + t * ldx + (long long)kvh * rep * HD + c * 8;
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int h = 0; h < rep; ++h) {
+        const uint4 u = *reinterpret_cast<const uint4*>(src + (long long)h * HD);
+        const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
+        acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += cc.x; acc[5] += cc.y; acc[6] += d.x; acc[7] += d.y;
+      }
+      uint4 o;
+      o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]);
+      o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
+      bf16* dst = (which ? dv + t * lddv : dk + t * lddk) + (long long)kvh * HD + c * 8;
+      *reinterpret_cast<uint4*>(dst) = o;
+    }
+  }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(ATT_THREADS)
+attn_bwd_dq_kernel(const AttnParams p, bf16* __restrict__ dq_out, long long ld_dq) {
+  using S = Smem<HD>;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  bf16* sQ = reinterpret_cast<bf16*>(smem_raw);
+  bf16* sdO = sQ + S::TILE;
+  bf16* sK = sdO + S::TILE;          // 2 buffers
+  bf16* sV = sK + 2 * S::TILE;       // 2 buffers
+  int* sMeta = reinterpret_cast<int*>(sV + 2 * S::TILE);  // 192 ints
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int q0 = blockIdx.x * BQ;
+  const int head = blockIdx.y;
+  const int kvh = head / (p.n_heads / p.n_kv_heads);
+  const bf16* kg = p.k + (long long)kvh * HD;
+  const bf16* vg = p.v + (long long)kvh * HD;
+
+  const TileBounds tb = tile_bounds(p.meta, q0, p.T, sMeta, tid);
+  const int r_lo = warp * 16 + g, r_hi = r_lo + 8;
+  const int pre_lo = sMeta[r_lo], st_lo = sMeta[64 + r_lo], en_lo = sMeta[128 + r_lo];
+  const int pre_hi = sMeta[r_hi], st_hi = sMeta[64 + r_hi], en_hi = sMeta[128 + r_hi];
+  const int row_lo = q0 + r_lo, row_hi = q0 + r_hi;
+  const float L2E = 1.4426950408889634f;
+  const float lse_lo = row_lo < p.T ? p.lse[(long long)head * p.T + row_lo] * L2E : 0.f;
+  const float lse_hi = row_hi < p.T ? p.lse[(long long)head * p.T + row_hi] * L2E : 0.f;
+  const float dl_lo = row_lo < p.T ? p.delta[(long long)head * p.T + row_lo] : 0.f;
+  const float dl_hi = row_hi < p.T ? p.delta[(long long)head * p.T + row_hi] : 0.f;
+  const int n_tiles = (min(max(tb.pmax, tb.emax), p.Tk) + BKV - 1) / BKV;
+
+  load_tile<HD>(smem_u32(sQ), p.q + (long long)head * HD, p.ldq, q0, p.T, tid);
+  load_tile<HD>(smem_u32(sdO), p.d_o + (long long)head * HD, p.lddo, q0, p.T, tid);
+  int jt = next_kv_tile(tb, 0, n_tiles);
+  if (jt < n_tiles) {
+    load_tile<HD>(smem_u32(sK), kg, p.ldk, jt * BKV, p.Tk, tid);
+    load_tile<HD>(smem_u32(sV), vg, p.ldv, jt * BKV, p.Tk, tid);
+  }
+  cp_async_commit();
+
+  constexpr int KS = HD / 16;
+  constexpr int NO = HD / 8;
+  uint32_t qf[KS][4];
+  float dq_acc[NO][4];
+#pragma unroll
+  for (int i = 0; i < NO; ++i) { dq_acc[i][0] = dq_acc[i][1] = dq_acc[i][2] = dq_acc[i][3] = 0.f; }
+  const float sc2 = p.scale * L2E;
+
+  int buf = 0;
+  bool q_loaded = false;
+  while (jt < n_tiles) {
+    const int jn = next_kv_tile(tb, jt + 1, n_tiles);
+    if (jn < n_tiles) {
+      load_tile<HD>(smem_u32(sK + (buf ^ 1) * S::TILE), kg, p.ldk, jn * BKV, p.Tk, tid);
+      load_tile<HD>(smem_u32(sV + (buf ^ 1) * S::TILE), vg, p.ldv, jn * BKV, p.Tk, tid);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    if (!q_loaded) {
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks)
+        ldsm_x4(smem_u32(sQ + (warp * 16 + (lane & 15)) * S::LD + ks * 16 + (lane >> 4) * 8), qf[ks][0], qf[ks][1],
+                qf[ks][2], qf[ks][3]);
+      q_loaded = true;
+    }
+    const bf16* cK = sK + buf * S::TILE;
+    const bf16* cV = sV + buf * S::TILE;
+    const int j0 = jt * BKV;
+    const bool full = kv_tile_full(tb, j0) && (j0 + BKV <= p.Tk);
+#pragma unroll 1
+    for (int hf = 0; hf < 2; ++hf) {   // two halves of 32 keys
+      const int kh = hf * 32;
+      float s[4][4], dp[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+        dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
+      }
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t da[4];
+        ldsm_x4(smem_u32(sdO + (warp * 16 + (lane & 15)) * S::LD + ks * 16 + (lane >> 4) * 8), da[0], da[1], da[2], da[3]);
+#pragma unroll
+        for (int np = 0; np < 2; ++np) {
+          uint32_t b0, b1, b2, b3;
+          const int brow = kh + np * 16 + (lane & 7) + (lane >> 4) * 8, bcol = ks * 16 + ((lane >> 3) & 1) * 8;
+          ldsm_x4(smem_u32(cK + brow * S::LD + bcol), b0, b1, b2, b3);
+          mma16816(s[np * 2], qf[ks], b0, b1);
+          mma16816(s[np * 2 + 1], qf[ks], b2, b3);
+          ldsm_x4(smem_u32(cV + brow * S::LD + bcol), b0, b1, b2, b3);
+          mma16816(dp[np * 2], da, b0, b1);
+          mma16816(dp[np * 2 + 1], da, b2, b3);
+        }
+      }
+      uint32_t dsf[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        float dsv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const bool hi = e >= 2;
+          bool vis = true;
+          if (!full) {
+            const int j = j0 + kh + nt * 8 + t4 * 2 + (e & 1);
+            const int pre = hi ? pre_hi : pre_lo, st = hi ? st_hi : st_lo, en = hi ? en_hi : en_lo;
+            vis = (j < p.Tk) && ((j < pre) || (j >= st && j < en));
+          }
+          const float pr = vis ? exp2f(s[nt][e] * sc2 - (hi ? lse_hi : lse_lo)) : 0.f;
+          dsv[e] = pr * (dp[nt][e] - (hi ? dl_hi : dl_lo));
+        }
+        dsf[nt >> 1][(nt & 1) * 2] = pack_bf16(dsv[0], dsv[1]);
+        dsf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(dsv[2], dsv[3]);
+      }
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll
+        for (int dpr = 0; dpr < NO / 2; ++dpr) {
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4_t(smem_u32(cK + (kh + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * S::LD + dpr * 16 + (lane >> 4) * 8),
+                    b0, b1, b2, b3);
+          mma16816(dq_acc[dpr * 2], dsf[kk], b0, b1);
+          mma16816(dq_acc[dpr * 2 + 1], dsf[kk], b2, b3);
+        }
+      }
+    }
+    __syncthreads();
+    buf ^= 1;
+    jt = jn;
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int i = 0; i < NO; ++i) {
+    const int col = head * HD + i * 8 + t4 * 2;
+    if (row_lo < p.T)
+      *reinterpret_cast<uint32_t*>(dq_out + (long long)row_lo * ld_dq + col) = pack_bf16(dq_acc[i][0] * p.scale, dq_acc[i][1] * p.scale);
+    if (row_hi < p.T)
+      *reinterpret_cast<uint32_t*>(dq_out + (long long)row_hi * ld_dq + col) = pack_bf16(dq_acc[i][2] * p.scale, dq_acc[i][3] * p.scale);
   }
 }
 
@@ -541,9 +680,9 @@ __global__ void f32_to_bf16_strided_kernel(const float* __restrict__ src, bf16* 
 template <int HD>
 size_t fwd_smem() { return (size_t)5 * Smem<HD>::TILE * 2 + 192 * 4; }
 template <int HD>
-size_t bwd_smem() {
-  return (size_t)(2 * Smem<HD>::TILE + 4 * BQB * Smem<HD>::LD + BQB * 72) * 2 + (4 * BQB) * 4 + 2 * 96 * 4;
-}
+size_t bwd_dkdv_smem() { return (size_t)6 * Smem<HD>::TILE * 2 + (4 * BQ) * 4 + 2 * 192 * 4; }
+template <int HD>
+size_t bwd_dq_smem() { return (size_t)6 * Smem<HD>::TILE * 2 + 192 * 4; }
 
 template <int HD>
 int launch_fwd(const AttnParams& p, cudaStream_t st) {
@@ -558,18 +697,40 @@ int launch_fwd(const AttnParams& p, cudaStream_t st) {
 }
 
 template <int HD>
-int launch_bwd(const AttnParams& p, cudaStream_t st) {
+int launch_bwd(const AttnParams& p, bf16* dq, long long lddq, bf16* gqa_ws, int* tile_ws, cudaStream_t st) {
   static bool done = false;
   if (!done) {
-    SB_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem<HD>()));
+    SB_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_dkdv_smem<HD>()));
+    SB_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_dq_smem<HD>()));
     done = true;
   }
   const long long items = (long long)p.T * p.n_heads;
   attn_delta_kernel<HD><<<(unsigned)((items + 7) / 8), 256, 0, st>>>(p.o, p.ldo, p.d_o, p.lddo, const_cast<float*>(p.delta), p.T, p.n_heads);
   if (sb_check_launch("sb_attn_bwd(delta)")) return 1;
-  dim3 grid((p.Tk + BKV - 1) / BKV, p.n_kv_heads);
-  attn_bwd_kernel<HD><<<grid, ATT_THREADS, bwd_smem<HD>(), st>>>(p);
-  return sb_check_launch("sb_attn_bwd");
+  const int n_qt = (p.T + BQ - 1) / BQ;
+  QTileBounds* qtb = reinterpret_cast<QTileBounds*>(tile_ws);
+  attn_qtile_bounds_kernel<<<(n_qt + 3) / 4, 128, 0, st>>>(p.meta, p.T, qtb);
+  if (sb_check_launch("sb_attn_bwd(bounds)")) return 1;
+  const int rep = p.n_heads / p.n_kv_heads;
+  const long long ldx = (long long)p.n_heads * HD;
+  bf16* xk = rep > 1 ? gqa_ws : p.dk;
+  bf16* xv = rep > 1 ? gqa_ws + (long long)p.Tk * ldx : p.dv;
+  dim3 grid_kv((p.Tk + BKV - 1) / BKV, p.n_heads);
+  // head offset folded into the output pointers: per-q-head columns in the expanded scratch, kv-head columns otherwise
+  // (rep == 1: q head == kv head)
+  attn_bwd_dkdv_kernel<HD><<<grid_kv, ATT_THREADS, bwd_dkdv_smem<HD>(), st>>>(p, qtb, xk, xv, rep > 1 ? ldx : p.lddk,
+                                                                              rep > 1 ? ldx : p.lddv);
+  if (sb_check_launch("sb_attn_bwd(dkdv)")) return 1;
+  if (rep > 1) {
+    const long long total = (long long)p.Tk * p.n_kv_heads * (HD / 8);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    attn_gqa_reduce_kernel<HD><<<blocks, 256, 0, st>>>(xk, xv, ldx, rep, p.dk, p.dv, p.lddk, p.lddv, p.Tk, p.n_kv_heads);
+    if (sb_check_launch("sb_attn_bwd(gqa reduce)")) return 1;
+  }
+  dim3 grid_q((p.T + BQ - 1) / BQ, p.n_heads);
+  attn_bwd_dq_kernel<HD><<<grid_q, ATT_THREADS, bwd_dq_smem<HD>(), st>>>(p, dq, lddq);
+  return sb_check_launch("sb_attn_bwd(dq)");
 }
 
 }  // namespace
@@ -591,21 +752,31 @@ extern "C" int sb_attn_fwd(const sb_attn_args* a, sb_stream_t stream) {
   return 1;
 }
 
+extern "C" int sb_attn_bwd_workspace(int T, int Tk, int n_heads, int n_kv_heads, int head_dim, long long* gqa_ws_elems,
+                                     long long* tile_ws_ints) {
+  SB_REQUIRE(gqa_ws_elems && tile_ws_ints && T > 0 && n_heads > 0 && n_kv_heads > 0, "sb_attn_bwd_workspace: bad arguments");
+  if (Tk <= 0) Tk = T;
+  *gqa_ws_elems = n_heads != n_kv_heads ? 2LL * Tk * n_heads * head_dim : 0;
+  *tile_ws_ints = (long long)((T + BQ - 1) / BQ) * 8;
+  return 0;
+}
+
 extern "C" int sb_attn_bwd(const sb_attn_args* a, sb_stream_t stream) {
-  SB_REQUIRE(a && a->q && a->k && a->v && a->o && a->meta && a->lse && a->d_o && a->delta && a->dq_acc && a->dk && a->dv,
-             "sb_attn_bwd: null pointer");
+  SB_REQUIRE(a && a->q && a->k && a->v && a->o && a->meta && a->lse && a->d_o && a->delta && a->dq && a->dk && a->dv &&
+                 a->tile_ws, "sb_attn_bwd: null pointer");
   SB_REQUIRE(a->T > 0 && a->n_heads % a->n_kv_heads == 0, "sb_attn_bwd: bad sizes");
+  SB_REQUIRE(a->n_heads == a->n_kv_heads || a->gqa_ws, "sb_attn_bwd: GQA needs the gqa_ws scratch (sb_attn_bwd_workspace)");
   AttnParams p{};
   p.q = (const bf16*)a->q; p.k = (const bf16*)a->k; p.v = (const bf16*)a->v;
   p.ldq = a->ldq; p.ldk = a->ldk; p.ldv = a->ldv;
   p.o = (bf16*)a->o; p.ldo = a->ldo; p.lse = a->lse; p.meta = (const int4*)a->meta;
   p.T = a->T; p.Tk = a->Tk > 0 ? a->Tk : a->T; p.n_heads = a->n_heads; p.n_kv_heads = a->n_kv_heads;
   p.scale = a->scale;
-  p.d_o = (const bf16*)a->d_o; p.lddo = a->lddo; p.delta = a->delta; p.dq_acc = a->dq_acc;
+  p.d_o = (const bf16*)a->d_o; p.lddo = a->lddo; p.delta = a->delta;
   p.dk = (bf16*)a->dk; p.dv = (bf16*)a->dv; p.lddk = a->lddk; p.lddv = a->lddv;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (a->head_dim == 128) return launch_bwd<128>(p, st);
-  if (a->head_dim == 80) return launch_bwd<80>(p, st);
+  if (a->head_dim == 128) return launch_bwd<128>(p, (bf16*)a->dq, a->lddq, (bf16*)a->gqa_ws, a->tile_ws, st);
+  if (a->head_dim == 80) return launch_bwd<80>(p, (bf16*)a->dq, a->lddq, (bf16*)a->gqa_ws, a->tile_ws, st);
   sb_set_error("sb_attn_bwd: head_dim %d not supported (80 or 128)", a->head_dim);
   return 1;
 }

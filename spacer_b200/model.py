@@ -336,7 +336,6 @@ class Qwen2VLB200:
         d_h = torch.empty((T, H), device=self.device, dtype=BF16)
         d_a = torch.empty((T, nq), device=self.device, dtype=BF16)
         d_qkv = torch.empty((T, d.qkv_dim), device=self.device, dtype=BF16)
-        dq_acc = torch.empty((T, nq), device=self.device, dtype=F32)
         delta = torch.empty((nh, T), device=self.device, dtype=F32)
         for i in reversed(range(d.layers)):
             p = f"l.{i}."
@@ -352,7 +351,7 @@ class Qwen2VLB200:
             ops.gemm(dx2, t["a"], a_mn=True, b_mn=True, out=G[p + "o_w"])
             qkv = t["qkv"]
             ops.attn_bwd(qkv[:, :nq], qkv[:, nq:nq + nk], qkv[:, nq + nk:], t["a"], t["lse"], d_a, tape["meta"], nh, nkv,
-                         hd, d_qkv[:, :nq], d_qkv[:, nq:nq + nk], d_qkv[:, nq + nk:], dq_acc=dq_acc, delta=delta)
+                         hd, d_qkv[:, :nq], d_qkv[:, nq:nq + nk], d_qkv[:, nq + nk:], delta=delta)
             ops.mrope(d_qkv, tape["pos"], nh, nkv, hd, d.rope_theta, d.mrope_section, inverse=True)
             ops.call("sb_colsum", d_qkv, G[p + "qkv_b"], T, d.qkv_dim, d.qkv_dim)
             ops.rmsnorm_fwd(t["x"], W[p + "ln1_w"], d.rms_eps, out=h)

@@ -198,22 +198,40 @@ def attn_fwd(q, k, v, meta, n_heads, n_kv_heads, head_dim, scale=None, out=None,
     return (o, lse) if save_lse else o
 
 
+_attn_ws = {}
+
+
+def attn_bwd_workspace(T, n_heads, n_kv_heads, head_dim, device):
+    """(gqa scratch bf16, tile scratch int32) for sb_attn_bwd, cached per shape (the kernels are stream-ordered)."""
+    key = (T, n_heads, n_kv_heads, head_dim, str(device))
+    ws = _attn_ws.get(key)
+    if ws is None:
+        a, b = C.c_longlong(0), C.c_longlong(0)
+        check(_lib.load().sb_attn_bwd_workspace(T, T, n_heads, n_kv_heads, head_dim, C.byref(a), C.byref(b)),
+              "sb_attn_bwd_workspace")
+        gqa = torch.empty(a.value, device=device, dtype=torch.bfloat16) if a.value else None
+        ws = (gqa, torch.empty(b.value, device=device, dtype=torch.int32))
+        _attn_ws.clear()          # one shape at a time: the scratch is as large as two activation tensors
+        _attn_ws[key] = ws
+    return ws
+
+
 def attn_bwd(q, k, v, o, lse, d_o, meta, n_heads, n_kv_heads, head_dim, dq_out, dk_out, dv_out, scale=None,
-             dq_acc=None, delta=None):
+             delta=None):
     """dq_out/dk_out/dv_out: bf16 column views (e.g. into a d_qkv buffer)."""
     T = q.shape[0]
     scale = head_dim ** -0.5 if scale is None else scale
-    if dq_acc is None:
-        dq_acc = torch.empty((T, n_heads * head_dim), device=q.device, dtype=torch.float32)
-    dq_acc.zero_()
     if delta is None:
         delta = torch.empty((n_heads, T), device=q.device, dtype=torch.float32)
+    gqa_ws, tile_ws = attn_bwd_workspace(T, n_heads, n_kv_heads, head_dim, q.device)
     a = attn_args(q, k, v, o, meta, n_heads, n_kv_heads, head_dim, scale, lse)
     a.d_o, a.lddo = d_o.data_ptr(), d_o.stride(0)
-    a.delta, a.dq_acc = delta.data_ptr(), dq_acc.data_ptr()
+    a.delta = delta.data_ptr()
+    a.dq, a.lddq = dq_out.data_ptr(), dq_out.stride(0)
     a.dk, a.dv, a.lddk, a.lddv = dk_out.data_ptr(), dv_out.data_ptr(), dk_out.stride(0), dv_out.stride(0)
+    a.gqa_ws = None if gqa_ws is None else gqa_ws.data_ptr()
+    a.tile_ws = tile_ws.data_ptr()
     check(_lib.load().sb_attn_bwd(C.byref(a), _stream()), "sb_attn_bwd")
-    call("sb_f32_to_bf16_2d", dq_acc, dq_out, T, n_heads * head_dim, dq_out.stride(0))
 
 
 def make_meta(prefix_len, seg_start, kv_end, device="cuda"):

@@ -221,10 +221,16 @@ def metas(kind, T):
         seg = torch.where(t < P, torch.zeros_like(t), P + ((t - P) // C) * C)
         pre = torch.where(t < P, torch.zeros_like(t), torch.full_like(t, P))
         return ops.make_meta(pre, seg, t + 1)
+    if kind == "prefix_big":  # several 64-row tiles per segment, ragged ends
+        P, C = 700, 130
+        seg = torch.where(t < P, torch.zeros_like(t), P + ((t - P) // C) * C)
+        pre = torch.where(t < P, torch.zeros_like(t), torch.full_like(t, P))
+        return ops.make_meta(pre, seg, t + 1)
     raise ValueError(kind)
 
 
 @pytest.mark.parametrize("kind,T,nh,nkv,hd", [("causal", 300, 4, 2, 128), ("slabs", 288, 2, 2, 80),
+                                               ("prefix_big", 1220, 7, 1, 128), ("slabs", 960, 3, 3, 80),
                                                ("prefix", 250, 4, 1, 128), ("causal", 64, 2, 2, 80),
                                                ("prefix", 333, 14, 2, 128)])
 def test_attention_fwd_bwd(kind, T, nh, nkv, hd):
