@@ -36,6 +36,9 @@ int sb_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* number of kernels this library has launched (successfully enqueued) since the last reset; a launch recorded
  * into a CUDA graph during stream capture counts once -- replays are the caller's to add.  count_host may be NULL. */
 int sb_launch_counter(long long* count_host, int reset);
+/* decode-step kernels are launched with programmatic dependent launch (next kernel's prologue and weight prefetch
+ * overlap the current kernel's tail); 0 turns it off (debugging / A-B timing).  Default on unless SB_NO_PDL is set. */
+int sb_set_pdl(int enable);
 
 /* ------------------------------------------------------------------------------------------------
  * GEMM  D[M,N] = epi(A[M,K] * B[N,K]^T)   (tcgen05 + TMEM + TMA)
@@ -69,6 +72,8 @@ typedef struct sb_gemm_args {
   float* tgt_logit;                       /* [M] LMHEAD out                                         */
   const float* lse;                       /* [M] DLOGITS in                                         */
   const float* coef;                      /* [M] DLOGITS in: dLoss/dlogprob                         */
+  const void* prefetch;                   /* F32T only, optional: device bytes to warm into L2 after this   */
+  long long prefetch_bytes;               /*   kernel's own loads (the NEXT weight matrix of the decode step) */
 } sb_gemm_args;
 
 int sb_gemm(const sb_gemm_args* args, sb_stream_t stream);

@@ -3,6 +3,7 @@
 #include "spacer_b200.h"
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include <atomic>
 
@@ -25,6 +26,21 @@ int sb_check_launch(const char* what) {
     return 1;
   }
   g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+namespace {
+int g_pdl = -1;
+}
+bool sb_pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("SB_NO_PDL");
+    g_pdl = (e && e[0] && e[0] != '0') ? 0 : 1;
+  }
+  return g_pdl == 1;
+}
+extern "C" int sb_set_pdl(int enable) {
+  g_pdl = enable ? 1 : 0;
   return 0;
 }
 

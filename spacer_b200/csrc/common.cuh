@@ -38,6 +38,34 @@ int sb_check_launch(const char* what);
   } while (0)
 
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Kernels of the decode step are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: kernel N+1 may become resident while kernel N still
+// runs.  pdl_launch_dependents() (called first thing) lets the successor start; everything that reads or
+// writes memory touched by earlier kernels must come after pdl_wait(), which returns once every preceding
+// kernel in the stream has completed and its writes are visible.  Both are no-ops in a normal launch.
+// ----------------------------------------------------------------------------------------------
+SB_DEVICE void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+SB_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t sb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                             bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+// decode-step kernels use PDL unless SB_NO_PDL is set in the environment (debugging aid)
+bool sb_pdl_enabled();
+
+// ----------------------------------------------------------------------------------------------
 // small math helpers
 // ----------------------------------------------------------------------------------------------
 SB_DEVICE float warp_sum(float v) {

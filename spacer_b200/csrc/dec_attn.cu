@@ -100,6 +100,7 @@ dec_attn_kernel(const DecAttnParams p) {
   const Plan& pl = p.pl;
   const int rep = pl.rep;
 
+  pdl_launch_dependents();
   // ---- decode the item
   int item = blockIdx.x;
   const bf16 *kbase, *vbase;
@@ -121,6 +122,7 @@ dec_attn_kernel(const DecAttnParams p) {
     j_hi = min(j_lo + pl.p_chunk, p.P);
     slot = s;
   } else {
+    pdl_wait();                              // the step counter and the completion cache come from earlier kernels
     item -= pl.n_prefix_items;
     const int s = item % pl.n_csplit;
     kvh = (item / pl.n_csplit) % p.nkv;
@@ -135,6 +137,7 @@ dec_attn_kernel(const DecAttnParams p) {
     j_hi = min(j_lo + per, n_ctx);
     slot = pl.n_psplit + s;
   }
+  const bool is_prefix = blockIdx.x < pl.n_prefix_items;
   const long long kv_ld = (long long)p.nkv * HD;
   const int n_tiles = j_hi > j_lo ? (j_hi - j_lo + TK - 1) / TK : 0;
 
@@ -149,7 +152,12 @@ dec_attn_kernel(const DecAttnParams p) {
     }
   };
 
-  // ---- Q tile (gathered query vectors) + first K/V tile
+  // ---- first K/V tile + Q tile (gathered query vectors).  The prompt cache is constant during decode, so prefix
+  // items request their first K/V tile before waiting for the kernels that produce q.
+  if (is_prefix) {
+    if (n_tiles > 0) load_kv(0, 0);
+    pdl_wait();
+  }
   for (int i = tid; i < TQ * (HD / 8); i += THREADS) {
     const int m = i / (HD / 8), c = i % (HD / 8);
     const bool ok = m < n_q;
@@ -157,7 +165,7 @@ dec_attn_kernel(const DecAttnParams p) {
     const bf16* src = p.q + (long long)(row0 + mm / rep) * p.nh * HD + (long long)(kvh * rep + mm % rep) * HD + c * 8;
     cp_async16(smem_u32(sQ + m * LD + c * 8), src, ok);
   }
-  if (n_tiles > 0) load_kv(0, 0);
+  if (!is_prefix && n_tiles > 0) load_kv(0, 0);
   cp_async_commit();
 
   const bool active = warp * 16 < n_q;   // warp-uniform: this warp owns at least one real query vector
@@ -277,6 +285,8 @@ dec_attn_kernel(const DecAttnParams p) {
 __global__ void __launch_bounds__(128)
 dec_attn_combine_kernel(const float* __restrict__ o_part, const float* __restrict__ lse_part, int NS, int n_pairs,
                         bf16* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int pair = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (pair >= n_pairs) return;
   const int lane = threadIdx.x & 31;
@@ -287,13 +297,25 @@ dec_attn_combine_kernel(const float* __restrict__ o_part, const float* __restric
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   float wsum = 0.f;
   if (mx > -INFINITY) {
-    for (int s = 0; s < NS; ++s) {
-      const float ls = lp[s];
-      if (ls == -INFINITY) continue;
-      const float w = exp2f(ls - mx);
-      const float4 v = *reinterpret_cast<const float4*>(o_part + ((long long)pair * NS + s) * HD + lane * 4);
-      acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
-      wsum += w;
+    // batches of 8 splits: all loads of a batch are issued before any is consumed (the partials sit in L2)
+    const float* op = o_part + (long long)pair * NS * HD + lane * 4;
+    for (int s0 = 0; s0 < NS; s0 += 8) {
+      float4 v[8];
+      float w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int s = min(s0 + j, NS - 1);
+        v[j] = *reinterpret_cast<const float4*>(op + (long long)s * HD);
+        const float ls = lp[s];
+        w[j] = (s0 + j < NS && ls > -INFINITY) ? exp2f(ls - mx) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (w[j] != 0.f) {   // empty partials may hold stale bits
+          acc.x += w[j] * v[j].x; acc.y += w[j] * v[j].y; acc.z += w[j] * v[j].z; acc.w += w[j] * v[j].w;
+          wsum += w[j];
+        }
+      }
     }
   }
   const float inv = wsum > 0.f ? 1.f / wsum : 0.f;
@@ -356,9 +378,10 @@ extern "C" int sb_dec_attn(const void* q, const void* kp0, const void* vp0, cons
     done = true;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  dec_attn_kernel<<<p.pl.n_items, THREADS, DEC_ATTN_SMEM, st>>>(p);
+  SB_CUDA(sb_launch(dec_attn_kernel, dim3(p.pl.n_items), dim3(THREADS), (size_t)DEC_ATTN_SMEM, st, sb_pdl_enabled(), p));
   if (sb_check_launch("sb_dec_attn")) return 1;
   const int n_pairs = R * n_heads;
-  dec_attn_combine_kernel<<<(n_pairs + 3) / 4, 128, 0, st>>>(p.o_part, p.lse_part, p.pl.NS, n_pairs, (bf16*)out);
+  SB_CUDA(sb_launch(dec_attn_combine_kernel, dim3((n_pairs + 3) / 4), dim3(128), 0, st, sb_pdl_enabled(),
+                    (const float*)p.o_part, (const float*)p.lse_part, p.pl.NS, n_pairs, (bf16*)out));
   return sb_check_launch("sb_dec_attn(combine)");
 }

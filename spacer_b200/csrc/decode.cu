@@ -12,6 +12,8 @@ namespace {
 // x[r] = embed[token[r]]
 __global__ void dec_embed_kernel(const int* __restrict__ tokens, const bf16* __restrict__ embed, bf16* __restrict__ x,
                                  int H) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int r = blockIdx.x;
   const bf16* src = embed + (long long)tokens[r] * H;
   for (int i = threadIdx.x; i < H / 8; i += blockDim.x)
@@ -25,6 +27,8 @@ __global__ void __launch_bounds__(RN_THREADS)
 dec_residual_rmsnorm_kernel(bf16* __restrict__ x, const float* __restrict__ parts, int S, long long part_stride_s,
                             long long part_stride_r, const bf16* __restrict__ w, bf16* __restrict__ xn, int H,
                             float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[32];
   const int r = blockIdx.x;
   constexpr int MAXV = 4;                      // up to 4 passes of 4096 elements (H <= 16384)
@@ -79,6 +83,8 @@ dec_qkv_post_kernel(const float* __restrict__ parts, int S, long long stride_s, 
                     const bf16* __restrict__ bias, const int* __restrict__ step_ptr, int rope_base, float theta,
                     int nh, int nkv, int hd, bf16* __restrict__ q_out, bf16* __restrict__ k_cache,
                     bf16* __restrict__ v_cache, long long cache_stride_r, int c_max) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int r = blockIdx.x, head = blockIdx.y;
   const int step = *step_ptr;
   const int half = hd / 2;
@@ -117,6 +123,8 @@ dec_qkv_post_kernel(const float* __restrict__ parts, int S, long long stride_s, 
 // act[r][c] = bf16( bf16(silu(g)) * u ),  g/u = bf16(sum of split-K partials) in the interleaved layout
 __global__ void dec_swiglu_kernel(const float* __restrict__ parts, int S, long long stride_s, long long stride_r,
                                   bf16* __restrict__ act, int I) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int r = blockIdx.y;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= I) return;
@@ -138,7 +146,8 @@ __global__ void dec_swiglu_kernel(const float* __restrict__ parts, int S, long l
 
 extern "C" int sb_dec_embed(const int* tokens, const void* embed, void* x, int R, int H, sb_stream_t stream) {
   SB_REQUIRE(tokens && embed && x && R > 0 && H % 8 == 0, "sb_dec_embed: bad arguments");
-  dec_embed_kernel<<<R, 256, 0, STREAM(stream)>>>(tokens, (const bf16*)embed, (bf16*)x, H);
+  SB_CUDA(sb_launch(dec_embed_kernel, dim3(R), dim3(256), 0, STREAM(stream), sb_pdl_enabled(), tokens, (const bf16*)embed,
+                    (bf16*)x, H));
   return sb_check_launch("sb_dec_embed");
 }
 
@@ -147,8 +156,8 @@ extern "C" int sb_dec_residual_rmsnorm(void* x, const float* parts, int S, long 
   SB_REQUIRE(x && R > 0 && H > 0 && H % 4 == 0 && H <= 16384 && (xn == nullptr || w != nullptr),
              "sb_dec_residual_rmsnorm: bad arguments (H must be a multiple of 4, <= 16384)");
   SB_REQUIRE(parts == nullptr || (stride_s % 4 == 0 && stride_r % 4 == 0), "sb_dec_residual_rmsnorm: partial strides must be multiples of 4");
-  dec_residual_rmsnorm_kernel<<<R, RN_THREADS, 0, STREAM(stream)>>>((bf16*)x, parts, S, stride_s, stride_r,
-                                                                             (const bf16*)w, (bf16*)xn, H, eps);
+  SB_CUDA(sb_launch(dec_residual_rmsnorm_kernel, dim3(R), dim3(RN_THREADS), 0, STREAM(stream), sb_pdl_enabled(), (bf16*)x,
+                    parts, S, stride_s, stride_r, (const bf16*)w, (bf16*)xn, H, eps));
   return sb_check_launch("sb_dec_residual_rmsnorm");
 }
 
@@ -158,15 +167,16 @@ extern "C" int sb_dec_qkv_post(const float* parts, int S, long long stride_s, lo
                                int c_max, int R, sb_stream_t stream) {
   SB_REQUIRE(parts && bias && step_ptr && q_out && k_cache && v_cache && R > 0 && S > 0, "sb_dec_qkv_post: bad arguments");
   SB_REQUIRE(head_dim == 128, "sb_dec_qkv_post: head_dim must be 128, got %d", head_dim);
-  dec_qkv_post_kernel<<<dim3(R, n_heads + 2 * n_kv_heads), 64, 0, STREAM(stream)>>>(parts, S, stride_s, stride_r, (const bf16*)bias, step_ptr,
-                                                     rope_base, theta, n_heads, n_kv_heads, head_dim, (bf16*)q_out,
-                                                     (bf16*)k_cache, (bf16*)v_cache, cache_stride_r, c_max);
+  SB_CUDA(sb_launch(dec_qkv_post_kernel, dim3(R, n_heads + 2 * n_kv_heads), dim3(64), 0, STREAM(stream), sb_pdl_enabled(),
+                    parts, S, stride_s, stride_r, (const bf16*)bias, step_ptr, rope_base, theta, n_heads, n_kv_heads,
+                    head_dim, (bf16*)q_out, (bf16*)k_cache, (bf16*)v_cache, cache_stride_r, c_max));
   return sb_check_launch("sb_dec_qkv_post");
 }
 
 extern "C" int sb_dec_swiglu(const float* parts, int S, long long stride_s, long long stride_r, void* act, int R, int I,
                              sb_stream_t stream) {
   SB_REQUIRE(parts && act && R > 0 && I % 64 == 0, "sb_dec_swiglu: bad arguments");
-  dec_swiglu_kernel<<<dim3((I + 255) / 256, R), 256, 0, STREAM(stream)>>>(parts, S, stride_s, stride_r, (bf16*)act, I);
+  SB_CUDA(sb_launch(dec_swiglu_kernel, dim3((I + 255) / 256, R), dim3(256), 0, STREAM(stream), sb_pdl_enabled(), parts, S,
+                    stride_s, stride_r, (bf16*)act, I));
   return sb_check_launch("sb_dec_swiglu");
 }

@@ -42,7 +42,14 @@ struct GemmParams {
   float* tgt_logit;
   const float* lse;
   const float* coef;
+  const uint8_t* prefetch;       // optional: bytes to pull into L2 once this kernel's own loads are issued
+  long long prefetch_bytes;
 };
+
+// 16 KB per instruction: cp.async.bulk.prefetch.L2 only warms L2, nothing is written to shared memory
+SB_DEVICE void l2_prefetch_bulk(const void* ptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
+}
 
 template <int BN>
 struct Cfg {
@@ -114,29 +121,51 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int total_tiles = p.m_tiles * p.n_tiles * p.k_splits;
 
+  pdl_launch_dependents();
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
+      // Decode GEMVs (F32T, launched with PDL): the A operand is a weight matrix nobody writes during decode, so the
+      // first ring of A tiles is requested BEFORE waiting for the preceding kernels -- the weight stream starts while
+      // the small kernel that produces the activations (B operand) is still running.
+      int pre = 0;
+      if constexpr (EPI == SB_EPI_F32T) {
+        for (int t = blockIdx.x; t < total_tiles && pre < NSTAGES; t += gridDim.x) {
+          const int mt = t % p.m_tiles;
+          const int ks = t / (p.m_tiles * p.n_tiles);
+          const int kb0 = ks * p.k_iters_per_split;
+          const int kb1 = min(kb0 + p.k_iters_per_split, p.k_iters);
+          for (int kb = kb0; kb < kb1 && pre < NSTAGES; ++kb, ++pre) {
+            const uint32_t fb = full0 + 8 * pre;
+            mbar_expect_tx(fb, C::STAGE_BYTES);
+            tma_load_2d(smem_base + pre * C::STAGE_BYTES, &tmA, fb, kb * BK, mt * BM);
+          }
+        }
+      }
+      pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
+      int issued = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int mt = t % p.m_tiles;
         const int nt = (t / p.m_tiles) % p.n_tiles;
         const int ks = t / (p.m_tiles * p.n_tiles);
         const int kb0 = ks * p.k_iters_per_split;
         const int kb1 = min(kb0 + p.k_iters_per_split, p.k_iters);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(empty0 + 8 * stage, phase ^ 1);
+        for (int kb = kb0; kb < kb1; ++kb, ++issued) {
           const uint32_t fb = full0 + 8 * stage;
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
           const uint32_t sb = sa + A_STAGE_BYTES;
-          mbar_expect_tx(fb, C::STAGE_BYTES);
-          if (!A_MN) {
-            tma_load_2d(sa, &tmA, fb, kb * BK, mt * BM);
-          } else {
+          if (issued >= pre) {
+            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+            mbar_expect_tx(fb, C::STAGE_BYTES);
+            if (!A_MN) {
+              tma_load_2d(sa, &tmA, fb, kb * BK, mt * BM);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j)
-              tma_load_2d(sa + j * 8192, &tmA, fb, mt * BM + j * 64, kb * BK);
+              for (int j = 0; j < BM / 64; ++j)
+                tma_load_2d(sa + j * 8192, &tmA, fb, mt * BM + j * 64, kb * BK);
+            }
           }
           if (!B_MN) {
             tma_load_2d(sb, &tmB, fb, kb * BK, nt * BN);
@@ -148,9 +177,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
         }
       }
+      if constexpr (EPI == SB_EPI_F32T) {
+        // Weight streaming never pauses: while the small kernels between two GEMVs run (HBM otherwise idle), the
+        // next weight matrix is already on its way into L2.  Each CTA prefetches its 1/gridDim slice.
+        if (p.prefetch_bytes > 0) {
+          constexpr long long CH = 16384;
+          const long long n_ch = (p.prefetch_bytes + CH - 1) / CH;
+          for (long long c = blockIdx.x; c < n_ch; c += gridDim.x) {
+            const long long off = c * CH;
+            const long long len = min(CH, p.prefetch_bytes - off);
+            l2_prefetch_bulk(p.prefetch + off, (uint32_t)(len & ~15LL));
+          }
+        }
+      }
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
+    pdl_wait();
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
       // per-UMMA_K(16) start-address advance inside a stage, in 16-byte units
@@ -188,6 +231,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else {
     // ------------------------------ epilogue (4 warps) ------------------------------
+    pdl_wait();
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
     const int row_in_tile = q * 32 + lane;
     int acc = 0;
@@ -440,9 +484,16 @@ int launch(const sb_gemm_args* a, cudaStream_t stream) {
   p.lse_part = reinterpret_cast<float2*>(a->lse_part);
   p.tgt_logit = a->tgt_logit;
   p.lse = a->lse; p.coef = a->coef;
+  p.prefetch = reinterpret_cast<const uint8_t*>(a->prefetch);
+  p.prefetch_bytes = a->prefetch ? a->prefetch_bytes : 0;
   const int total = p.m_tiles * p.n_tiles * p.k_splits;
   const int grid = total < num_sms() ? total : num_sms();
-  kfn<<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  const bool pdl = (EPI == SB_EPI_F32T) && sb_pdl_enabled();
+  cudaError_t le = sb_launch(kfn, dim3(grid), dim3(GEMM_THREADS), (size_t)C::SMEM_BYTES, stream, pdl, tmA, tmB, p);
+  if (le != cudaSuccess) {
+    sb_set_error("sb_gemm: launch failed: %s", cudaGetErrorString(le));
+    return 1;
+  }
   return sb_check_launch("sb_gemm");
 }
 
@@ -471,6 +522,8 @@ extern "C" int sb_gemm(const sb_gemm_args* a, sb_stream_t stream_) {
     SB_REQUIRE(!amn && !bmn, "sb_gemm: F32T epilogue needs K-major operands");
     SB_REQUIRE(a->N <= 32, "sb_gemm: F32T epilogue is for N<=32 (decode rows), got %d", a->N);
     SB_REQUIRE(a->ldd >= a->M, "sb_gemm: F32T ldd (%lld) < M (%d)", a->ldd, a->M);
+    SB_REQUIRE(a->prefetch == nullptr || ((reinterpret_cast<uintptr_t>(a->prefetch) & 15) == 0 && a->prefetch_bytes >= 0),
+               "sb_gemm: prefetch pointer must be 16-byte aligned");
     if (a->N <= 16) return launch<false, false, 16, SB_EPI_F32T>(a, stream);
     return launch<false, false, 32, SB_EPI_F32T>(a, stream);
   }

@@ -129,6 +129,8 @@ SB_DEVICE bool kept_token(uint32_t k, uint32_t kstar, int& tie_rank, int n_drop)
 
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(ST)
 sample_kernel(const SampleParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) uint8_t smem_raw[];
   Shared* sh = reinterpret_cast<Shared*>(smem_raw);
@@ -308,7 +310,11 @@ sample_kernel(const SampleParams p) {
   cluster.sync();  // keep every CTA's shared memory alive until all remote reads are done
 }
 
-__global__ void step_advance_kernel(int* step_ptr) { *step_ptr += 1; }
+__global__ void step_advance_kernel(int* step_ptr) {
+  pdl_launch_dependents();
+  pdl_wait();
+  *step_ptr += 1;
+}
 
 }  // namespace
 
@@ -330,12 +336,12 @@ extern "C" int sb_sample_top_p(const float* logits, long long ld, int R, int V, 
     SB_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
   }
-  sample_kernel<<<R * CL, ST, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  SB_CUDA(sb_launch(sample_kernel, dim3(R * CL), dim3(ST), smem, reinterpret_cast<cudaStream_t>(stream), sb_pdl_enabled(), p));
   return sb_check_launch("sb_sample_top_p");
 }
 
 extern "C" int sb_step_advance(int* step_ptr, sb_stream_t stream) {
   SB_REQUIRE(step_ptr, "sb_step_advance: null pointer");
-  step_advance_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(step_ptr);
+  SB_CUDA(sb_launch(step_advance_kernel, dim3(1), dim3(1), 0, reinterpret_cast<cudaStream_t>(stream), sb_pdl_enabled(), step_ptr));
   return sb_check_launch("sb_step_advance");
 }
