@@ -154,14 +154,15 @@ def cpu_reference_sample(cfg_name, threads=None):
     slab = gh * gh
 
     def vit_block(x):
+        n = x.shape[0]
         h = F.layer_norm(x, (E,))
-        qkv = F.linear(h, wq, bq).view(n_p, 3, full.v_heads, -1)
+        qkv = F.linear(h, wq, bq).view(n, 3, full.v_heads, -1)
         q, k, v = qkv.unbind(1)
         outs = []
-        for s0 in range(0, n_p, slab):
+        for s0 in range(0, n, slab):
             qs, ks, vs = (t[s0:s0 + slab].transpose(0, 1) for t in (q, k, v))
             outs.append(F.scaled_dot_product_attention(qs, ks, vs).transpose(0, 1))
-        x = x + F.linear(torch.cat(outs).reshape(n_p, E), wp)
+        x = x + F.linear(torch.cat(outs).reshape(n, E), wp)
         h = F.linear(F.layer_norm(x, (E,)), w1)
         return x + F.linear(h * torch.sigmoid(1.702 * h), w2)
 

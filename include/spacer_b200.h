@@ -189,11 +189,14 @@ int sb_step_advance(int* step_ptr, sb_stream_t stream);
  * GRPO loss tail, forward + backward (SG_RLVR_trainer.py:353-366, 489-494, 551-552, 632-643)
  * inputs are the LMHEAD-epilogue partials of the lm_head GEMM over the G*C scoring rows.
  * out2 = {loss, mean_kl}; coef_out = dLoss/dlogprob per token (0 outside the completion mask).
+ * `workspace` holds sb_grpo_loss_workspace() floats which the caller zeroes ONCE (it starts with ticket counters the
+ * kernel resets itself).
  * ------------------------------------------------------------------------------------------------ */
+int sb_grpo_loss_workspace(int G, int C, long long* floats_out);
 int sb_grpo_loss(const float* lse_part, int n_tiles, const float* tgt_logit, const int* comp_ids, int G, int C,
                  int eos_id, const float* ref_lp, const float* adv, float beta, float* lp_out, float* lse_out,
                  float* coef_out, int* mask_out, float* row_loss, float* row_kl, int* row_len, float* out2,
-                 sb_stream_t stream);
+                 float* workspace, sb_stream_t stream);
 int sb_logprob_from_partials(const float* lse_part, int n_tiles, const float* tgt_logit, float* lp_out, long long rows,
                              sb_stream_t stream);
 

@@ -414,7 +414,7 @@ class Qwen2VLB200:
         adv = advantages.to(self.device, F32).contiguous()
         ref = None if ref_logps is None else ref_logps.to(self.device, F32).contiguous()
         ops.call("sb_grpo_loss", part, nt, tl, batch.comp_ids, G_, C, d.eos_id, ref, adv, float(beta), lp, lse, coef,
-                 mask, row_loss, row_kl, row_len, out2)
+                 mask, row_loss, row_kl, row_len, out2, ops.grpo_loss_workspace(G_, C, self.device))
         del part
         # backward through lm_head: recompute logits tile by tile, emit dlogits, two GEMMs
         grads.zero_for_step()

@@ -236,6 +236,13 @@ def attn_bwd(q, k, v, o, lse, d_o, meta, n_heads, n_kv_heads, head_dim, dq_out, 
     check(_lib.load().sb_attn_bwd(C.byref(a), _stream()), "sb_attn_bwd")
 
 
+def grpo_loss_workspace(G, C_len, device):
+    """Zeroed fp32 scratch for sb_grpo_loss (ticket counter + per-CTA partial sums)."""
+    n = C.c_longlong(0)
+    check(_lib.load().sb_grpo_loss_workspace(G, C_len, C.byref(n)), "sb_grpo_loss_workspace")
+    return torch.zeros(n.value, device=device, dtype=torch.float32)
+
+
 def make_meta(prefix_len, seg_start, kv_end, device="cuda"):
     """int32 [T,4] visibility metadata from three equal-length integer sequences/tensors."""
     m = torch.stack([torch.as_tensor(prefix_len), torch.as_tensor(seg_start), torch.as_tensor(kv_end),

@@ -231,10 +231,11 @@ def test_sampler_eos_and_finished():
     assert toks.tolist() == [6, 6, 6] and fin.tolist() == [0, 0, 0]
 
 
-def test_grpo_loss_matches_oracle():
+@pytest.mark.parametrize("G,C,V", [(4, 37, 1000), (4, 150, 1200), (4, 64, 256)])
+def test_grpo_loss_matches_oracle(G, C, V):
     from oracle import grpo_ref as GR
     from spacer_b200 import ops
-    G, C, V, K, eos = 4, 37, 1000, 128, 77
+    K, eos = 128, 77
     H, Wm = rnd((G * C, K), 1), rnd((V, K), 2, 0.2)
     comp = torch.randint(0, V, (G, C))
     comp[comp == eos] = 0
@@ -259,8 +260,11 @@ def test_grpo_loss_matches_oracle():
     rl, rk = torch.empty(G, device="cuda"), torch.empty(G, device="cuda")
     rlen = torch.empty(G, dtype=torch.int32, device="cuda")
     out2 = torch.empty(2, device="cuda")
-    ops.call("sb_grpo_loss", part, nt, tl, comp.to(torch.int32).cuda(), G, C, eos, ref_lp.cuda().contiguous(),
-             adv.cuda(), 0.04, outs[0], outs[1], outs[2], mask_o, rl, rk, rlen, out2)
+    ws = ops.grpo_loss_workspace(G, C, "cuda")
+    for _ in range(2):   # twice: the ticket counter in the workspace must reset itself
+        out2.fill_(float("nan"))
+        ops.call("sb_grpo_loss", part, nt, tl, comp.to(torch.int32).cuda(), G, C, eos, ref_lp.cuda().contiguous(),
+                 adv.cuda(), 0.04, outs[0], outs[1], outs[2], mask_o, rl, rk, rlen, out2, ws)
     assert (outs[0].cpu().view(G, C) - lp_ref).abs().max() < 2e-3
     assert torch.equal(mask_o.cpu().view(G, C), mask)
     assert rlen.tolist() == mask.sum(1).tolist()
