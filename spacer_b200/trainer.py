@@ -15,6 +15,7 @@ from typing import Callable, Sequence
 
 import torch
 
+from . import dist as D
 from . import ops
 from .model import GradStore, Qwen2VLB200, pack_prompt_completions
 from .params import ParamStore
@@ -116,25 +117,15 @@ class SGRLVRTrainerB200:
         self.global_step = 0
         self.last_rollout_stats = None
 
-    # -- distributed helpers ---------------------------------------------------------------------------
+    # -- distributed helpers (spacer_b200/dist.py) ---------------------------------------------------------
     def _world(self):
-        import torch.distributed as dist
-        return dist.get_world_size(self.pg) if (dist.is_available() and dist.is_initialized()) else 1
+        return D.world_size(self.pg)
 
     def _allreduce_grads(self):
-        import torch.distributed as dist
-        if self._world() > 1:
-            dist.all_reduce(self.grads.mat, group=self.pg)
-            dist.all_reduce(self.grads.vec, group=self.pg)
+        D.allreduce_sum_([self.grads.mat, self.grads.vec], group=self.pg)
 
     def _gather(self, t: torch.Tensor) -> torch.Tensor:
-        import torch.distributed as dist
-        w = self._world()
-        if w == 1:
-            return t
-        out = [torch.empty_like(t) for _ in range(w)]
-        dist.all_gather(out, t.contiguous(), group=self.pg)
-        return torch.cat(out)
+        return D.gather_rows(t, group=self.pg)
 
     # -- the step --------------------------------------------------------------------------------------
     def rollout(self, example, seed):
@@ -249,7 +240,7 @@ class SGRLVRTrainerB200:
         # metrics (TRN:650-683), one gather per quantity like the reference but on a packed struct
         packed = torch.cat([lengths.float(), rewards_per_func.reshape(-1), rewards,
                             torch.stack([std, out["mean_kl"], torch.tensor(temporal_rewards, device=m.device)])])
-        allp = self._gather(packed).view(-1, packed.numel())
+        allp = self._gather(packed)
         nf = len(self.reward_funcs)
         gl = allp[:, :G]
         grpf = allp[:, G:G + G * nf].reshape(-1, nf)

