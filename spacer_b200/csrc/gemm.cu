@@ -368,7 +368,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     if (p.aux) st8(p.aux + (long long)row * p.ldaux + col, v);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                      const float z = p.aux ? bf16_round(v[j]) : v[j];
+                      const float z = bf16_round(v[j]);   // the activation sees the bf16 pre-activation, stored or not
                       v[j] = (EPI == SB_EPI_QUICKGELU) ? quick_gelu(z) : gelu_erf(z);
                     }
                   }
