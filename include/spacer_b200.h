@@ -39,6 +39,10 @@ int sb_launch_counter(long long* count_host, int reset);
 /* decode-step kernels are launched with programmatic dependent launch (next kernel's prologue and weight prefetch
  * overlap the current kernel's tail); 0 turns it off (debugging / A-B timing).  Default on unless SB_NO_PDL is set. */
 int sb_set_pdl(int enable);
+/* profiling aid: with a device buffer of 1 + 4*capacity uint64 installed (buf[0] = 0), every decode-step kernel
+ * appends {kind, t_entry, t_ready (dependencies satisfied), t_end} of its block 0 in globaltimer ns; buf[0] counts
+ * records.  (NULL, 0) disables.  Not for production runs. */
+int sb_trace_enable(unsigned long long* buf_dev, int capacity);
 
 /* ------------------------------------------------------------------------------------------------
  * GEMM  D[M,N] = epi(A[M,K] * B[N,K]^T)   (tcgen05 + TMEM + TMA)
@@ -53,7 +57,9 @@ enum {
   SB_EPI_SWIGLU = 3,    /* B rows interleaved [64 gate | 64 up]; D[M,N/2] = silu(g)*u; aux = raw    */
   SB_EPI_F32T = 4,      /* D_f32[split][n][m] = partial acc (swap-AB decode GEMV with split-K)      */
   SB_EPI_LMHEAD = 5,    /* per-row (max, sumexp) per N tile of bf16-rounded logits + target gather  */
-  SB_EPI_DLOGITS = 6    /* D = bf16(coef[m] * (onehot(target[m]) - exp(logit - lse[m])))            */
+  SB_EPI_DLOGITS = 6,   /* D = bf16(coef[m] * (onehot(target[m]) - exp(logit - lse[m])))            */
+  SB_EPI_F32T_SWIGLU = 7 /* swap-AB decode gate|up GEMV, A rows interleaved [64 gate | 64 up]:
+                           D_bf16[n][m/2] = silu(gate)*up for the N <= 32 decode rows (no split-K)         */
 };
 
 typedef struct sb_gemm_args {
@@ -74,6 +80,8 @@ typedef struct sb_gemm_args {
   const float* coef;                      /* [M] DLOGITS in: dLoss/dlogprob                         */
   const void* prefetch;                   /* F32T only, optional: device bytes to warm into L2 after this   */
   long long prefetch_bytes;               /*   kernel's own loads (the NEXT weight matrix of the decode step) */
+  const void* prefetch2;                  /* second L2-prefetch range (the matrix after next), 16-byte aligned */
+  long long prefetch2_bytes;
 } sb_gemm_args;
 
 int sb_gemm(const sb_gemm_args* args, sb_stream_t stream);

@@ -28,10 +28,11 @@ class GemmArgs(C.Structure):
         ("targets", C.c_void_p), ("lse_part", C.c_void_p), ("tgt_logit", C.c_void_p),
         ("lse", C.c_void_p), ("coef", C.c_void_p),
         ("prefetch", C.c_void_p), ("prefetch_bytes", C.c_longlong),
+        ("prefetch2", C.c_void_p), ("prefetch2_bytes", C.c_longlong),
     ]
 
 
-EPI_STORE, EPI_QUICKGELU, EPI_GELU, EPI_SWIGLU, EPI_F32T, EPI_LMHEAD, EPI_DLOGITS = range(7)
+EPI_STORE, EPI_QUICKGELU, EPI_GELU, EPI_SWIGLU, EPI_F32T, EPI_LMHEAD, EPI_DLOGITS, EPI_F32T_SWIGLU = range(8)
 
 _lib = None
 

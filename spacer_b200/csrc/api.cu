@@ -44,6 +44,19 @@ extern "C" int sb_set_pdl(int enable) {
   return 0;
 }
 
+int sb_trace_set_gemm(unsigned long long*, int);
+int sb_trace_set_decode(unsigned long long*, int);
+int sb_trace_set_dec_attn(unsigned long long*, int);
+int sb_trace_set_sampler(unsigned long long*, int);
+
+extern "C" int sb_trace_enable(unsigned long long* buf_dev, int capacity) {
+  SB_REQUIRE((buf_dev == nullptr) == (capacity == 0), "sb_trace_enable: pass (NULL, 0) to disable");
+  SB_REQUIRE(!sb_trace_set_gemm(buf_dev, capacity) && !sb_trace_set_decode(buf_dev, capacity) &&
+                 !sb_trace_set_dec_attn(buf_dev, capacity) && !sb_trace_set_sampler(buf_dev, capacity),
+             "sb_trace_enable: cudaMemcpyToSymbol failed");
+  return 0;
+}
+
 extern "C" int sb_launch_counter(long long* count_host, int reset) {
   if (count_host) *count_host = g_launches.load(std::memory_order_relaxed);
   if (reset) g_launches.store(0, std::memory_order_relaxed);

@@ -66,6 +66,41 @@ inline cudaError_t sb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, si
 bool sb_pdl_enabled();
 
 // ----------------------------------------------------------------------------------------------
+// Timeline tracing of the decode step (debug/profiling aid, off by default: one predictable branch per kernel).
+// When a buffer is installed with sb_trace_enable(), one designated thread of block 0 of every decode kernel appends
+// {kind, t_entry, t_ready (after pdl_wait), t_end} in globaltimer nanoseconds.  buf[0] is the record cursor.
+// Each translation unit has its own copy of the pointer (no relocatable device code); api.cu sets all of them.
+// ----------------------------------------------------------------------------------------------
+enum { SB_TR_GEMV = 1, SB_TR_EMBED, SB_TR_RMSNORM, SB_TR_QKVPOST, SB_TR_ATTN, SB_TR_COMBINE, SB_TR_SWIGLU, SB_TR_SAMPLE,
+       SB_TR_ADVANCE };
+static __device__ unsigned long long* sb_tu_trace = nullptr;
+static __device__ int sb_tu_trace_cap = 0;
+SB_DEVICE unsigned long long sb_gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// returns the record slot (or -1); call from ONE thread
+SB_DEVICE int sb_trace_begin(int kind) {
+  unsigned long long* b = sb_tu_trace;
+  if (b == nullptr) return -1;
+  const int k = (int)atomicAdd(b, 1ull);
+  if (k >= sb_tu_trace_cap) return -1;
+  b[1 + 4 * k] = (unsigned long long)kind;
+  b[2 + 4 * k] = sb_gtime();
+  return k;
+}
+SB_DEVICE void sb_trace_mark(int slot, int which /*1 = ready, 2 = end*/) {
+  if (slot >= 0) sb_tu_trace[2 + 4 * slot + which] = sb_gtime();
+}
+#define SB_DEFINE_TRACE_SETTER(name)                                                     \
+  int name(unsigned long long* buf, int cap) {                                           \
+    cudaError_t e = cudaMemcpyToSymbol(sb_tu_trace, &buf, sizeof(buf));                  \
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(sb_tu_trace_cap, &cap, sizeof(cap));    \
+    return e == cudaSuccess ? 0 : 1;                                                     \
+  }
+
+// ----------------------------------------------------------------------------------------------
 // small math helpers
 // ----------------------------------------------------------------------------------------------
 SB_DEVICE float warp_sum(float v) {

@@ -101,6 +101,7 @@ dec_attn_kernel(const DecAttnParams p) {
   const int rep = pl.rep;
 
   pdl_launch_dependents();
+  const int tr = (blockIdx.x == 0 && tid == 0) ? sb_trace_begin(SB_TR_ATTN) : -1;
   // ---- decode the item
   int item = blockIdx.x;
   const bf16 *kbase, *vbase;
@@ -158,6 +159,7 @@ dec_attn_kernel(const DecAttnParams p) {
     if (n_tiles > 0) load_kv(0, 0);
     pdl_wait();
   }
+  sb_trace_mark(tr, 1);
   for (int i = tid; i < TQ * (HD / 8); i += THREADS) {
     const int m = i / (HD / 8), c = i % (HD / 8);
     const bool ok = m < n_q;
@@ -279,6 +281,7 @@ dec_attn_kernel(const DecAttnParams p) {
     }
     if (t4 == 0) p.lse_part[pbase] = l > 0.f ? mxv + log2f(l) : -INFINITY;
   }
+  sb_trace_mark(tr, 2);
 }
 
 // out[row][head*HD + d] = sum_s w_s O_s / sum_s w_s, w_s = 2^(lse_s - max lse); one warp per (row, head)
@@ -286,7 +289,9 @@ __global__ void __launch_bounds__(128)
 dec_attn_combine_kernel(const float* __restrict__ o_part, const float* __restrict__ lse_part, int NS, int n_pairs,
                         bf16* __restrict__ out) {
   pdl_launch_dependents();
+  const int tr = (blockIdx.x == 0 && threadIdx.x == 0) ? sb_trace_begin(SB_TR_COMBINE) : -1;
   pdl_wait();
+  sb_trace_mark(tr, 1);
   const int pair = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (pair >= n_pairs) return;
   const int lane = threadIdx.x & 31;
@@ -323,6 +328,7 @@ dec_attn_combine_kernel(const float* __restrict__ o_part, const float* __restric
   u.x = pack_bf16(acc.x * inv, acc.y * inv);
   u.y = pack_bf16(acc.z * inv, acc.w * inv);
   *reinterpret_cast<uint2*>(out + (long long)pair * HD + lane * 4) = u;
+  sb_trace_mark(tr, 2);
 }
 
 int g_sms = 0;
@@ -339,6 +345,8 @@ int sm_count() {
 constexpr int DEC_ATTN_SMEM = 5 * TILE * 2;
 
 }  // namespace
+
+SB_DEFINE_TRACE_SETTER(sb_trace_set_dec_attn)
 
 extern "C" int sb_dec_attn_workspace(int R, int rows_group0, int P, int c_max, int n_heads, int n_kv_heads,
                                      long long* floats_out) {

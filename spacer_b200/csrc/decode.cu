@@ -13,11 +13,15 @@ namespace {
 __global__ void dec_embed_kernel(const int* __restrict__ tokens, const bf16* __restrict__ embed, bf16* __restrict__ x,
                                  int H) {
   pdl_launch_dependents();
+  const bool tr_on = blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+  const int tr = tr_on ? sb_trace_begin(SB_TR_EMBED) : -1;
   pdl_wait();
+  sb_trace_mark(tr, 1);
   const int r = blockIdx.x;
   const bf16* src = embed + (long long)tokens[r] * H;
   for (int i = threadIdx.x; i < H / 8; i += blockDim.x)
     *reinterpret_cast<uint4*>(x + (long long)r * H + i * 8) = *reinterpret_cast<const uint4*>(src + i * 8);
+  sb_trace_mark(tr, 2);
 }
 
 // x[r] += bf16(sum_s parts[s][r][:]) (if parts);  xn[r] = w * bf16(x * rstd)
@@ -28,7 +32,10 @@ dec_residual_rmsnorm_kernel(bf16* __restrict__ x, const float* __restrict__ part
                             long long part_stride_r, const bf16* __restrict__ w, bf16* __restrict__ xn, int H,
                             float eps) {
   pdl_launch_dependents();
+  const bool tr_on = blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+  const int tr = tr_on ? sb_trace_begin(SB_TR_RMSNORM) : -1;
   pdl_wait();
+  sb_trace_mark(tr, 1);
   __shared__ float red[32];
   const int r = blockIdx.x;
   constexpr int MAXV = 4;                      // up to 4 passes of 4096 elements (H <= 16384)
@@ -74,6 +81,7 @@ dec_residual_rmsnorm_kernel(bf16* __restrict__ x, const float* __restrict__ part
       *reinterpret_cast<uint2*>(xn + (long long)r * H + i) = o;
     }
   }
+  sb_trace_mark(tr, 2);
 }
 
 // qkv = bf16(sum parts + bias); rope(q,k) at position rope_base + step; q -> q_out, k,v -> completion cache slot.
@@ -84,7 +92,10 @@ dec_qkv_post_kernel(const float* __restrict__ parts, int S, long long stride_s, 
                     int nh, int nkv, int hd, bf16* __restrict__ q_out, bf16* __restrict__ k_cache,
                     bf16* __restrict__ v_cache, long long cache_stride_r, int c_max) {
   pdl_launch_dependents();
+  const bool tr_on = blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+  const int tr = tr_on ? sb_trace_begin(SB_TR_QKVPOST) : -1;
   pdl_wait();
+  sb_trace_mark(tr, 1);
   const int r = blockIdx.x, head = blockIdx.y;
   const int step = *step_ptr;
   const int half = hd / 2;
@@ -118,13 +129,17 @@ dec_qkv_post_kernel(const float* __restrict__ parts, int S, long long stride_s, 
     kd[i] = __float2bfloat16_rn(o0);
     kd[i + half] = __float2bfloat16_rn(o1);
   }
+  sb_trace_mark(tr, 2);
 }
 
 // act[r][c] = bf16( bf16(silu(g)) * u ),  g/u = bf16(sum of split-K partials) in the interleaved layout
 __global__ void dec_swiglu_kernel(const float* __restrict__ parts, int S, long long stride_s, long long stride_r,
                                   bf16* __restrict__ act, int I) {
   pdl_launch_dependents();
+  const bool tr_on = blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+  const int tr = tr_on ? sb_trace_begin(SB_TR_SWIGLU) : -1;
   pdl_wait();
+  sb_trace_mark(tr, 1);
   const int r = blockIdx.y;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= I) return;
@@ -138,9 +153,12 @@ __global__ void dec_swiglu_kernel(const float* __restrict__ parts, int S, long l
   u = bf16_round(u);
   const float si = bf16_round(g / (1.f + __expf(-g)));
   act[(long long)r * I + c] = __float2bfloat16_rn(si * u);
+  sb_trace_mark(tr, 2);
 }
 
 }  // namespace
+
+SB_DEFINE_TRACE_SETTER(sb_trace_set_decode)
 
 #define STREAM(s) reinterpret_cast<cudaStream_t>(s)
 

@@ -44,6 +44,8 @@ struct GemmParams {
   const float* coef;
   const uint8_t* prefetch;       // optional: bytes to pull into L2 once this kernel's own loads are issued
   long long prefetch_bytes;
+  const uint8_t* prefetch2;      // second range (the matrix after next)
+  long long prefetch2_bytes;
 };
 
 // 16 KB per instruction: cp.async.bulk.prefetch.L2 only warms L2, nothing is written to shared memory
@@ -58,7 +60,8 @@ struct Cfg {
   static constexpr int NSTAGES_RAW = (196 * 1024) / STAGE_BYTES;
   static constexpr int NSTAGES = NSTAGES_RAW > 8 ? 8 : NSTAGES_RAW;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int XBUF_BYTES = 64 * 33 * 4;  // gate/up exchange of the fused decode SwiGLU epilogue
+  static constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + XBUF_BYTES;
 };
 
 SB_DEVICE float quick_gelu(float x) { return x / (1.f + __expf(-1.702f * x)); }
@@ -95,6 +98,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t tfull0 = smem_u32(bars + 2 * NSTAGES);
   const uint32_t tempty0 = smem_u32(bars + 2 * NSTAGES + 2);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGES + 4);
+  float* xbuf = reinterpret_cast<float*>(smem + NSTAGES * C::STAGE_BYTES + 256);
   const uint32_t smem_base = smem_u32(smem);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -129,7 +133,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // first ring of A tiles is requested BEFORE waiting for the preceding kernels -- the weight stream starts while
       // the small kernel that produces the activations (B operand) is still running.
       int pre = 0;
-      if constexpr (EPI == SB_EPI_F32T) {
+      int tr = -1;
+      if constexpr (EPI == SB_EPI_F32T || EPI == SB_EPI_F32T_SWIGLU) {
+        if (blockIdx.x == 0) { tr = sb_trace_begin(SB_TR_GEMV); *reinterpret_cast<volatile int*>(tmem_slot + 1) = tr; }
         for (int t = blockIdx.x; t < total_tiles && pre < NSTAGES; t += gridDim.x) {
           const int mt = t % p.m_tiles;
           const int ks = t / (p.m_tiles * p.n_tiles);
@@ -143,6 +149,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
       pdl_wait();
+      sb_trace_mark(tr, 1);
       int stage = 0;
       uint32_t phase = 0;
       int issued = 0;
@@ -177,16 +184,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
         }
       }
-      if constexpr (EPI == SB_EPI_F32T) {
+      if constexpr (EPI == SB_EPI_F32T || EPI == SB_EPI_F32T_SWIGLU) {
         // Weight streaming never pauses: while the small kernels between two GEMVs run (HBM otherwise idle), the
         // next weight matrix is already on its way into L2.  Each CTA prefetches its 1/gridDim slice.
-        if (p.prefetch_bytes > 0) {
-          constexpr long long CH = 16384;
-          const long long n_ch = (p.prefetch_bytes + CH - 1) / CH;
+        constexpr long long CH = 16384;
+#pragma unroll 1
+        for (int which = 0; which < 2; ++which) {
+          const uint8_t* base = which ? p.prefetch2 : p.prefetch;
+          const long long bytes = which ? p.prefetch2_bytes : p.prefetch_bytes;
+          const long long n_ch = (bytes + CH - 1) / CH;
           for (long long c = blockIdx.x; c < n_ch; c += gridDim.x) {
             const long long off = c * CH;
-            const long long len = min(CH, p.prefetch_bytes - off);
-            l2_prefetch_bulk(p.prefetch + off, (uint32_t)(len & ~15LL));
+            const long long len = min(CH, bytes - off);
+            l2_prefetch_bulk(base + off, (uint32_t)(len & ~15LL));
           }
         }
       }
@@ -262,6 +272,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (col < p.N) out[((long long)ks * p.N + col) * p.ldd + row] = __uint_as_float(r[j]);
           }
         }
+      } else if constexpr (EPI == SB_EPI_F32T_SWIGLU) {
+        // decode gate|up GEMV (swap-AB, no split-K) with SwiGLU fused: the tile's 128 weight rows are [64 gate | 64 up]
+        // of the same 64 activation columns, i.e. gate sits in TMEM lanes 0-63 (epilogue warps 0,1) and up in lanes
+        // 64-127 (warps 2,3).  Warps 2,3 hand their values over through shared memory; warps 0,1 write
+        // act[r][c] = bf16( bf16(silu(bf16 g)) * bf16 u ) for the <= BN decode rows r.
+        static_assert(BN == 16 || BN == 32, "decode tile");
+        uint32_t r[BN];
+        if constexpr (BN == 16) tmem_ld_32x16(taddr, r);
+        else tmem_ld_32x32(taddr, r);
+        tmem_ld_wait();
+        if (q >= 2) {
+#pragma unroll
+          for (int j = 0; j < BN; ++j) xbuf[(row_in_tile - 64) * 33 + j] = __uint_as_float(r[j]);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (q < 2) {
+          bf16* Dp = reinterpret_cast<bf16*>(p.D);
+          const int c = mt * 64 + row_in_tile;   // activation column
+#pragma unroll
+          for (int j = 0; j < BN; ++j) {
+            const int drow = col_base + j;       // decode row
+            if (drow < p.N) {
+              const float g = bf16_round(__uint_as_float(r[j]));
+              const float u = bf16_round(xbuf[row_in_tile * 33 + j]);
+              Dp[(long long)drow * p.ldd + c] = __float2bfloat16_rn(bf16_round(silu(g)) * u);
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // xbuf is free for the next tile
       } else if constexpr (EPI == SB_EPI_SWIGLU) {
         // weight rows are interleaved [64 gate | 64 up] per 128 output columns of the fused gate/up
         // matrix; D gets silu(gate)*up (N/2 columns), aux (optional) the raw [gate|up] tile.
@@ -394,6 +433,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (EPI == SB_EPI_F32T || EPI == SB_EPI_F32T_SWIGLU) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) sb_trace_mark(*reinterpret_cast<volatile int*>(tmem_slot + 1), 2);
+  }
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
@@ -486,9 +528,11 @@ int launch(const sb_gemm_args* a, cudaStream_t stream) {
   p.lse = a->lse; p.coef = a->coef;
   p.prefetch = reinterpret_cast<const uint8_t*>(a->prefetch);
   p.prefetch_bytes = a->prefetch ? a->prefetch_bytes : 0;
+  p.prefetch2 = reinterpret_cast<const uint8_t*>(a->prefetch2);
+  p.prefetch2_bytes = a->prefetch2 ? a->prefetch2_bytes : 0;
   const int total = p.m_tiles * p.n_tiles * p.k_splits;
   const int grid = total < num_sms() ? total : num_sms();
-  const bool pdl = (EPI == SB_EPI_F32T) && sb_pdl_enabled();
+  const bool pdl = (EPI == SB_EPI_F32T || EPI == SB_EPI_F32T_SWIGLU) && sb_pdl_enabled();
   cudaError_t le = sb_launch(kfn, dim3(grid), dim3(GEMM_THREADS), (size_t)C::SMEM_BYTES, stream, pdl, tmA, tmB, p);
   if (le != cudaSuccess) {
     sb_set_error("sb_gemm: launch failed: %s", cudaGetErrorString(le));
@@ -498,6 +542,8 @@ int launch(const sb_gemm_args* a, cudaStream_t stream) {
 }
 
 }  // namespace
+
+SB_DEFINE_TRACE_SETTER(sb_trace_set_gemm)
 
 extern "C" int sb_gemm_effective_splits(int K, int k_splits) {
   int k_iters = (K + BK - 1) / BK;
@@ -526,6 +572,17 @@ extern "C" int sb_gemm(const sb_gemm_args* a, sb_stream_t stream_) {
                "sb_gemm: prefetch pointer must be 16-byte aligned");
     if (a->N <= 16) return launch<false, false, 16, SB_EPI_F32T>(a, stream);
     return launch<false, false, 32, SB_EPI_F32T>(a, stream);
+  }
+  if (e == SB_EPI_F32T_SWIGLU) {
+    SB_REQUIRE(!amn && !bmn, "sb_gemm: F32T_SWIGLU epilogue needs K-major operands");
+    SB_REQUIRE(a->N <= 32, "sb_gemm: F32T_SWIGLU epilogue is for N<=32 (decode rows), got %d", a->N);
+    SB_REQUIRE(a->M % 128 == 0, "sb_gemm: F32T_SWIGLU needs M %% 128 == 0 (interleaved gate/up rows), got %d", a->M);
+    SB_REQUIRE(a->k_splits <= 1, "sb_gemm: F32T_SWIGLU cannot be split along K");
+    SB_REQUIRE(a->ldd >= a->M / 2, "sb_gemm: F32T_SWIGLU ldd (%lld) < M/2 (%d)", a->ldd, a->M / 2);
+    SB_REQUIRE(a->prefetch == nullptr || (reinterpret_cast<uintptr_t>(a->prefetch) & 15) == 0,
+               "sb_gemm: prefetch pointer must be 16-byte aligned");
+    if (a->N <= 16) return launch<false, false, 16, SB_EPI_F32T_SWIGLU>(a, stream);
+    return launch<false, false, 32, SB_EPI_F32T_SWIGLU>(a, stream);
   }
   SB_REQUIRE(a->N % 8 == 0 && a->ldd % 8 == 0, "sb_gemm: N and ldd must be multiples of 8");
   SB_REQUIRE(a->k_splits <= 1, "sb_gemm: split-K only with the F32T epilogue");

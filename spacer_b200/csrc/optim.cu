@@ -43,6 +43,39 @@ struct AdamArgs {
   float grad_scale;   // extra factor on gradients (e.g. 1/world_size after a sum all-reduce)
 };
 
+// 4 consecutive elements per thread: 16-byte loads/stores of master, m, v (fp32), 8-byte of grad/param (bf16)
+template <typename T>
+SB_DEVICE void ld4(const T* p, long long i, float* o);
+template <>
+SB_DEVICE void ld4<float>(const float* p, long long i, float* o) {
+  const float4 v = *reinterpret_cast<const float4*>(p + i);
+  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+template <>
+SB_DEVICE void ld4<bf16>(const bf16* p, long long i, float* o) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p + i);
+  const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+}
+SB_DEVICE void st4(float* p, long long i, const float* v) {
+  *reinterpret_cast<float4*>(p + i) = make_float4(v[0], v[1], v[2], v[3]);
+}
+SB_DEVICE void st4(bf16* p, long long i, const float* v) {
+  uint2 u;
+  u.x = pack_bf16(v[0], v[1]);
+  u.y = pack_bf16(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p + i) = u;
+}
+
+SB_DEVICE void adam_elem(float& w, float& mi, float& vi, float gr, const AdamArgs& a) {
+  mi = a.beta1 * mi + (1.f - a.beta1) * gr;
+  vi = a.beta2 * vi + (1.f - a.beta2) * gr * gr;
+  // torch.optim.AdamW: decoupled decay, then the Adam step with bias correction
+  w *= 1.f - a.lr * a.wd;
+  const float denom = sqrtf(vi) / sqrtf(a.bc2) + a.eps;
+  w -= (a.lr / a.bc1) * (mi / denom);
+}
+
 template <typename GT, typename MT>
 __global__ void __launch_bounds__(256)
 adamw_kernel(bf16* __restrict__ p, float* __restrict__ master, MT* __restrict__ m, MT* __restrict__ v,
@@ -53,18 +86,27 @@ adamw_kernel(bf16* __restrict__ p, float* __restrict__ master, MT* __restrict__ 
     clip = fminf(1.f, a.max_norm / (norm + 1e-6f));
   }
   const float gs = clip * a.grad_scale;
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
-    const float gr = ldg<GT>(g, i) * gs;
-    float w = master[i];
-    float mi, vi;
+  const long long n4 = n / 4;
+  for (long long q = (long long)blockIdx.x * 256 + threadIdx.x; q < n4; q += (long long)gridDim.x * 256) {
+    const long long i = q * 4;
+    float gr[4], w[4], mi[4], vi[4];
+    ld4<GT>(g, i, gr);
+    ld4<float>(master, i, w);
+    ld4<MT>(m, i, mi);
+    ld4<MT>(v, i, vi);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) adam_elem(w[j], mi[j], vi[j], gr[j] * gs, a);
+    st4(master, i, w);
+    st4(m, i, mi);
+    st4(v, i, vi);
+    st4(p, i, w);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (int)(n - n4 * 4)) {   // tail (arenas are 128-element aligned: normally empty)
+    const long long i = n4 * 4 + threadIdx.x;
+    float w = master[i], mi, vi;
     if constexpr (sizeof(MT) == 2) { mi = __bfloat162float(m[i]); vi = __bfloat162float(v[i]); }
     else { mi = m[i]; vi = v[i]; }
-    mi = a.beta1 * mi + (1.f - a.beta1) * gr;
-    vi = a.beta2 * vi + (1.f - a.beta2) * gr * gr;
-    // torch.optim.AdamW: decoupled decay, then the Adam step with bias correction
-    w *= 1.f - a.lr * a.wd;
-    const float denom = sqrtf(vi) / sqrtf(a.bc2) + a.eps;
-    w -= (a.lr / a.bc1) * (mi / denom);
+    adam_elem(w, mi, vi, ldg<GT>(g, i) * gs, a);
     master[i] = w;
     if constexpr (sizeof(MT) == 2) { m[i] = __float2bfloat16_rn(mi); v[i] = __float2bfloat16_rn(vi); }
     else { m[i] = mi; v[i] = vi; }
@@ -94,6 +136,9 @@ extern "C" int sb_adamw_step(void* param_bf16, float* master, void* m, void* v, 
                              float beta2, float eps, float weight_decay, int step, float max_norm, float grad_scale,
                              sb_stream_t stream) {
   SB_REQUIRE(param_bf16 && master && m && v && grad && n > 0 && step >= 1, "sb_adamw_step: bad arguments");
+  SB_REQUIRE(((reinterpret_cast<uintptr_t>(param_bf16) | reinterpret_cast<uintptr_t>(master) | reinterpret_cast<uintptr_t>(m) |
+               reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(grad)) & 15) == 0,
+             "sb_adamw_step: arenas must be 16-byte aligned");
   AdamArgs a;
   a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = weight_decay;
   a.bc1 = 1.f - powf(beta1, (float)step);

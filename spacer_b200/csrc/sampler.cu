@@ -130,7 +130,9 @@ SB_DEVICE bool kept_token(uint32_t k, uint32_t kstar, int& tie_rank, int n_drop)
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(ST)
 sample_kernel(const SampleParams p) {
   pdl_launch_dependents();
+  const int tr = (blockIdx.x == 0 && threadIdx.x == 0) ? sb_trace_begin(SB_TR_SAMPLE) : -1;
   pdl_wait();
+  sb_trace_mark(tr, 1);
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) uint8_t smem_raw[];
   Shared* sh = reinterpret_cast<Shared*>(smem_raw);
@@ -308,15 +310,21 @@ sample_kernel(const SampleParams p) {
     }
   }
   cluster.sync();  // keep every CTA's shared memory alive until all remote reads are done
+  sb_trace_mark(tr, 2);
 }
 
 __global__ void step_advance_kernel(int* step_ptr) {
   pdl_launch_dependents();
+  const int tr = sb_trace_begin(SB_TR_ADVANCE);
   pdl_wait();
+  sb_trace_mark(tr, 1);
   *step_ptr += 1;
+  sb_trace_mark(tr, 2);
 }
 
 }  // namespace
+
+SB_DEFINE_TRACE_SETTER(sb_trace_set_sampler)
 
 extern "C" int sb_sample_top_p(const float* logits, long long ld, int R, int V, float top_p, unsigned long long seed,
                                const int* step_ptr, int* finished, int* out_tokens, int* out_ids, long long out_ld,

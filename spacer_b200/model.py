@@ -459,7 +459,7 @@ class Qwen2VLB200:
                 p = f"l.{i}."
                 self._gemv(W[p + "qkv_w"], st["xn"], st["p_qkv"], S["qkv"])
                 self._gemv(W[p + "o_w"], st["attn"], st["p_o"], S["o"])
-                self._gemv(W[p + "gu_w"], st["xn"], st["p_gu"], S["gu"])
+                self._gemv(W[p + "gu_w"], st["xn"], st["act"], 1, swiglu=True)
                 self._gemv(W[p + "down_w"], st["act"], st["p_down"], S["down"])
             self._gemv(W["lm_head"], st["xn"], st["logits"], 1)
 
@@ -476,14 +476,24 @@ class Qwen2VLB200:
         return dict(gbs=byts / (ms * 1e-3) / 1e9, bytes_per_launch=byts / launches, avg_us=ms * 1e3 / launches,
                     launches=launches, ms_per_sweep=ms)
 
-    L2_PREFETCH_BYTES = 16 << 20     # how much of the next weight matrix a decode GEMV asks L2 to fetch ahead
-                                     # (measured on cfg3: 0 MB 3.25 ms/step, 16 MB 3.21, 48 MB 3.26, 96 MB 3.30)
+    # L2 prefetch plan of the decode step: behind its own loads every GEMV asks L2 for the head of the matrices that
+    # come next, sized to the HBM-idle window that follows it (the small kernels + dependency gaps, see
+    # profiles/r01_decode_trace.txt): after qkv comes the ~24 us attention window -> all of o_w plus the head of gate|up.
+    L2_PREFETCH_BYTES = 16 << 20          # default window after a GEMV (o, gate|up, down, lm_head)
+    L2_PREFETCH_ATTN_BYTES = 48 << 20     # head of gate|up requested behind the qkv GEMV
 
-    def _gemv(self, w, x16, out_parts, splits, next_w=None):
+    def _gemv(self, w, x16, out_parts, splits, next_w=None, swiglu=False, next2_w=None, next_bytes=None, next2_bytes=0):
         """parts[s][r][n] = x16[r] . w[n] over K split s   (swap-AB tcgen05 GEMM, weights streamed once).
-        next_w: the weight matrix the decode step reads next; its head is prefetched into L2 behind this GEMV."""
-        nb = 0 if next_w is None else min(next_w.numel() * 2, self.L2_PREFETCH_BYTES)
-        ops.gemm(w, x16, out=out_parts, epilogue=EPI_F32T, k_splits=splits, prefetch=next_w, prefetch_bytes=nb)
+        next_w / next2_w: weight matrices the decode step reads next; their heads are prefetched into L2 behind this
+        GEMV.  swiglu: w is the interleaved gate|up matrix and out_parts the bf16 activation [rows, I] (fused epilogue)."""
+        cap = self.L2_PREFETCH_BYTES if next_bytes is None else next_bytes
+        nb = 0 if next_w is None else min(next_w.numel() * 2, cap)
+        nb2 = 0 if next2_w is None else min(next2_w.numel() * 2, next2_bytes)
+        kw = dict(prefetch=next_w if nb else None, prefetch_bytes=nb, prefetch2=next2_w if nb2 else None, prefetch2_bytes=nb2)
+        if swiglu:
+            ops.gemm(w, x16, out=out_parts, epilogue=ops.EPI_F32T_SWIGLU, **kw)
+        else:
+            ops.gemm(w, x16, out=out_parts, epilogue=EPI_F32T, k_splits=splits, **kw)
 
     def _splits_for(self, n_out, k):
         m_tiles = (n_out + 127) // 128
@@ -558,7 +568,8 @@ class Qwen2VLB200:
         for i in range(d.layers):
             p = f"l.{i}."
             ops.call("sb_dec_residual_rmsnorm", st["x"], parts, sp, RP * H, H, W[p + "ln1_w"], st["xn"], R, H, d.rms_eps)
-            self._gemv(W[p + "qkv_w"], st["xn"], st["p_qkv"], S["qkv"], next_w=W[p + "o_w"])
+            self._gemv(W[p + "qkv_w"], st["xn"], st["p_qkv"], S["qkv"], next_w=W[p + "o_w"], next_bytes=1 << 30,
+                       next2_w=W[p + "gu_w"], next2_bytes=self.L2_PREFETCH_ATTN_BYTES)
             ops.call("sb_dec_qkv_post", st["p_qkv"], S["qkv"], RP * d.qkv_dim, d.qkv_dim, W[p + "qkv_b"], st["step"],
                      rope_base, float(d.rope_theta), nh, nkv, hd, st["q"], st["kc"][i], st["vc"][i],
                      st["c_max"] * nkv * hd, st["c_max"], R)
@@ -570,8 +581,11 @@ class Qwen2VLB200:
             self._gemv(W[p + "o_w"], st["attn"], st["p_o"], S["o"], next_w=W[p + "gu_w"])
             ops.call("sb_dec_residual_rmsnorm", st["x"], st["p_o"], S["o"], RP * H, H, W[p + "ln2_w"], st["xn"], R, H,
                      d.rms_eps)
-            self._gemv(W[p + "gu_w"], st["xn"], st["p_gu"], S["gu"], next_w=W[p + "down_w"])
-            ops.call("sb_dec_swiglu", st["p_gu"], S["gu"], RP * 2 * I, 2 * I, st["act"], R, I)
+            if S["gu"] == 1:     # SwiGLU fused into the GEMV epilogue (no fp32 partials, one kernel less)
+                self._gemv(W[p + "gu_w"], st["xn"], st["act"], 1, next_w=W[p + "down_w"], swiglu=True)
+            else:
+                self._gemv(W[p + "gu_w"], st["xn"], st["p_gu"], S["gu"], next_w=W[p + "down_w"])
+                ops.call("sb_dec_swiglu", st["p_gu"], S["gu"], RP * 2 * I, 2 * I, st["act"], R, I)
             self._gemv(W[p + "down_w"], st["act"], st["p_down"], S["down"],
                        next_w=W[f"l.{i + 1}.qkv_w"] if i + 1 < d.layers else W["lm_head"])
             parts, sp = st["p_down"], S["down"]

@@ -123,3 +123,22 @@ def test_gemm_lmhead_and_dlogits():
     oh = torch.nn.functional.one_hot(tg.long(), V).float()
     ref_d = coef[:, None] * (oh - p)
     assert (d.float() - ref_d).abs().max().item() < 1e-2 * ref_d.abs().max().item() + 1e-5
+
+
+@pytest.mark.parametrize("R,I,K", [(12, 512, 256), (16, 18944, 3584), (24, 1024, 512)])
+def test_gemm_f32t_swiglu_decode(R, I, K):
+    """Decode gate|up GEMV with the SwiGLU fused into the swap-AB epilogue == unfused partials + sb_dec_swiglu math."""
+    from spacer_b200 import ops
+    RP = 16 if R <= 16 else 32
+    g = torch.Generator(device="cuda").manual_seed(5)
+    w = (torch.randn(2 * I, K, device="cuda", generator=g) * 0.05).bfloat16()
+    x = torch.zeros(RP, K, device="cuda", dtype=torch.bfloat16)
+    x[:R] = torch.randn(R, K, device="cuda", generator=g).bfloat16()
+    act = torch.full((RP, I), 7.0, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(w, x, out=act, epilogue=ops.EPI_F32T_SWIGLU)
+    gu = (x.float() @ w.float().t()).bfloat16().float().view(RP, I // 64, 2, 64)
+    ref = (torch.nn.functional.silu(gu[:, :, 0]).bfloat16().float() * gu[:, :, 1]).reshape(RP, I)
+    err = (act.float() - ref).abs().max().item()
+    assert err < 2e-2 * ref.abs().max().item() + 1e-3, err
+    with pytest.raises(ops.SpacerError):
+        ops.gemm(w, x, out=act, epilogue=ops.EPI_F32T_SWIGLU, k_splits=2)

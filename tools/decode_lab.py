@@ -2,6 +2,7 @@
 """A/B timing of the decode step on one B200 (cfg3 shapes): PDL on/off, L2 weight prefetch size, per-GEMV cold/warm/hot.
 Prints one JSON line per experiment.   python tools/decode_lab.py [--config c3]"""
 import argparse
+import ctypes
 import json
 import os
 import sys
@@ -54,12 +55,12 @@ def main():
     flush = torch.empty(512 << 20, device=dev, dtype=torch.uint8)
 
     if "step" in a.exp:
-        for pdl in (1, 0):
-            for pf in (48 << 20, 0, 16 << 20, 96 << 20):
-                if pdl == 0 and pf not in (0, 48 << 20):
-                    continue
+        for pdl, pf, pfa in ((1, 16, 48), (1, 16, 0), (1, 16, 24), (1, 16, 72), (1, 32, 48), (1, 8, 48), (1, 0, 0), (0, 16, 48)):
+            if True:
+                pf <<= 20
                 lib.sb_set_pdl(pdl)
                 m.L2_PREFETCH_BYTES = pf
+                m.L2_PREFETCH_ATTN_BYTES = pfa << 20
                 st["graphs"].clear()
                 st["step"].fill_(200)
                 graph, nodes = m._decode_graph(st, nxt, G, 0.95, True)
@@ -70,10 +71,54 @@ def main():
                 ms = timed(graph.replay, 100)
                 kv = 2 * dims.layers * dims.kv_heads * dims.head_dim * 2
                 byts = wbytes + 2 * ids.numel() * kv + (G + G // 2) * 250 * kv
-                print(json.dumps({"exp": "decode_step_graph", "pdl": pdl, "l2_prefetch_mb": pf >> 20, "ms": round(ms, 4),
+                print(json.dumps({"exp": "decode_step_graph", "pdl": pdl, "l2_prefetch_mb": pf >> 20, "l2_prefetch_attn_mb": pfa, "ms": round(ms, 4),
                                   "gbs": round(byts / ms / 1e6, 1), "nodes": nodes}), flush=True)
         lib.sb_set_pdl(1)
-        m.L2_PREFETCH_BYTES = 48 << 20
+        m.L2_PREFETCH_BYTES = 16 << 20
+        m.L2_PREFETCH_ATTN_BYTES = 48 << 20
+
+    for trace_cfg in ([(16, 48), (0, 0)] if "trace" in a.exp else []):
+        m.L2_PREFETCH_BYTES, m.L2_PREFETCH_ATTN_BYTES = trace_cfg[0] << 20, trace_cfg[1] << 20
+        KINDS = {1: "gemv", 2: "embed", 3: "rmsnorm", 4: "qkv_post", 5: "attn", 6: "combine", 7: "swiglu", 8: "sample", 9: "advance"}
+        cap = 4096
+        buf = torch.zeros(1 + 4 * cap, device=dev, dtype=torch.int64)
+        st["graphs"].clear()
+        st["step"].fill_(200)
+        graph, nodes = m._decode_graph(st, nxt, G, 0.95, True)
+        for _ in range(3):
+            graph.replay()
+        torch.cuda.synchronize()
+        lib.sb_trace_enable(ctypes.c_void_p(buf.data_ptr()), cap)
+        graph.replay()
+        graph.replay()
+        torch.cuda.synchronize()
+        lib.sb_trace_enable(None, 0)
+        h = buf.cpu().tolist()
+        n = min(h[0], cap)
+        recs = [(h[1 + 4 * k], h[2 + 4 * k], h[3 + 4 * k], h[4 + 4 * k]) for k in range(n)]
+        recs.sort(key=lambda r: r[1])
+        # second replay only (steady state): records after the first sampler
+        idx = [i for i, r in enumerate(recs) if r[0] == 8]
+        one = recs[idx[0] + 1: idx[1] + 1] if len(idx) >= 2 else recs
+        t0 = one[0][1]
+        out_path = os.path.join(ROOT, "gpurun_out", f"decode_trace_pf{trace_cfg[0]}_{trace_cfg[1]}.txt")
+        os.makedirs(os.path.dirname(out_path), exist_ok=True)
+        agg = {}
+        with open(out_path, "w") as f:
+            f.write("# kind entry_us ready_us end_us | wait_us exec_us gap_from_prev_end_us   (block 0 of every kernel, globaltimer)\n")
+            prev_end = None
+            for kind, te, tr_, tn in one:
+                name = KINDS.get(kind, str(kind))
+                gap = (tr_ - prev_end) / 1e3 if prev_end else 0.0
+                f.write(f"{name:9s} {(te - t0) / 1e3:9.2f} {(tr_ - t0) / 1e3:9.2f} {(tn - t0) / 1e3:9.2f} | {(tr_ - te) / 1e3:7.2f} {(tn - tr_) / 1e3:7.2f} {gap:7.2f}\n")
+                d = agg.setdefault(name, [0, 0.0, 0.0, 0.0])
+                d[0] += 1; d[1] += (tr_ - te) / 1e3; d[2] += (tn - tr_) / 1e3; d[3] += gap
+                prev_end = tn
+        total = (one[-1][3] - t0) / 1e3
+        print(json.dumps({"exp": "trace", "prefetch_mb": trace_cfg, "records": n, "step_kernels": len(one), "step_us": round(total, 1),
+                          "per_kind": {k: {"n": v[0], "wait_us": round(v[1] / v[0], 2), "exec_us": round(v[2] / v[0], 2),
+                                           "gap_after_prev_end_us": round(v[3] / v[0], 2), "exec_total_us": round(v[2], 1),
+                                           "gap_total_us": round(v[3], 1)} for k, v in agg.items()}}), flush=True)
 
     if "gemv" in a.exp:
         W = m.params
