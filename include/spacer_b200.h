@@ -131,6 +131,19 @@ int sb_colsum(const void* dy, float* out, int T, int N, long long ld, sb_stream_
 int sb_f32_to_bf16_2d(const float* src, void* dst, int T, int W, long long ldd, sb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Video front-end: frames [F][C][H][W] (uint8, or float32 holding 0..255 as qwen_vl_utils.fetch_video returns them)
+ * -> pixel_values_videos [gt*gh*gw][C*t_patch*patch*patch] with gt = ceil(F/t_patch), gh = H/patch, gw = W/patch.
+ * replaces Qwen2VLVideoProcessor._preprocess (video_processing_qwen2_vl.py:240-272: fused rescale+normalise in fp32,
+ * last-frame temporal padding, patch permutation), T-GRPO's second processor pass over shuffled frames
+ * (SG_RLVR_trainer.py:442-458; `perm`, device int32 [F], output frame f reads source frame perm[f]) and the bf16 cast
+ * at MQ2:306.  mean_host/std_host: C floats on the HOST, already divided by the rescale factor (mean*255, std*255).
+ * out_f32 is bit-exact with the HF CPU path; out_bf16 is what sb_gemm consumes.  Either output may be NULL.
+ * ------------------------------------------------------------------------------------------------ */
+int sb_video_patchify(const void* frames, int frames_are_u8, int F, int C, int H, int W, const int* perm,
+                      const float* mean_host, const float* std_host, int patch, int t_patch, int merge, float* out_f32,
+                      void* out_bf16, sb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Attention (flash-style, varlen/prefix mask).  replaces flash_attn_varlen_func / sdpa under MQ2:415-454
  * (ViT, head_dim 80, block-diagonal) and MQ2:575-590 (Qwen2 causal GQA, head_dim 128).
  * meta: int32 [T][4] = (prefix_len, seg_start, kv_end, 0): key j visible to query t iff

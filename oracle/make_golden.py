@@ -314,9 +314,60 @@ def gen_tiny_model():
     print("tiny_model.pt: loss", float(loss), "kl", float(mean_kl), "lp[0,:4]", lp[0, :4].tolist())
 
 
+def gen_vision():
+    """Golden vectors for the video front-end:
+      * smart_resize / smart_nframes / frame indices from the reference's OWN vendored qwen-vl-utils
+        (/root/reference/SpaceR-SG-RLVR/src/qwen-vl-utils/src/qwen_vl_utils/vision_process.py), over a grid of inputs;
+      * pixel_values_videos of the real HF Qwen2VLVideoProcessor (transformers 5.5.0, do_resize=False) on small random
+        uint8 videos (even and odd frame counts)."""
+    sys.path.insert(0, "/root/reference/SpaceR-SG-RLVR/src/qwen-vl-utils/src")
+    from qwen_vl_utils import vision_process as VP
+    rng = random.Random(7)
+    resize = []
+    for _ in range(200):
+        h, w = rng.randint(28, 2200), rng.randint(28, 2200)
+        for mn, mx in ((VP.VIDEO_MIN_PIXELS, VP.VIDEO_MAX_PIXELS), (VP.MIN_PIXELS, VP.MAX_PIXELS), (4 * 28 * 28, 448 * 28 * 28)):
+            try:
+                out = list(VP.smart_resize(h, w, factor=VP.IMAGE_FACTOR, min_pixels=mn, max_pixels=mx))
+            except ValueError:
+                out = "ValueError"
+            resize.append([h, w, mn, mx, out])
+    nframes = []
+    for _ in range(200):
+        total = rng.randint(2, 4000)
+        fps_v = rng.choice([23.976, 24, 25, 29.97, 30, 60, 15, 10.5])
+        ele = rng.choice([{}, {"fps": 1.0}, {"fps": 4.0}, {"nframes": rng.randint(2, 40)}, {"min_frames": 6, "max_frames": 12},
+                          {"fps": 2.0, "max_frames": 32}])
+        try:
+            n = VP.smart_nframes(dict(ele), total_frames=total, video_fps=fps_v)
+            idx = torch.linspace(0, total - 1, n).round().long().tolist()
+        except (ValueError, AssertionError) as e:
+            n, idx = type(e).__name__, None
+        nframes.append([ele, total, fps_v, n, idx])
+    with open(os.path.join(OUT, "vision.json"), "w") as f:
+        json.dump({"source": "qwen_vl_utils.vision_process (vendored in the reference)", "smart_resize": resize,
+                   "smart_nframes": nframes}, f)
+    from transformers.models.qwen2_vl.video_processing_qwen2_vl import Qwen2VLVideoProcessor
+    proc = Qwen2VLVideoProcessor(do_resize=False, do_sample_frames=False)
+    cases = []
+    g = torch.Generator().manual_seed(21)
+    for F_, H, W in ((4, 56, 84), (3, 28, 56), (2, 112, 28)):
+        video = torch.randint(0, 256, (F_, 3, H, W), generator=g, dtype=torch.uint8)
+        out = proc(videos=[video], return_tensors="pt")
+        cases.append({"video": video, "pixel_values_videos": out["pixel_values_videos"].clone(),
+                      "video_grid_thw": out["video_grid_thw"].clone()})
+    torch.save({"cases": cases, "transformers_version": __import__("transformers").__version__,
+                "image_mean": list(proc.image_mean), "image_std": list(proc.image_std),
+                "rescale_factor": float(proc.rescale_factor)}, os.path.join(OUT, "video_processor.pt"))
+    print("vision.json:", len(resize), "resize cases,", len(nframes), "nframes cases; video_processor.pt:",
+          [tuple(c["pixel_values_videos"].shape) for c in cases])
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["rewards", "tiny"]
+    which = sys.argv[1:] or ["rewards", "tiny", "vision"]
+    if "vision" in which:
+        gen_vision()
     if "rewards" in which:
         gen_rewards()
     if "tiny" in which:

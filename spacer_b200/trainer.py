@@ -17,6 +17,7 @@ import torch
 
 from . import dist as D
 from . import ops
+from . import vision
 from .model import GradStore, Qwen2VLB200, pack_prompt_completions
 from .params import ParamStore
 
@@ -132,6 +133,13 @@ class SGRLVRTrainerB200:
         """TRN:442-481: G completions of the prompt (+ G/2 of the frame-shuffled video when temporal)."""
         c = self.cfg
         G = c.num_generations
+        frames = example.get("video_frames")
+        if frames is not None:
+            # GPU front-end (SURVEY 8(f) row 2): rescale + normalise + patchify + bf16 cast in one kernel; the T-GRPO
+            # frame shuffle (TRN:442-458) is an index permutation inside the same kernel instead of a second
+            # processor pass
+            pix, _, grid = vision.patchify(frames)
+            example["pixel_values_videos"], example["video_grid_thw"] = pix, grid
         pix = example["pixel_values_videos"]
         grid = example["video_grid_thw"]
         ids = example["input_ids"]
@@ -139,7 +147,12 @@ class SGRLVRTrainerB200:
             ids = ids[..., -c.max_prompt_length:]                    # TRN:432-440
         kw = dict(max_new_tokens=c.max_completion_length, top_p=TOP_P, seed=seed, min_new_tokens=c.min_new_tokens)
         if c.temporal and pix is not None:
-            pix2 = self.shuffle_frames(pix, grid, seed)
+            if frames is not None:
+                g = torch.Generator(device="cpu").manual_seed(int(seed) + 7919)
+                perm = torch.randperm(frames.shape[0], generator=g).to(torch.int32).to(frames.device)
+                pix2, _, _ = vision.patchify(frames, perm)
+            else:
+                pix2 = self.shuffle_frames(pix, grid, seed)
             main, shuf = self.model.generate(ids, pix, grid, num_return_sequences=G, pixel_values_videos_2=pix2,
                                              num_return_sequences_2=G // 2, **kw)
             self.last_rollout_stats = self.model.last_generate_stats
@@ -170,7 +183,8 @@ class SGRLVRTrainerB200:
         completions = [[{"role": "assistant", "content": s}] for s in completions_text]
         per_func = torch.zeros(G, len(self.reward_funcs), device=self.model.device)
         extra = {k: [example[k]] * G for k in example
-                 if k not in ("prompt", "completion", "input_ids", "pixel_values_videos", "video_grid_thw", "path")}
+                 if k not in ("prompt", "completion", "input_ids", "pixel_values_videos", "video_grid_thw", "path",
+                              "video_frames")}
         for i, fn in enumerate(self.reward_funcs):
             out = fn(prompts=prompts, completions=completions, path=[example.get("path", "")] * G, **extra)  # TRN:592
             per_func[:, i] = torch.tensor([float(x) for x in out], device=self.model.device)

@@ -1,0 +1,116 @@
+"""Video front-end of the SG-RLVR step: the integer logic of the reference's vendored qwen-vl-utils
+(/root/reference/SpaceR-SG-RLVR/src/qwen-vl-utils/src/qwen_vl_utils/vision_process.py, "QVU") and the HF video
+processor's rescale/normalise/patchify on the GPU (sb_video_patchify).
+
+Host side (pure Python integers, checked against the reference's own functions via tests/golden/vision.json):
+    smart_resize      QVU:61-87     target (h, w): multiples of 28 inside [min_pixels, max_pixels]
+    smart_nframes     QVU:145-182   frame count from fps / min / max, floored to a multiple of 2
+    frame_indices     QVU:246       torch.linspace(0, total - 1, nframes).round().long()
+Device side:
+    patchify(frames[, perm])  ->  pixel_values_videos (bf16 for the ViT and/or fp32 bit-exact with HF), video_grid_thw
+Video decoding (decord) and the bicubic-antialias resize (QVU:310-315) are not part of this module: frames arrive
+decoded and resized, as uint8 or float TCHW.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import ops
+from .ops import SpacerError
+
+IMAGE_FACTOR = 28
+MIN_PIXELS = 4 * 28 * 28
+MAX_PIXELS = 256 * 28 * 28
+MAX_RATIO = 200
+VIDEO_MIN_PIXELS = 128 * 28 * 28        # QVU:32-33 (the SpaceR fork pins min == max == 128*28*28)
+VIDEO_MAX_PIXELS = 128 * 28 * 28
+FRAME_FACTOR = 2
+FPS = 2.0
+FPS_MIN_FRAMES = 4
+FPS_MAX_FRAMES = 16
+CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)      # transformers/utils/constants.py:5-6
+CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+def round_by_factor(number, factor):
+    return round(number / factor) * factor           # Python round: half to even, like the reference (QVU:48)
+
+
+def ceil_by_factor(number, factor):
+    return math.ceil(number / factor) * factor
+
+
+def floor_by_factor(number, factor):
+    return math.floor(number / factor) * factor
+
+
+def smart_resize(height, width, factor=IMAGE_FACTOR, min_pixels=MIN_PIXELS, max_pixels=MAX_PIXELS):
+    """QVU:61-87."""
+    if max(height, width) / min(height, width) > MAX_RATIO:
+        raise ValueError(f"absolute aspect ratio must be smaller than {MAX_RATIO}, got {max(height, width) / min(height, width)}")
+    h_bar = max(factor, round_by_factor(height, factor))
+    w_bar = max(factor, round_by_factor(width, factor))
+    if h_bar * w_bar > max_pixels:
+        beta = math.sqrt((height * width) / max_pixels)
+        h_bar = floor_by_factor(height / beta, factor)
+        w_bar = floor_by_factor(width / beta, factor)
+    elif h_bar * w_bar < min_pixels:
+        beta = math.sqrt(min_pixels / (height * width))
+        h_bar = ceil_by_factor(height * beta, factor)
+        w_bar = ceil_by_factor(width * beta, factor)
+    return h_bar, w_bar
+
+
+def smart_nframes(ele: dict, total_frames: int, video_fps) -> int:
+    """QVU:145-182."""
+    if "fps" in ele and "nframes" in ele:
+        raise AssertionError("Only accept either `fps` or `nframes`")
+    if "nframes" in ele:
+        nframes = round_by_factor(ele["nframes"], FRAME_FACTOR)
+    else:
+        fps = ele.get("fps", FPS)
+        min_frames = ceil_by_factor(ele.get("min_frames", FPS_MIN_FRAMES), FRAME_FACTOR)
+        max_frames = floor_by_factor(ele.get("max_frames", min(FPS_MAX_FRAMES, total_frames)), FRAME_FACTOR)
+        nframes = total_frames / video_fps * fps
+        nframes = min(min(max(nframes, min_frames), max_frames), total_frames)
+        nframes = floor_by_factor(nframes, FRAME_FACTOR)
+    if not (FRAME_FACTOR <= nframes and nframes <= total_frames):
+        raise ValueError(f"nframes should in interval [{FRAME_FACTOR}, {total_frames}], but got {nframes}.")
+    return nframes
+
+
+def frame_indices(total_frames: int, nframes: int) -> list[int]:
+    """QVU:246 (decord path) / QVU:213 (torchvision path)."""
+    return torch.linspace(0, total_frames - 1, nframes).round().long().tolist()
+
+
+def fused_mean_std(rescale_factor: float = 1 / 255, mean=CLIP_MEAN, std=CLIP_STD):
+    """HF's fused rescale+normalise constants (image_processing_backends.py:292-306): fp32 mean * (1 / rescale_factor)."""
+    m = torch.tensor(mean) * (1.0 / rescale_factor)
+    s = torch.tensor(std) * (1.0 / rescale_factor)
+    return m.tolist(), s.tolist()
+
+
+def patchify(frames: torch.Tensor, perm: torch.Tensor | None = None, *, patch=14, t_patch=2, merge=2, want_f32=False,
+             want_bf16=True, rescale_factor=1 / 255, mean=CLIP_MEAN, std=CLIP_STD):
+    """frames: CUDA uint8 or float32 [F, 3, H, W] with H, W multiples of patch*merge.  perm: optional int32 [F] on the
+    device.  Returns (pixel_values bf16 or None, pixel_values fp32 or None, video_grid_thw LongTensor [1, 3])."""
+    if not frames.is_cuda or frames.dtype not in (torch.uint8, torch.float32) or frames.dim() != 4:
+        raise SpacerError("patchify: frames must be a CUDA uint8/float32 tensor [F, C, H, W]")
+    frames = frames.contiguous()
+    F_, Cc, H, W = frames.shape
+    gt, gh, gw = -(-F_ // t_patch), H // patch, W // patch
+    n, row = gt * gh * gw, Cc * t_patch * patch * patch
+    o32 = torch.empty((n, row), device=frames.device, dtype=torch.float32) if want_f32 else None
+    o16 = torch.empty((n, row), device=frames.device, dtype=torch.bfloat16) if want_bf16 else None
+    m, s = fused_mean_std(rescale_factor, mean, std)
+    mh = (C.c_float * 4)(*(m + [0.0] * (4 - len(m))))
+    sh = (C.c_float * 4)(*(s + [1.0] * (4 - len(s))))
+    if perm is not None and (perm.dtype != torch.int32 or not perm.is_cuda or perm.numel() != F_):
+        raise SpacerError("patchify: perm must be a CUDA int32 tensor with one entry per frame")
+    ops.call("sb_video_patchify", frames, int(frames.dtype == torch.uint8), F_, Cc, H, W, perm,
+             C.cast(mh, C.c_void_p), C.cast(sh, C.c_void_p), patch, t_patch, merge, o32, o16)
+    return o16, o32, torch.tensor([[gt, gh, gw]])

@@ -1,0 +1,42 @@
+"""sb_video_patchify (through the C ABI) vs the real HF video processor's output (golden) and vs the oracle."""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def test_patchify_bit_exact_with_hf_processor():
+    from spacer_b200 import vision as V
+    g = torch.load(os.path.join(GOLD, "video_processor.pt"), weights_only=False)
+    for c in g["cases"]:
+        for frames in (c["video"].cuda(), c["video"].float().cuda()):          # uint8 and float (0..255) frames
+            o16, o32, grid = V.patchify(frames, want_f32=True, want_bf16=True)
+            assert grid.tolist() == c["video_grid_thw"].tolist()
+            assert torch.equal(o32.cpu(), c["pixel_values_videos"])             # fp32: bit-exact with HF on CPU
+            assert torch.equal(o16.cpu(), c["pixel_values_videos"].bfloat16())  # bf16: the cast of MQ2:306
+
+
+def test_patchify_frame_permutation_and_full_size():
+    """T-GRPO's shuffled rollout: permuting frames inside the kernel == patchifying the permuted video (TRN:442-458);
+    checked at the headline size 16 x 448 x 448 against the oracle."""
+    from oracle import vision_ref as VR
+    from spacer_b200 import vision as V
+    from spacer_b200.ops import SpacerError
+    g = torch.Generator().manual_seed(9)
+    frames = torch.randint(0, 256, (16, 3, 448, 448), generator=g, dtype=torch.uint8)
+    perm = torch.randperm(16, generator=g)
+    o16, o32, grid = V.patchify(frames.cuda(), want_f32=True)
+    assert grid.tolist() == [[8, 32, 32]] and o16.shape == (8192, 1176)
+    ref, _ = VR.patchify_ref(frames)
+    assert torch.equal(o32.cpu(), ref)
+    p16, p32, _ = V.patchify(frames.cuda(), perm.to(torch.int32).cuda(), want_f32=True)
+    ref_p, _ = VR.patchify_ref(frames[perm])
+    assert torch.equal(p32.cpu(), ref_p) and torch.equal(p16.cpu(), ref_p.bfloat16())
+    with pytest.raises(SpacerError):
+        V.patchify(torch.zeros(2, 3, 30, 56, dtype=torch.uint8, device="cuda"))   # not a multiple of 28: resize first
