@@ -167,6 +167,8 @@ typedef struct sb_attn_args {
   int* tile_ws;                                /* int32 scratch, sb_attn_bwd_workspace() ints            */
 } sb_attn_args;
 int sb_attn_fwd(const sb_attn_args* args, sb_stream_t stream);
+/* forward implementation: 0 = tcgen05/TMEM/TMA kernel (default), 1 = mma.sync kernel (A/B timing, cross-checks) */
+int sb_set_attn_impl(int impl);
 /* deterministic (no atomics): a key-tile-major kernel produces dK, dV, a query-tile-major kernel produces dQ */
 int sb_attn_bwd(const sb_attn_args* args, sb_stream_t stream);
 int sb_attn_bwd_workspace(int T, int Tk, int n_heads, int n_kv_heads, int head_dim, long long* gqa_ws_elems,

@@ -735,10 +735,21 @@ int launch_bwd(const AttnParams& p, bf16* dq, long long lddq, bf16* gqa_ws, int*
 
 }  // namespace
 
+int sb_attn_fwd_tc(const sb_attn_args* a, cudaStream_t st);   // attention_tc.cu
+namespace {
+int g_attn_impl = 0;   // 0 = tcgen05 forward (default), 1 = mma.sync forward
+}
+extern "C" int sb_set_attn_impl(int impl) {
+  SB_REQUIRE(impl == 0 || impl == 1, "sb_set_attn_impl: 0 = tcgen05 (default), 1 = mma.sync");
+  g_attn_impl = impl;
+  return 0;
+}
+
 extern "C" int sb_attn_fwd(const sb_attn_args* a, sb_stream_t stream) {
   SB_REQUIRE(a && a->q && a->k && a->v && a->o && a->meta, "sb_attn_fwd: null pointer");
   SB_REQUIRE(a->T > 0 && a->n_heads > 0 && a->n_kv_heads > 0 && a->n_heads % a->n_kv_heads == 0, "sb_attn_fwd: bad sizes");
   SB_REQUIRE(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a->ldo % 2 == 0, "sb_attn_fwd: strides must be multiples of 8");
+  if (g_attn_impl == 0) return sb_attn_fwd_tc(a, reinterpret_cast<cudaStream_t>(stream));
   AttnParams p{};
   p.q = (const bf16*)a->q; p.k = (const bf16*)a->k; p.v = (const bf16*)a->v;
   p.ldq = a->ldq; p.ldk = a->ldk; p.ldv = a->ldv;

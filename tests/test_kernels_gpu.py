@@ -233,7 +233,19 @@ def metas(kind, T):
                                                ("prefix_big", 1220, 7, 1, 128), ("slabs", 960, 3, 3, 80),
                                                ("prefix", 250, 4, 1, 128), ("causal", 64, 2, 2, 80),
                                                ("prefix", 333, 14, 2, 128)])
-def test_attention_fwd_bwd(kind, T, nh, nkv, hd):
+@pytest.mark.parametrize("impl", [0, 1])
+def test_attention_fwd_bwd(kind, T, nh, nkv, hd, impl):
+    """impl 0 = tcgen05/TMEM/TMA forward (default), 1 = mma.sync forward; the backward is shared."""
+    from spacer_b200 import ops
+    lib = ops._lib.load()
+    assert lib.sb_set_attn_impl(impl) == 0
+    try:
+        _attention_case(kind, T, nh, nkv, hd)
+    finally:
+        lib.sb_set_attn_impl(0)
+
+
+def _attention_case(kind, T, nh, nkv, hd):
     from spacer_b200 import ops
     W = (nh + 2 * nkv) * hd
     qkv = rnd((T, W), 11, 0.7)
