@@ -236,6 +236,7 @@ def test_grpo_loss_matches_oracle(G, C, V):
     from oracle import grpo_ref as GR
     from spacer_b200 import ops
     K, eos = 128, 77
+    torch.manual_seed(1234 + C)   # fixed data: a bf16 rounding flip of a target logit (p ~ 1e-4 each) would move lp by an ulp
     H, Wm = rnd((G * C, K), 1), rnd((V, K), 2, 0.2)
     comp = torch.randint(0, V, (G, C))
     comp[comp == eos] = 0
