@@ -296,29 +296,48 @@ dec_attn_combine_kernel(const float* __restrict__ o_part, const float* __restric
   if (pair >= n_pairs) return;
   const int lane = threadIdx.x & 31;
   const float* lp = lse_part + (long long)pair * NS;
-  float mx = -INFINITY;
-  for (int s = lane; s < NS; s += 32) mx = fmaxf(mx, lp[s]);
-  mx = warp_max(mx);
+  const float* op = o_part + (long long)pair * NS * HD + lane * 4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   float wsum = 0.f;
-  if (mx > -INFINITY) {
-    // batches of 8 splits: all loads of a batch are issued before any is consumed (the partials sit in L2)
-    const float* op = o_part + (long long)pair * NS * HD + lane * 4;
-    for (int s0 = 0; s0 < NS; s0 += 8) {
-      float4 v[8];
-      float w[8];
+  if (NS <= 32) {
+    // one round trip to L2: the log-sum-exps and ALL partial outputs are requested before anything is consumed
+    const float ls = lane < NS ? lp[lane] : -INFINITY;
+    float4 v[32];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int s = min(s0 + j, NS - 1);
-        v[j] = *reinterpret_cast<const float4*>(op + (long long)s * HD);
-        const float ls = lp[s];
-        w[j] = (s0 + j < NS && ls > -INFINITY) ? exp2f(ls - mx) : 0.f;
+    for (int j = 0; j < 32; ++j)
+      if (j < NS) v[j] = *reinterpret_cast<const float4*>(op + (long long)j * HD);
+    const float mx = warp_max(ls);
+    const float w = ls > -INFINITY ? exp2f(ls - mx) : 0.f;   // mx == -inf only if every partial is empty (w = 0)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float wj = __shfl_sync(0xffffffffu, w, j);
+      if (j < NS && wj != 0.f) {   // empty partials may hold stale bits
+        acc.x += wj * v[j].x; acc.y += wj * v[j].y; acc.z += wj * v[j].z; acc.w += wj * v[j].w;
+        wsum += wj;
       }
+    }
+  } else {
+    float mx = -INFINITY;
+    for (int s = lane; s < NS; s += 32) mx = fmaxf(mx, lp[s]);
+    mx = warp_max(mx);
+    if (mx > -INFINITY) {
+      // batches of 8 splits: all loads of a batch are issued before any is consumed (the partials sit in L2)
+      for (int s0 = 0; s0 < NS; s0 += 8) {
+        float4 v[8];
+        float w[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (w[j] != 0.f) {   // empty partials may hold stale bits
-          acc.x += w[j] * v[j].x; acc.y += w[j] * v[j].y; acc.z += w[j] * v[j].z; acc.w += w[j] * v[j].w;
-          wsum += w[j];
+        for (int j = 0; j < 8; ++j) {
+          const int s = min(s0 + j, NS - 1);
+          v[j] = *reinterpret_cast<const float4*>(op + (long long)s * HD);
+          const float ls = lp[s];
+          w[j] = (s0 + j < NS && ls > -INFINITY) ? exp2f(ls - mx) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (w[j] != 0.f) {   // empty partials may hold stale bits
+            acc.x += w[j] * v[j].x; acc.y += w[j] * v[j].y; acc.z += w[j] * v[j].z; acc.w += w[j] * v[j].w;
+            wsum += w[j];
+          }
         }
       }
     }
