@@ -19,6 +19,7 @@
 #include "spacer_b200.h"
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <cstring>
 
 namespace {
 
@@ -46,7 +47,10 @@ struct GemmParams {
   long long prefetch_bytes;
   const uint8_t* prefetch2;      // second range (the matrix after next)
   long long prefetch2_bytes;
+  sb_dec_fuse dec;               // fused decode-step epilogues (zeroed when unused)
 };
+
+constexpr int DEC_MAX_SPLITS = 8;   // portable cluster size: the K splits of one tile form a cluster
 
 // 16 KB per instruction: cp.async.bulk.prefetch.L2 only warms L2, nothing is written to shared memory
 SB_DEVICE void l2_prefetch_bulk(const void* ptr, uint32_t bytes) {
@@ -60,7 +64,9 @@ struct Cfg {
   static constexpr int NSTAGES_RAW = (196 * 1024) / STAGE_BYTES;
   static constexpr int NSTAGES = NSTAGES_RAW > 8 ? 8 : NSTAGES_RAW;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int XBUF_BYTES = 64 * 33 * 4;  // gate/up exchange of the fused decode SwiGLU epilogue
+  // gate/up exchange of the fused decode SwiGLU epilogue / rotary-partner exchange of DEC_QKV / cross-warp scratch of
+  // DEC_RESID, then 32 per-row scales of the fused decode epilogues
+  static constexpr int XBUF_BYTES = 128 * 33 * 4 + 256;
   static constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + XBUF_BYTES;
 };
 
@@ -83,12 +89,95 @@ SB_DEVICE void ld8(const bf16* p, float* v) {
   v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused decode-step epilogues (SB_EPI_DEC_QKV / SB_EPI_DEC_RESID).  The k_splits CTAs that share one 128-row weight
+// tile form a thread-block CLUSTER (rank = K split).  Ranks > 0 push their fp32 partial tile straight into rank 0's
+// shared memory (st.shared::cluster) and signal an mbarrier there; rank 0 adds the partials in rank order
+// (deterministic) and finishes the tile in registers -- what used to be a separate kernel behind a global-memory
+// round trip.  The 128 epilogue threads act together; named barrier 1 is theirs.
+// ---------------------------------------------------------------------------------------------
+SB_DEVICE void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// qkv tile mt = one head (BM == head_dim == 128), thread = head-dim index `e`, acc[j] = decode row j:
+// bf16(acc + bias), rotary at position rope_base + step for q and k heads (partner element e ^ 64 comes through
+// shared memory), q -> q_out, k/v -> completion-cache slot `step`.  Same arithmetic as dec_qkv_post_kernel.
+template <int BN>
+SB_DEVICE void dec_qkv_finish(const GemmParams& p, int mt, int e, float* acc, float* xch /*[128][BN+1]*/) {
+  const sb_dec_fuse& d = p.dec;
+  const int R = d.R, nh = d.n_heads, nkv = d.n_kv_heads;
+  const float bias = __bfloat162float(p.bias[mt * BM + e]);
+  const int step = *d.step_ptr;
+  const int slot = min(step, d.c_max - 1);
+  if (mt >= nh + nkv) {   // v head: bias only
+    bf16* vd = reinterpret_cast<bf16*>(d.v_cache) + (long long)slot * nkv * BM + (mt - nh - nkv) * BM + e;
+#pragma unroll
+    for (int j = 0; j < BN; ++j)
+      if (j < R) vd[j * d.cache_stride_r] = __float2bfloat16_rn(acc[j] + bias);
+    return;
+  }
+  const int i = e & 63;
+  const float pos = (float)(d.rope_base + step);
+  const float inv_freq = 1.0f / powf(d.theta, (float)(2 * i) / (float)BM);
+  float sn, cs;
+  sincosf(pos * inv_freq, &sn, &cs);
+  cs = bf16_round(cs);
+  sn = bf16_round(sn);
+  if (e < 64) sn = -sn;       // out[i] = a cs - b sn ; out[i + 64] = b cs + a sn   (a = element i, b = element i + 64)
+#pragma unroll
+  for (int j = 0; j < BN; ++j) {
+    acc[j] = bf16_round(acc[j] + bias);
+    xch[e * (BN + 1) + j] = acc[j];
+  }
+  epi_bar();
+  bf16* dst = (mt < nh) ? reinterpret_cast<bf16*>(d.q_out) + mt * BM + e
+                        : reinterpret_cast<bf16*>(d.k_cache) + (long long)slot * nkv * BM + (mt - nh) * BM + e;
+  const long long row_stride = (mt < nh) ? (long long)nh * BM : d.cache_stride_r;
+#pragma unroll
+  for (int j = 0; j < BN; ++j) {
+    const float partner = xch[(e ^ 64) * (BN + 1) + j];
+    const float o = bf16_round(bf16_round(acc[j] * cs) + bf16_round(partner * sn));
+    if (j < R) dst[j * row_stride] = __float2bfloat16_rn(o);
+  }
+  epi_bar();   // xch is free again
+}
+
+// residual tile mt = hidden columns [128 mt, 128 mt + 128), thread = column, acc[j] = decode row j:
+// x += bf16(acc) (dec_residual_rmsnorm's arithmetic; xin = the old x, loaded before the main loop finished),
+// xw = bf16(x * w_next) -- the NEXT norm's weight without its rstd, which the consuming GEMV applies per row in its
+// epilogue -- and ssq_out[mt][r] = sum over the tile of x^2.
+template <int BN>
+SB_DEVICE void dec_resid_finish(const GemmParams& p, int mt, int e, const float* acc, const float* xin, float wn,
+                                float* sred /*[4][32]*/) {
+  const sb_dec_fuse& d = p.dec;
+  const int R = d.R;
+  const int col = mt * BM + e;
+  const bool col_ok = col < p.M;
+  const int lane = e & 31, w = e >> 5;
+  bf16* x = reinterpret_cast<bf16*>(d.x);
+  bf16* xw = reinterpret_cast<bf16*>(d.xw);
+#pragma unroll
+  for (int j = 0; j < BN; ++j) {
+    const float c = bf16_round(bf16_round(acc[j]) + xin[j]);
+    if (col_ok && j < R) {
+      x[(long long)j * p.M + col] = __float2bfloat16_rn(c);
+      xw[(long long)j * p.M + col] = __float2bfloat16_rn(c * wn);
+    }
+    const float sq = warp_sum(col_ok ? c * c : 0.f);
+    if (lane == 0) sred[w * 32 + j] = sq;
+  }
+  epi_bar();
+  if (e < R) d.ssq_out[(long long)mt * d.ld_ssq + e] = (sred[e] + sred[32 + e]) + (sred[64 + e] + sred[96 + e]);
+  epi_bar();
+}
+
 template <bool A_MN, bool B_MN, int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const GemmParams p) {
   using C = Cfg<BN>;
   constexpr int NSTAGES = C::NSTAGES;
+  // the swap-AB weight-streaming GEMVs of the decode step (PDL launch, early weight ring, L2 prefetch of the next matrix)
+  constexpr bool kDec = EPI == SB_EPI_F32T || EPI == SB_EPI_F32T_SWIGLU || EPI == SB_EPI_DEC_QKV || EPI == SB_EPI_DEC_RESID;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -99,6 +188,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t tempty0 = smem_u32(bars + 2 * NSTAGES + 2);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGES + 4);
   float* xbuf = reinterpret_cast<float*>(smem + NSTAGES * C::STAGE_BYTES + 256);
+  float* sscale = xbuf + 128 * 33;                                 // [32] per-decode-row scale (RMSNorm rstd)
+  // cluster split-K reduction (kClu): rank 0 receives the partial tiles of ranks 1.. in red[rank-1][128][BN+4]
+  constexpr bool kClu = EPI == SB_EPI_DEC_QKV || EPI == SB_EPI_DEC_RESID;
+  constexpr int RSTR = BN + 4;
+  float* red = sscale + 64;
+  const uint32_t redbar = smem_u32(bars + 2 * NSTAGES + 6);
+  uint32_t crank = 0, csize = 1;
+  if constexpr (kClu) { crank = cluster_ctarank(); csize = cluster_nctarank(); }
   const uint32_t smem_base = smem_u32(smem);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -115,6 +212,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(tfull0 + 8 * a, 1);
       mbar_init(tempty0 + 8 * a, 4);
     }
+    if constexpr (kClu) mbar_init(redbar, csize > 1 ? csize - 1 : 1);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), C::TMEM_COLS);
@@ -122,8 +220,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if constexpr (kClu) cluster_sync_all();   // rank 0's mbarrier is initialised before any rank signals it
 
   const int total_tiles = p.m_tiles * p.n_tiles * p.k_splits;
+  // tile t = (ks * n_tiles + nt) * m_tiles + mt.  Persistent: CTA b takes t = b, b + grid, ...; cluster mode: exactly
+  // one tile per CTA, (mt, ks) = (cluster index, rank in cluster)
+  int t_begin = blockIdx.x, t_step = gridDim.x;
+  if constexpr (kClu) { t_begin = (int)crank * p.m_tiles + (int)(blockIdx.x / csize); t_step = total_tiles; }
 
   pdl_launch_dependents();
   if (warp == 0) {
@@ -134,9 +237,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // the small kernel that produces the activations (B operand) is still running.
       int pre = 0;
       int tr = -1;
-      if constexpr (EPI == SB_EPI_F32T || EPI == SB_EPI_F32T_SWIGLU) {
+      if constexpr (kDec) {
         if (blockIdx.x == 0) { tr = sb_trace_begin(SB_TR_GEMV); *reinterpret_cast<volatile int*>(tmem_slot + 1) = tr; }
-        for (int t = blockIdx.x; t < total_tiles && pre < NSTAGES; t += gridDim.x) {
+        for (int t = t_begin; t < total_tiles && pre < NSTAGES; t += t_step) {
           const int mt = t % p.m_tiles;
           const int ks = t / (p.m_tiles * p.n_tiles);
           const int kb0 = ks * p.k_iters_per_split;
@@ -153,7 +256,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int stage = 0;
       uint32_t phase = 0;
       int issued = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = t_begin; t < total_tiles; t += t_step) {
         const int mt = t % p.m_tiles;
         const int nt = (t / p.m_tiles) % p.n_tiles;
         const int ks = t / (p.m_tiles * p.n_tiles);
@@ -184,7 +287,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
         }
       }
-      if constexpr (EPI == SB_EPI_F32T || EPI == SB_EPI_F32T_SWIGLU) {
+      if constexpr (kDec) {
         // Weight streaming never pauses: while the small kernels between two GEMVs run (HBM otherwise idle), the
         // next weight matrix is already on its way into L2.  Each CTA prefetches its 1/gridDim slice.
         constexpr long long CH = 16384;
@@ -213,7 +316,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = t_begin; t < total_tiles; t += t_step) {
         const int ks = t / (p.m_tiles * p.n_tiles);
         const int kb0 = ks * p.k_iters_per_split;
         const int kb1 = min(kb0 + p.k_iters_per_split, p.k_iters);
@@ -246,7 +349,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int row_in_tile = q * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    bool scaled = false;
+    if constexpr (kDec) {
+      // the B rows hold bf16(x * w_norm): the RMSNorm's 1/rms is applied here, per decode row, from the per-tile sums
+      // of squares the producing GEMV left behind
+      scaled = p.dec.ssq_in != nullptr;
+      if (scaled) {
+        if (row_in_tile < BN) {
+          float ss = 0.f;
+          for (int t = 0; t < p.dec.n_ssq_in; ++t) ss += p.dec.ssq_in[(long long)t * p.dec.ld_ssq + row_in_tile];
+          sscale[row_in_tile] = rsqrtf(ss / (float)p.dec.norm_dim + p.dec.eps);
+        }
+        epi_bar();
+      }
+    }
+    for (int t = t_begin; t < total_tiles; t += t_step) {
       const int mt = t % p.m_tiles;
       const int nt = (t / p.m_tiles) % p.n_tiles;
       const int ks = t / (p.m_tiles * p.n_tiles);
@@ -269,8 +386,55 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int j = 0; j < BN; ++j) {
             const int col = col_base + j;
-            if (col < p.N) out[((long long)ks * p.N + col) * p.ldd + row] = __uint_as_float(r[j]);
+            float v = __uint_as_float(r[j]);
+            if (scaled) v *= sscale[j];
+            if (col < p.N) out[((long long)ks * p.N + col) * p.ldd + row] = v;
           }
+        }
+      } else if constexpr (kClu) {
+        static_assert(BN == 16 || BN == 32, "decode tile");
+        // rank 0 owns the tile: operands of its finishing step that do not depend on this kernel are requested now
+        float xin[BN];
+        float wn = 0.f;
+        if constexpr (EPI == SB_EPI_DEC_RESID) {
+          if (crank == 0) {
+            const bool col_ok = row < p.M;
+            const bf16* xr = reinterpret_cast<const bf16*>(p.dec.x) + row;
+#pragma unroll
+            for (int j = 0; j < BN; ++j) xin[j] = (col_ok && j < p.dec.R) ? __bfloat162float(xr[(long long)j * p.M]) : 0.f;
+            wn = col_ok ? __bfloat162float(reinterpret_cast<const bf16*>(p.dec.w_next)[row]) : 0.f;
+          }
+        }
+        uint32_t r[BN];
+        if constexpr (BN == 16) tmem_ld_32x16(taddr, r);
+        else tmem_ld_32x32(taddr, r);
+        tmem_ld_wait();
+        float accv[BN];
+#pragma unroll
+        for (int j = 0; j < BN; ++j) accv[j] = __uint_as_float(r[j]);
+        if (crank != 0) {
+          const uint32_t dst = mapa_shared(smem_u32(red + ((crank - 1) * BM + row_in_tile) * RSTR), 0);
+#pragma unroll
+          for (int j = 0; j < BN; j += 4) st_cluster_v4(dst + j * 4, accv[j], accv[j + 1], accv[j + 2], accv[j + 3]);
+          fence_acq_rel_cluster();
+          epi_bar();
+          if (row_in_tile == 0) mbar_arrive_cluster(mapa_shared(redbar, 0));
+        } else {
+          if (csize > 1) mbar_wait_cluster(redbar, 0);
+          for (uint32_t s2 = 1; s2 < csize; ++s2) {
+            const float4* src = reinterpret_cast<const float4*>(red + ((s2 - 1) * BM + row_in_tile) * RSTR);
+#pragma unroll
+            for (int j = 0; j < BN; j += 4) {
+              const float4 v = src[j >> 2];
+              accv[j] += v.x; accv[j + 1] += v.y; accv[j + 2] += v.z; accv[j + 3] += v.w;
+            }
+          }
+          if (scaled) {
+#pragma unroll
+            for (int j = 0; j < BN; ++j) accv[j] *= sscale[j];
+          }
+          if constexpr (EPI == SB_EPI_DEC_QKV) dec_qkv_finish<BN>(p, mt, row_in_tile, accv, xbuf);
+          else dec_resid_finish<BN>(p, mt, row_in_tile, accv, xin, wn, xbuf);
         }
       } else if constexpr (EPI == SB_EPI_F32T_SWIGLU) {
         // decode gate|up GEMV (swap-AB, no split-K) with SwiGLU fused: the tile's 128 weight rows are [64 gate | 64 up]
@@ -282,6 +446,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if constexpr (BN == 16) tmem_ld_32x16(taddr, r);
         else tmem_ld_32x32(taddr, r);
         tmem_ld_wait();
+        if (scaled) {
+#pragma unroll
+          for (int j = 0; j < BN; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * sscale[j]);
+        }
         if (q >= 2) {
 #pragma unroll
           for (int j = 0; j < BN; ++j) xbuf[(row_in_tile - 64) * 33 + j] = __uint_as_float(r[j]);
@@ -433,7 +601,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   tc_fence_before();
   __syncthreads();
-  if constexpr (EPI == SB_EPI_F32T || EPI == SB_EPI_F32T_SWIGLU) {
+  if constexpr (kDec) {
     if (blockIdx.x == 0 && threadIdx.x == 0) sb_trace_mark(*reinterpret_cast<volatile int*>(tmem_slot + 1), 2);
   }
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -489,6 +657,35 @@ int num_sms() {
   return g_num_sms;
 }
 
+// shared memory of rank 0's receive buffer for the partial tiles of ranks 1..k_splits-1 (see gemm_kernel, kClu)
+size_t dec_red_bytes(int k_splits, int bn) { return (size_t)(k_splits > 1 ? k_splits - 1 : 0) * BM * (bn + 4) * 4; }
+
+// can `m_tiles` clusters of `k_splits` CTAs of the fused decode GEMV be resident at the same time?
+template <int BN>
+int dec_clusters_fit(int k_splits, int m_tiles, int* fit) {
+  using C = Cfg<BN>;
+  auto kfn = gemm_kernel<false, false, BN, SB_EPI_DEC_RESID>;
+  const size_t smem = C::SMEM_BYTES + dec_red_bytes(k_splits, BN);
+  *fit = 0;
+  if (smem > 227 * 1024) return 0;
+  SB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(m_tiles * k_splits);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = k_splits;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  SB_CUDA(cudaOccupancyMaxActiveClusters(&n, kfn, &cfg));
+  *fit = n >= m_tiles;
+  return 0;
+}
+
 template <bool A_MN, bool B_MN, int BN, int EPI>
 int launch(const sb_gemm_args* a, cudaStream_t stream) {
   using C = Cfg<BN>;
@@ -530,7 +727,39 @@ int launch(const sb_gemm_args* a, cudaStream_t stream) {
   p.prefetch_bytes = a->prefetch ? a->prefetch_bytes : 0;
   p.prefetch2 = reinterpret_cast<const uint8_t*>(a->prefetch2);
   p.prefetch2_bytes = a->prefetch2 ? a->prefetch2_bytes : 0;
+  if (a->dec) p.dec = *a->dec;
+  else memset(&p.dec, 0, sizeof(p.dec));
   const int total = p.m_tiles * p.n_tiles * p.k_splits;
+  if constexpr (EPI == SB_EPI_DEC_QKV || EPI == SB_EPI_DEC_RESID) {
+    // one cluster of k_splits CTAs per 128-row weight tile; every cluster must be resident at once (one tile per CTA)
+    const size_t smem = C::SMEM_BYTES + dec_red_bytes(p.k_splits, BN);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+      SB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smem_set = smem;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(total);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = p.k_splits;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = sb_pdl_enabled() ? 2 : 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kfn, tmA, tmB, p);
+    if (le != cudaSuccess) {
+      sb_set_error("sb_gemm: cluster launch failed (%d clusters of %d CTAs, %zu B smem): %s", p.m_tiles, p.k_splits, smem,
+                   cudaGetErrorString(le));
+      return 1;
+    }
+    return sb_check_launch("sb_gemm");
+  }
   const int grid = total < num_sms() ? total : num_sms();
   const bool pdl = (EPI == SB_EPI_F32T || EPI == SB_EPI_F32T_SWIGLU) && sb_pdl_enabled();
   cudaError_t le = sb_launch(kfn, dim3(grid), dim3(GEMM_THREADS), (size_t)C::SMEM_BYTES, stream, pdl, tmA, tmB, p);
@@ -553,6 +782,21 @@ extern "C" int sb_gemm_effective_splits(int K, int k_splits) {
   return (k_iters + per - 1) / per;
 }
 
+extern "C" int sb_gemm_dec_splits(int M, int N, int K, int want, int* splits_out) {
+  SB_REQUIRE(splits_out && M > 0 && N > 0 && N <= 32 && K > 0, "sb_gemm_dec_splits: bad arguments");
+  const int m_tiles = (M + BM - 1) / BM;
+  int s = want < 1 ? 1 : (want > DEC_MAX_SPLITS ? DEC_MAX_SPLITS : want);
+  for (; s > 1; --s) {
+    const int eff = sb_gemm_effective_splits(K, s);
+    if (eff != s) continue;
+    int fit = 0;
+    if (N <= 16 ? dec_clusters_fit<16>(s, m_tiles, &fit) : dec_clusters_fit<32>(s, m_tiles, &fit)) return 1;
+    if (fit) break;
+  }
+  *splits_out = s;
+  return 0;
+}
+
 extern "C" int sb_gemm(const sb_gemm_args* a, sb_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   SB_REQUIRE(a != nullptr, "sb_gemm: null args");
@@ -570,6 +814,8 @@ extern "C" int sb_gemm(const sb_gemm_args* a, sb_stream_t stream_) {
     SB_REQUIRE(a->ldd >= a->M, "sb_gemm: F32T ldd (%lld) < M (%d)", a->ldd, a->M);
     SB_REQUIRE(a->prefetch == nullptr || ((reinterpret_cast<uintptr_t>(a->prefetch) & 15) == 0 && a->prefetch_bytes >= 0),
                "sb_gemm: prefetch pointer must be 16-byte aligned");
+    SB_REQUIRE(a->dec == nullptr || a->dec->ssq_in == nullptr || (a->dec->n_ssq_in > 0 && a->dec->ld_ssq >= a->N && a->dec->norm_dim > 0),
+               "sb_gemm: bad ssq_in description");
     if (a->N <= 16) return launch<false, false, 16, SB_EPI_F32T>(a, stream);
     return launch<false, false, 32, SB_EPI_F32T>(a, stream);
   }
@@ -581,9 +827,34 @@ extern "C" int sb_gemm(const sb_gemm_args* a, sb_stream_t stream_) {
     SB_REQUIRE(a->ldd >= a->M / 2, "sb_gemm: F32T_SWIGLU ldd (%lld) < M/2 (%d)", a->ldd, a->M / 2);
     SB_REQUIRE(a->prefetch == nullptr || (reinterpret_cast<uintptr_t>(a->prefetch) & 15) == 0,
                "sb_gemm: prefetch pointer must be 16-byte aligned");
+    SB_REQUIRE(a->dec == nullptr || a->dec->ssq_in == nullptr || (a->dec->n_ssq_in > 0 && a->dec->ld_ssq >= a->N && a->dec->norm_dim > 0),
+               "sb_gemm: bad ssq_in description");
     if (a->N <= 16) return launch<false, false, 16, SB_EPI_F32T_SWIGLU>(a, stream);
     return launch<false, false, 32, SB_EPI_F32T_SWIGLU>(a, stream);
   }
+  if (e == SB_EPI_DEC_QKV || e == SB_EPI_DEC_RESID) {
+    const sb_dec_fuse* d = a->dec;
+    SB_REQUIRE(!amn && !bmn, "sb_gemm: decode epilogues need K-major operands");
+    SB_REQUIRE(d != nullptr, "sb_gemm: decode epilogue without sb_dec_fuse");
+    SB_REQUIRE(a->N <= 32 && d->R > 0 && d->R <= a->N, "sb_gemm: decode epilogue needs R <= N <= 32 (R=%d, N=%d)", d->R, a->N);
+    SB_REQUIRE(sb_gemm_effective_splits(a->K, a->k_splits) <= DEC_MAX_SPLITS, "sb_gemm: decode epilogues take at most %d K splits", DEC_MAX_SPLITS);
+    SB_REQUIRE((a->N <= 16 ? Cfg<16>::SMEM_BYTES : Cfg<32>::SMEM_BYTES) +
+                       dec_red_bytes(sb_gemm_effective_splits(a->K, a->k_splits), a->N <= 16 ? 16 : 32) <= 227 * 1024,
+               "sb_gemm: too many K splits for the cluster reduction buffer (use sb_gemm_dec_splits)");
+    SB_REQUIRE(d->ssq_in == nullptr || (d->n_ssq_in > 0 && d->ld_ssq >= a->N && d->norm_dim > 0),
+               "sb_gemm: bad ssq_in description (n=%d ld=%d dim=%d)", d->n_ssq_in, d->ld_ssq, d->norm_dim);
+    if (e == SB_EPI_DEC_QKV) {
+      SB_REQUIRE(a->bias && d->step_ptr && d->q_out && d->k_cache && d->v_cache && d->c_max > 0, "sb_gemm: DEC_QKV needs bias, step_ptr, q_out and the caches");
+      SB_REQUIRE(d->n_heads > 0 && d->n_kv_heads > 0 && a->M == (d->n_heads + 2 * d->n_kv_heads) * BM,
+                 "sb_gemm: DEC_QKV needs head_dim 128 and M = (heads + 2 kv_heads) * 128, got M=%d", a->M);
+      if (a->N <= 16) return launch<false, false, 16, SB_EPI_DEC_QKV>(a, stream);
+      return launch<false, false, 32, SB_EPI_DEC_QKV>(a, stream);
+    }
+    SB_REQUIRE(d->x && d->w_next && d->xw && d->ssq_out && d->ld_ssq >= d->R, "sb_gemm: DEC_RESID needs x, w_next, xw, ssq_out");
+    if (a->N <= 16) return launch<false, false, 16, SB_EPI_DEC_RESID>(a, stream);
+    return launch<false, false, 32, SB_EPI_DEC_RESID>(a, stream);
+  }
+  SB_REQUIRE(a->dec == nullptr || e == SB_EPI_F32T || e == SB_EPI_F32T_SWIGLU, "sb_gemm: sb_dec_fuse only with the decode epilogues");
   SB_REQUIRE(a->N % 8 == 0 && a->ldd % 8 == 0, "sb_gemm: N and ldd must be multiples of 8");
   SB_REQUIRE(a->k_splits <= 1, "sb_gemm: split-K only with the F32T epilogue");
   if (e == SB_EPI_LMHEAD) {

@@ -101,7 +101,8 @@ def main():
         idx = [i for i, r in enumerate(recs) if r[0] == 8]
         one = recs[idx[0] + 1: idx[1] + 1] if len(idx) >= 2 else recs
         t0 = one[0][1]
-        out_path = os.path.join(ROOT, "gpurun_out", f"decode_trace_pf{trace_cfg[0]}_{trace_cfg[1]}.txt")
+        tag = "fused" if m.decode_fused else "unfused"
+        out_path = os.path.join(ROOT, "gpurun_out", f"decode_trace_{tag}_pf{trace_cfg[0]}_{trace_cfg[1]}.txt")
         os.makedirs(os.path.dirname(out_path), exist_ok=True)
         agg = {}
         with open(out_path, "w") as f:
@@ -115,7 +116,7 @@ def main():
                 d[0] += 1; d[1] += (tr_ - te) / 1e3; d[2] += (tn - tr_) / 1e3; d[3] += gap
                 prev_end = tn
         total = (one[-1][3] - t0) / 1e3
-        print(json.dumps({"exp": "trace", "prefetch_mb": trace_cfg, "records": n, "step_kernels": len(one), "step_us": round(total, 1),
+        print(json.dumps({"exp": "trace", "fused": m.decode_fused, "splits": st["S"], "prefetch_mb": trace_cfg, "records": n, "step_kernels": len(one), "step_us": round(total, 1),
                           "per_kind": {k: {"n": v[0], "wait_us": round(v[1] / v[0], 2), "exec_us": round(v[2] / v[0], 2),
                                            "gap_after_prev_end_us": round(v[3] / v[0], 2), "exec_total_us": round(v[2], 1),
                                            "gap_total_us": round(v[3], 1)} for k, v in agg.items()}}), flush=True)
