@@ -196,6 +196,9 @@ int sb_attn_fwd(const sb_attn_args* args, sb_stream_t stream);
 int sb_set_attn_impl(int impl);
 /* deterministic (no atomics): a key-tile-major kernel produces dK, dV, a query-tile-major kernel produces dQ */
 int sb_attn_bwd(const sb_attn_args* args, sb_stream_t stream);
+/* backward implementation: 0 = tcgen05/TMEM/TMA kernels (default); bit 0 = dQ on the mma.sync kernel, bit 1 = dK/dV on
+ * the mma.sync kernel (A/B timing, cross-checks) */
+int sb_set_attn_bwd_impl(int impl);
 int sb_attn_bwd_workspace(int T, int Tk, int n_heads, int n_kv_heads, int head_dim, long long* gqa_ws_elems,
                           long long* tile_ws_ints);
 

@@ -10,6 +10,11 @@
 #include "common.cuh"
 #include "spacer_b200.h"
 
+// attention_bwd_tc.cu
+int sb_attn_bwd_dkdv_tc(const sb_attn_args* a, const int* qtb, void* dk_out, void* dv_out, long long ld_dk,
+                        long long ld_dv, cudaStream_t st);
+int sb_attn_bwd_dq_tc(const sb_attn_args* a, cudaStream_t st);
+
 namespace {
 
 constexpr int ATT_THREADS = 128;  // 4 warps x 16 query rows
@@ -696,8 +701,11 @@ int launch_fwd(const AttnParams& p, cudaStream_t st) {
   return sb_check_launch("sb_attn_fwd");
 }
 
+int g_attn_bwd_impl = 0;   // 0 = tcgen05 backward (default); bit 0: dQ on mma.sync, bit 1: dK/dV on mma.sync
+
 template <int HD>
-int launch_bwd(const AttnParams& p, bf16* dq, long long lddq, bf16* gqa_ws, int* tile_ws, cudaStream_t st) {
+int launch_bwd(const AttnParams& p, const sb_attn_args* a, bf16* dq, long long lddq, bf16* gqa_ws, int* tile_ws,
+               cudaStream_t st) {
   static bool done = false;
   if (!done) {
     SB_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_dkdv_smem<HD>()));
@@ -718,9 +726,14 @@ int launch_bwd(const AttnParams& p, bf16* dq, long long lddq, bf16* gqa_ws, int*
   dim3 grid_kv((p.Tk + BKV - 1) / BKV, p.n_heads);
   // head offset folded into the output pointers: per-q-head columns in the expanded scratch, kv-head columns otherwise
   // (rep == 1: q head == kv head)
-  attn_bwd_dkdv_kernel<HD><<<grid_kv, ATT_THREADS, bwd_dkdv_smem<HD>(), st>>>(p, qtb, xk, xv, rep > 1 ? ldx : p.lddk,
-                                                                              rep > 1 ? ldx : p.lddv);
-  if (sb_check_launch("sb_attn_bwd(dkdv)")) return 1;
+  if (g_attn_bwd_impl & 2) {
+    attn_bwd_dkdv_kernel<HD><<<grid_kv, ATT_THREADS, bwd_dkdv_smem<HD>(), st>>>(p, qtb, xk, xv, rep > 1 ? ldx : p.lddk,
+                                                                                rep > 1 ? ldx : p.lddv);
+    if (sb_check_launch("sb_attn_bwd(dkdv)")) return 1;
+  } else {
+    if (sb_attn_bwd_dkdv_tc(a, reinterpret_cast<const int*>(qtb), xk, xv, rep > 1 ? ldx : p.lddk, rep > 1 ? ldx : p.lddv, st))
+      return 1;
+  }
   if (rep > 1) {
     const long long total = (long long)p.Tk * p.n_kv_heads * (HD / 8);
     int blocks = (int)((total + 255) / 256);
@@ -728,6 +741,7 @@ int launch_bwd(const AttnParams& p, bf16* dq, long long lddq, bf16* gqa_ws, int*
     attn_gqa_reduce_kernel<HD><<<blocks, 256, 0, st>>>(xk, xv, ldx, rep, p.dk, p.dv, p.lddk, p.lddv, p.Tk, p.n_kv_heads);
     if (sb_check_launch("sb_attn_bwd(gqa reduce)")) return 1;
   }
+  if (!(g_attn_bwd_impl & 1)) return sb_attn_bwd_dq_tc(a, st);
   dim3 grid_q((p.T + BQ - 1) / BQ, p.n_heads);
   attn_bwd_dq_kernel<HD><<<grid_q, ATT_THREADS, bwd_dq_smem<HD>(), st>>>(p, dq, lddq);
   return sb_check_launch("sb_attn_bwd(dq)");
@@ -742,6 +756,12 @@ int g_attn_impl = 0;   // 0 = tcgen05 forward (default), 1 = mma.sync forward
 extern "C" int sb_set_attn_impl(int impl) {
   SB_REQUIRE(impl == 0 || impl == 1, "sb_set_attn_impl: 0 = tcgen05 (default), 1 = mma.sync");
   g_attn_impl = impl;
+  return 0;
+}
+
+extern "C" int sb_set_attn_bwd_impl(int impl) {
+  SB_REQUIRE(impl >= 0 && impl <= 3, "sb_set_attn_bwd_impl: 0 = tcgen05 (default), bit 0 = dQ on mma.sync, bit 1 = dK/dV on mma.sync");
+  g_attn_bwd_impl = impl;
   return 0;
 }
 
@@ -786,8 +806,8 @@ extern "C" int sb_attn_bwd(const sb_attn_args* a, sb_stream_t stream) {
   p.d_o = (const bf16*)a->d_o; p.lddo = a->lddo; p.delta = a->delta;
   p.dk = (bf16*)a->dk; p.dv = (bf16*)a->dv; p.lddk = a->lddk; p.lddv = a->lddv;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (a->head_dim == 128) return launch_bwd<128>(p, (bf16*)a->dq, a->lddq, (bf16*)a->gqa_ws, a->tile_ws, st);
-  if (a->head_dim == 80) return launch_bwd<80>(p, (bf16*)a->dq, a->lddq, (bf16*)a->gqa_ws, a->tile_ws, st);
+  if (a->head_dim == 128) return launch_bwd<128>(p, a, (bf16*)a->dq, a->lddq, (bf16*)a->gqa_ws, a->tile_ws, st);
+  if (a->head_dim == 80) return launch_bwd<80>(p, a, (bf16*)a->dq, a->lddq, (bf16*)a->gqa_ws, a->tile_ws, st);
   sb_set_error("sb_attn_bwd: head_dim %d not supported (80 or 128)", a->head_dim);
   return 1;
 }

@@ -233,16 +233,19 @@ def metas(kind, T):
                                                ("prefix_big", 1220, 7, 1, 128), ("slabs", 960, 3, 3, 80),
                                                ("prefix", 250, 4, 1, 128), ("causal", 64, 2, 2, 80),
                                                ("prefix", 333, 14, 2, 128)])
-@pytest.mark.parametrize("impl", [0, 1])
-def test_attention_fwd_bwd(kind, T, nh, nkv, hd, impl):
-    """impl 0 = tcgen05/TMEM/TMA forward (default), 1 = mma.sync forward; the backward is shared."""
+@pytest.mark.parametrize("impl,bwd_impl", [(0, 0), (1, 3), (0, 1), (0, 2)])
+def test_attention_fwd_bwd(kind, T, nh, nkv, hd, impl, bwd_impl):
+    """impl 0 = tcgen05/TMEM/TMA forward (default), 1 = mma.sync forward; bwd_impl 0 = tcgen05 backward (default),
+    bit 0 = dQ on mma.sync, bit 1 = dK/dV on mma.sync (each tcgen05 kernel is also checked on its own)."""
     from spacer_b200 import ops
     lib = ops._lib.load()
     assert lib.sb_set_attn_impl(impl) == 0
+    assert lib.sb_set_attn_bwd_impl(bwd_impl) == 0
     try:
         _attention_case(kind, T, nh, nkv, hd)
     finally:
         lib.sb_set_attn_impl(0)
+        lib.sb_set_attn_bwd_impl(0)
 
 
 def _attention_case(kind, T, nh, nkv, hd):
