@@ -11,8 +11,9 @@
 //                            the keys: S^T = K Q^T, dP^T = V dO^T -> P^T, dS^T as bf16 operands -> dV += P^T dO,
 //                            dK += dS^T Q.  With GQA the per-q-head dK/dV land in an expanded scratch that
 //                            attn_gqa_reduce_kernel (attention.cu) sums over the group.
-// Warp roles as in the forward kernel (attention_tc.cu): warp 0 TMA producer, warp 1 single-thread MMA issuer,
-// warps 2..5 element-wise work (thread = TMEM lane) and epilogue.  One CTA per SM (512 TMEM columns, 144-163 KB smem);
+// Warp roles: warp 0 TMA producer, warp 1 single-thread MMA issuer, warps 2..9 element-wise work and epilogue -- two
+// warps per TMEM lane quarter, each taking 32 of the 64 columns of a tile (the element-wise pass, not the tensor
+// pipe, bounds a tile: exp2 + mask + two bf16 operand rows per score).  One CTA per SM (512 TMEM columns, 144-163 KB smem);
 // the MMAs of tile i+1 (S, dP) are issued before the element-wise pass of tile i is consumed.
 #include "common.cuh"
 #include "spacer_b200.h"
@@ -21,7 +22,8 @@
 
 namespace {
 
-constexpr int THREADS = 192;
+constexpr int THREADS = 320;          // TMA warp, MMA warp, 8 element-wise warps (two per TMEM lane quarter)
+constexpr int EW_THREADS = 256;
 constexpr int TB = 64;            // inner tile (keys in the dQ kernel, queries in the dK/dV kernel)
 constexpr int SLAB = 128 * 128;   // bytes of one [128 rows x 64 bf16] 128B-swizzled slab
 constexpr int HSLAB = 64 * 128;   // bytes of one [64 rows x 64 bf16] slab
@@ -32,7 +34,7 @@ SB_DEVICE float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-SB_DEVICE void epi_bar2() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+SB_DEVICE void epi_bar2() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
 
 struct BwdParams {
   const float* lse;      // [n_heads][T] natural log
@@ -105,7 +107,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(kv_full0 + 8 * s, 1); mbar_init(kv_empty0 + 8 * s, 1); mbar_init(s_full0 + 8 * s, 1); }
-    mbar_init(ds_full, 128);
+    mbar_init(ds_full, EW_THREADS);
     mbar_init(acc_done, 1);
     mbar_fence_init();
   }
@@ -208,6 +210,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
   } else {
     const int quarter = warp & 3;
+    const int hf = (warp - 2) >> 2;          // which 32 of the tile's 64 key columns this warp handles
     const int r = quarter * 32 + lane;
     const int row = q0 + r;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
@@ -226,37 +229,34 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       tc_fence_after();
       const int j0 = jt * TB;
       const bool full = ktile_full(tb, j0) && (j0 + TB <= p.Tk) && (q0 + 128 <= p.T);
-#pragma unroll 1
-      for (int hf = 0; hf < 2; ++hf) {
-        uint32_t sv_[32], dp_[32];
-        tmem_ld_32x32(lane_addr + L::S_COL + buf * TB + hf * 32, sv_);
-        tmem_ld_32x32(lane_addr + L::DP_COL + buf * TB + hf * 32, dp_);
-        tmem_ld_wait();
-        if (hf == 0 && it > 0) {   // the previous dQ MMA has finished reading the dS tile
-          mbar_wait(acc_done, (it - 1) & 1);
-          tc_fence_after();
-        }
+      uint32_t sv_[32], dp_[32];
+      tmem_ld_32x32(lane_addr + L::S_COL + buf * TB + hf * 32, sv_);
+      tmem_ld_32x32(lane_addr + L::DP_COL + buf * TB + hf * 32, dp_);
+      tmem_ld_wait();
+      if (it > 0) {   // the previous dQ MMA has finished reading the dS tile
+        mbar_wait(acc_done, (it - 1) & 1);
+        tc_fence_after();
+      }
 #pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {
-          uint32_t pk[4];
+      for (int c8 = 0; c8 < 4; ++c8) {
+        uint32_t pk[4];
 #pragma unroll
-          for (int j = 0; j < 8; j += 2) {
-            float ds[2];
+        for (int j = 0; j < 8; j += 2) {
+          float ds[2];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int c = c8 * 8 + j + e;
-              bool vis = true;
-              if (!full) {
-                const int key = j0 + hf * 32 + c;
-                vis = (row < p.T) && (key < p.Tk) && ((key < pre) || (key >= seg && key < kve));
-              }
-              const float pr = vis ? fast_exp2(fmaf(__uint_as_float(sv_[c]), sc2, -lse2)) : 0.f;
-              ds[e] = pr * (__uint_as_float(dp_[c]) - dl) * p.scale;
+          for (int e = 0; e < 2; ++e) {
+            const int c = c8 * 8 + j + e;
+            bool vis = true;
+            if (!full) {
+              const int key = j0 + hf * 32 + c;
+              vis = (row < p.T) && (key < p.Tk) && ((key < pre) || (key >= seg && key < kve));
             }
-            pk[j >> 1] = pack_bf16(ds[0], ds[1]);
+            const float pr = vis ? fast_exp2(fmaf(__uint_as_float(sv_[c]), sc2, -lse2)) : 0.f;
+            ds[e] = pr * (__uint_as_float(dp_[c]) - dl) * p.scale;
           }
-          *reinterpret_cast<uint4*>(rowp + (((hf * 4 + c8) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          pk[j >> 1] = pack_bf16(ds[0], ds[1]);
         }
+        *reinterpret_cast<uint4*>(rowp + (((hf * 4 + c8) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
       fence_proxy_async();
       tc_fence_before();
@@ -267,8 +267,10 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       tc_fence_after();
     }
     bf16* orow = p.out0 + (long long)row * p.ld0 + (long long)head * HD;
+    constexpr int NCH = HD / 16;
+    const int c_lo = hf == 0 ? 0 : (NCH + 1) / 2, c_hi = hf == 0 ? (NCH + 1) / 2 : NCH;
 #pragma unroll 1
-    for (int c = 0; c < HD / 16; ++c) {
+    for (int c = c_lo; c < c_hi; ++c) {
       uint32_t v[16];
       if (it > 0) {
         tmem_ld_32x16(lane_addr + L::ACC_COL + c * 16, v);
@@ -306,13 +308,9 @@ SB_DEVICE Bounds load_qtb(const int* qtb, int qt) {
   r.pmin = a.x; r.pmax = a.y; r.smin = a.z; r.smax = a.w; r.emin = b.x; r.emax = b.y;
   return r;
 }
-// first 64-query tile >= qt that sees at least one key of [j0, j0 + 128)
-SB_DEVICE int next_qtile(const int* qtb, int qt, int n_qt, int j0) {
-  while (qt < n_qt) {
-    const Bounds b = load_qtb(qtb, qt);
-    if ((j0 < b.pmax) || (j0 + 128 > b.smin && j0 < b.emax)) break;
-    ++qt;
-  }
+// first 64-query tile >= qt that sees at least one key of this CTA's key tile (flags: shared memory, see below)
+SB_DEVICE int next_qtile(const uint8_t* flags, int qt, int n_qt) {
+  while (qt < n_qt && !(flags[qt] & 1)) ++qt;
   return qt;
 }
 
@@ -326,7 +324,9 @@ struct LayK {
   static constexpr int OFF_PT = OFF_DO + 2 * NSLAB * HSLAB;      // [128 keys x 64 q] K-major
   static constexpr int OFF_DST = OFF_PT + SLAB;
   static constexpr int OFF_ROW = OFF_DST + SLAB;                 // 2 x {lse2[64], delta[64], pre[64], seg[64], kve[64]}
-  static constexpr int OFF_BAR = OFF_ROW + 2 * 5 * 64 * 4;
+  static constexpr int OFF_FLAG = OFF_ROW + 2 * 5 * 64 * 4;      // per 64-query tile: bit 0 relevant, bit 1 fully visible
+  static constexpr int MAX_QT = 4096;
+  static constexpr int OFF_BAR = OFF_FLAG + MAX_QT;
   static constexpr int SMEM = OFF_BAR + 256;
   static constexpr int S_COL = 0, DP_COL = 128, DV_COL = 256, DK_COL = 384;
 };
@@ -357,12 +357,22 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   const int head = blockIdx.y;
   const int kvh = head / (p.n_heads / p.n_kv_heads);
   const int n_qt = (p.T + TB - 1) / TB;
+  uint8_t* flags = smem + L::OFF_FLAG;
 
+  // which query tiles see this key tile: evaluated once, in parallel (a sequential scan of the bounds in global memory
+  // costs one dependent load per tile per warp role)
+  for (int qt = threadIdx.x; qt < n_qt; qt += THREADS) {
+    const Bounds b = load_qtb(p.qtb, qt);
+    const bool rel = (j0 < b.pmax) || (j0 + 128 > b.smin && j0 < b.emax);
+    const bool full = ((j0 + 128 <= b.pmin) || (j0 >= b.smax && j0 + 128 <= b.emin)) && (j0 + 128 <= p.Tk) &&
+                      (qt * TB + TB <= p.T);
+    flags[qt] = (rel ? 1 : 0) | (full ? 2 : 0);
+  }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     mbar_init(kv_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(q_full0 + 8 * s, 1); mbar_init(q_empty0 + 8 * s, 1); mbar_init(s_full0 + 8 * s, 1); }
-    mbar_init(pds_full, 128);
+    mbar_init(pds_full, EW_THREADS);
     mbar_init(acc_done, 1);
     mbar_fence_init();
   }
@@ -382,7 +392,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       }
       int stage = 0;
       uint32_t phase = 0;
-      for (int qt = next_qtile(p.qtb, 0, n_qt, j0); qt < n_qt; qt = next_qtile(p.qtb, qt + 1, n_qt, j0)) {
+      for (int qt = next_qtile(flags, 0, n_qt); qt < n_qt; qt = next_qtile(flags, qt + 1, n_qt)) {
         mbar_wait(q_empty0 + 8 * stage, phase ^ 1);
         const uint32_t fb = q_full0 + 8 * stage;
         mbar_expect_tx(fb, 2 * L::NSLAB * HSLAB);
@@ -417,14 +427,14 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       };
       mbar_wait(kv_full, 0);
       tc_fence_after();
-      int qt = next_qtile(p.qtb, 0, n_qt, j0);
+      int qt = next_qtile(flags, 0, n_qt);
       if (qt < n_qt) {
         mbar_wait(q_full0, 0);
         tc_fence_after();
         issue_s(0, 0);
       }
       for (int it = 0; qt < n_qt; ++it) {
-        const int qn = next_qtile(p.qtb, qt + 1, n_qt, j0);
+        const int qn = next_qtile(flags, qt + 1, n_qt);
         const int stage = it & 1;
         if (qn < n_qt) {
           const int nt = it + 1;
@@ -455,22 +465,24 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     }
   } else {
     const int quarter = warp & 3;
+    const int hf = (warp - 2) >> 2;           // which 32 of the tile's 64 query columns this warp handles
     const int r = quarter * 32 + lane;        // key row of this thread
+    const int ew = (warp - 2) * 32 + lane;    // 0..255
     const int key = j0 + r;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const float sc2 = p.scale * L2E;
     uint8_t* rowP = smem + L::OFF_PT + r * 128;
     uint8_t* rowD = smem + L::OFF_DST + r * 128;
     int it = 0;
-    for (int qt = next_qtile(p.qtb, 0, n_qt, j0); qt < n_qt; qt = next_qtile(p.qtb, qt + 1, n_qt, j0), ++it) {
+    for (int qt = next_qtile(flags, 0, n_qt); qt < n_qt; qt = next_qtile(flags, qt + 1, n_qt), ++it) {
       const int buf = it & 1;
       const int q0 = qt * TB;
       // per-query row parameters of this tile -> shared memory (double-buffered by tile parity)
       float* cL = sRow + buf * 5 * 64;
       float* cD = cL + 64;
       int* cM = reinterpret_cast<int*>(cD + 64);
-      if (r < 64) {
-        const int q = q0 + r;
+      if (ew < 64) {
+        const int q = q0 + ew;
         float l2 = INFINITY, dl = 0.f;
         int4 m = make_int4(0, 0, 0, 0);
         if (q < p.T) {
@@ -479,50 +491,50 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           dl = p.delta[(long long)head * p.T + q];
           m = p.meta[q];
         }
-        cL[r] = l2; cD[r] = dl; cM[r] = m.x; cM[64 + r] = m.y; cM[128 + r] = m.z;
+        cL[ew] = -l2; cD[ew] = dl; cM[ew] = m.x; cM[64 + ew] = m.y; cM[128 + ew] = m.z;
       }
       epi_bar2();
-      const Bounds b = load_qtb(p.qtb, qt);
-      const bool full = ((j0 + 128 <= b.pmin) || (j0 >= b.smax && j0 + 128 <= b.emin)) && (j0 + 128 <= p.Tk) &&
-                        (q0 + TB <= p.T);
+      const bool full = (flags[qt] & 2) != 0;
       mbar_wait(s_full0 + 8 * buf, (it >> 1) & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int hf = 0; hf < 2; ++hf) {
-        uint32_t sv_[32], dp_[32];
-        tmem_ld_32x32(lane_addr + L::S_COL + buf * TB + hf * 32, sv_);
-        tmem_ld_32x32(lane_addr + L::DP_COL + buf * TB + hf * 32, dp_);
-        tmem_ld_wait();
-        if (hf == 0 && it > 0) {   // the previous dV/dK MMAs have finished reading the P^T / dS^T tiles
-          mbar_wait(acc_done, (it - 1) & 1);
-          tc_fence_after();
-        }
+      uint32_t sv_[32], dp_[32];
+      tmem_ld_32x32(lane_addr + L::S_COL + buf * TB + hf * 32, sv_);
+      tmem_ld_32x32(lane_addr + L::DP_COL + buf * TB + hf * 32, dp_);
+      tmem_ld_wait();
+      if (it > 0) {   // the previous dV/dK MMAs have finished reading the P^T / dS^T tiles
+        mbar_wait(acc_done, (it - 1) & 1);
+        tc_fence_after();
+      }
 #pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {
-          uint32_t pk[4], dk_[4];
+      for (int c8 = 0; c8 < 4; ++c8) {
+        const int qb = hf * 32 + c8 * 8;
+        const float4 la = *reinterpret_cast<const float4*>(cL + qb), lb = *reinterpret_cast<const float4*>(cL + qb + 4);
+        const float4 da = *reinterpret_cast<const float4*>(cD + qb), db = *reinterpret_cast<const float4*>(cD + qb + 4);
+        const float nl[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
+        const float dd[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+        uint32_t pk[4], dk_[4];
 #pragma unroll
-          for (int j = 0; j < 8; j += 2) {
-            float pv[2], ds[2];
+        for (int j = 0; j < 8; j += 2) {
+          float pv[2], ds[2];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int c = c8 * 8 + j + e;
-              const int ql = hf * 32 + c;
-              bool vis = true;
-              if (!full) {
-                const int pre = cM[ql], seg = cM[64 + ql], kve = cM[128 + ql];
-                vis = (q0 + ql < p.T) && (key < p.Tk) && ((key < pre) || (key >= seg && key < kve));
-              }
-              const float pr = vis ? fast_exp2(fmaf(__uint_as_float(sv_[c]), sc2, -cL[ql])) : 0.f;
-              pv[e] = pr;
-              ds[e] = pr * (__uint_as_float(dp_[c]) - cD[ql]) * p.scale;
+          for (int e = 0; e < 2; ++e) {
+            const int c = c8 * 8 + j + e;
+            bool vis = true;
+            if (!full) {
+              const int ql = qb + j + e;
+              const int pre = cM[ql], seg = cM[64 + ql], kve = cM[128 + ql];
+              vis = (q0 + ql < p.T) && (key < p.Tk) && ((key < pre) || (key >= seg && key < kve));
             }
-            pk[j >> 1] = pack_bf16(pv[0], pv[1]);
-            dk_[j >> 1] = pack_bf16(ds[0], ds[1]);
+            const float pr = vis ? fast_exp2(fmaf(__uint_as_float(sv_[c]), sc2, nl[j + e])) : 0.f;
+            pv[e] = pr;
+            ds[e] = pr * (__uint_as_float(dp_[c]) - dd[j + e]) * p.scale;
           }
-          const int ch = ((hf * 4 + c8) ^ (r & 7)) << 4;
-          *reinterpret_cast<uint4*>(rowP + ch) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(rowD + ch) = make_uint4(dk_[0], dk_[1], dk_[2], dk_[3]);
+          pk[j >> 1] = pack_bf16(pv[0], pv[1]);
+          dk_[j >> 1] = pack_bf16(ds[0], ds[1]);
         }
+        const int ch = ((hf * 4 + c8) ^ (r & 7)) << 4;
+        *reinterpret_cast<uint4*>(rowP + ch) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(rowD + ch) = make_uint4(dk_[0], dk_[1], dk_[2], dk_[3]);
       }
       fence_proxy_async();
       tc_fence_before();
@@ -532,8 +544,8 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       mbar_wait(acc_done, (it - 1) & 1);
       tc_fence_after();
     }
-#pragma unroll 1
-    for (int which = 0; which < 2; ++which) {   // 0: dK, 1: dV
+    {   // warps of column half 0 write dK, the others dV
+      const int which = hf;
       bf16* orow = (which ? p.out1 + (long long)key * p.ld1 : p.out0 + (long long)key * p.ld0) + (long long)head * HD;
       const uint32_t col0 = which ? L::DV_COL : L::DK_COL;
 #pragma unroll 1
@@ -639,6 +651,7 @@ int launch_dkdv(const sb_attn_args* a, const int* qtb, void* dk_out, void* dv_ou
     SB_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_tc_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM));
     done = true;
   }
+  SB_REQUIRE((a->T + TB - 1) / TB <= L::MAX_QT, "sb_attn_bwd(tcgen05): at most %d query tiles of %d (T = %d)", L::MAX_QT, TB, a->T);
   BwdParams p = base_params(a);
   p.out0 = (bf16*)dk_out; p.ld0 = ld_dk;
   p.out1 = (bf16*)dv_out; p.ld1 = ld_dv;
