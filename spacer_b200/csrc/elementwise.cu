@@ -176,40 +176,57 @@ norm_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const fl
 // fp32 math, one rounding to bf16.  inverse=1 rotates by -angle (backward).
 // token n of a (t,h,w) grid sits at frame n/(h*w), merge-block-major inside the frame.
 // ------------------------------------------------------------------------------------------
-__global__ void rope_vit_kernel(bf16* __restrict__ qkv, int T, int heads, int hd, const int* __restrict__ grids,
-                                int n_grids, int merge, int inverse) {
+// one CTA per token: the token's half = hd/2 (cos, sin) pairs are computed once into shared memory, then every
+// (q|k, head, 8-element chunk) is rotated with 16-byte loads and stores
+__global__ void __launch_bounds__(256)
+rope_vit_kernel(bf16* __restrict__ qkv, int T, int heads, int hd, const int* __restrict__ grids, int n_grids, int merge,
+                int inverse) {
+  __shared__ float s_cs[128], s_sn[128];
   const int half = hd / 2;      // 40: rotation pairs (i, i+half)
   const int quarter = hd / 4;   // 20: first quarter of freqs follows h, second follows w
-  const long long total = (long long)T * 2 * heads * half;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int i = idx % half;
-    const int head = (idx / half) % heads;
-    const int which = (idx / ((long long)half * heads)) % 2;  // 0 = q, 1 = k
-    const int n = idx / ((long long)half * heads * 2);
-    // locate the grid this token belongs to
-    int base = 0, gh = 1, gw = 1;
-    for (int g = 0; g < n_grids; ++g) {
-      const int gt = grids[g * 3], h_ = grids[g * 3 + 1], w_ = grids[g * 3 + 2];
-      const int cnt = gt * h_ * w_;
-      if (n < base + cnt || g == n_grids - 1) { gh = h_; gw = w_; break; }
-      base += cnt;
+  const int chunks = half / 8;
+  for (int n = blockIdx.x; n < T; n += gridDim.x) {
+    if ((int)threadIdx.x < half) {
+      const int i = threadIdx.x;
+      // locate the grid this token belongs to
+      int base = 0, gh = 1, gw = 1;
+      for (int g = 0; g < n_grids; ++g) {
+        const int gt = grids[g * 3], h_ = grids[g * 3 + 1], w_ = grids[g * 3 + 2];
+        const int cnt = gt * h_ * w_;
+        if (n < base + cnt || g == n_grids - 1) { gh = h_; gw = w_; break; }
+        base += cnt;
+      }
+      const int r = (n - base) % (gh * gw);
+      const int blk = r / (merge * merge), inner = r % (merge * merge);
+      const int bw_n = gw / merge;
+      const int hpos = (blk / bw_n) * merge + inner / merge;
+      const int wpos = (blk % bw_n) * merge + inner % merge;
+      const int fi = i < quarter ? i : i - quarter;
+      const float inv_freq = 1.0f / powf(10000.0f, (float)(2 * fi) / (float)half);
+      const float ang = (float)(i < quarter ? hpos : wpos) * inv_freq;
+      float sn, cs;
+      sincosf(ang, &sn, &cs);
+      s_cs[i] = cs;
+      s_sn[i] = inverse ? -sn : sn;
     }
-    const int r = (n - base) % (gh * gw);
-    const int blk = r / (merge * merge), inner = r % (merge * merge);
-    const int bw_n = gw / merge;
-    const int hpos = (blk / bw_n) * merge + inner / merge;
-    const int wpos = (blk % bw_n) * merge + inner % merge;
-    const int fi = i < quarter ? i : i - quarter;
-    const float inv_freq = 1.0f / powf(10000.0f, (float)(2 * fi) / (float)half);
-    const float ang = (float)(i < quarter ? hpos : wpos) * inv_freq;
-    float sn, cs;
-    sincosf(ang, &sn, &cs);
-    if (inverse) sn = -sn;
-    bf16* p = qkv + (long long)n * 3 * heads * hd + (long long)which * heads * hd + head * hd;
-    const float a = __bfloat162float(p[i]), b = __bfloat162float(p[i + half]);
-    p[i] = __float2bfloat16_rn(a * cs - b * sn);
-    p[i + half] = __float2bfloat16_rn(b * cs + a * sn);
+    __syncthreads();
+    bf16* row = qkv + (long long)n * 3 * heads * hd;
+    for (int w = threadIdx.x; w < 2 * heads * chunks; w += blockDim.x) {
+      const int c = w % chunks;
+      bf16* p = row + (w / chunks) * hd + c * 8;      // (which, head) are contiguous: q heads then k heads
+      float a[8], b[8], oa[8], ob[8];
+      ld8f(p, a);
+      ld8f(p + half, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float cs = s_cs[c * 8 + j], sn = s_sn[c * 8 + j];
+        oa[j] = a[j] * cs - b[j] * sn;
+        ob[j] = b[j] * cs + a[j] * sn;
+      }
+      st8f(p, oa);
+      st8f(p + half, ob);
+    }
+    __syncthreads();
   }
 }
 
@@ -217,48 +234,55 @@ __global__ void rope_vit_kernel(bf16* __restrict__ qkv, int T, int heads, int hd
 // M-RoPE in place on q,k of qkv [T, (nh+2nkv)*hd] + optional KV-cache write   MQ2:188-254
 // pos: int32 [3, T].  HF numerics: cos/sin fp32 -> bf16; bf16(q*cos) + bf16(rot*sin) -> bf16.
 // ------------------------------------------------------------------------------------------
-__global__ void mrope_kernel(bf16* __restrict__ qkv, const int* __restrict__ pos, int T, int nh, int nkv, int hd,
-                             float theta, int sec_t, int sec_h, int inverse, bf16* __restrict__ k_out,
-                             bf16* __restrict__ v_out, long long kv_ld) {
+// one CTA per token: (cos, sin) of the hd/2 frequencies once into shared memory, then 16-byte chunks per head
+__global__ void __launch_bounds__(256)
+mrope_kernel(bf16* __restrict__ qkv, const int* __restrict__ pos, int T, int nh, int nkv, int hd, float theta,
+             int sec_t, int sec_h, int inverse, bf16* __restrict__ k_out, bf16* __restrict__ v_out, long long kv_ld) {
+  __shared__ float s_cs[128], s_sn[128];
   const int half = hd / 2;
+  const int chunks = half / 8;
   const int nrot = nh + nkv;
   const int qkv_ld = (nh + 2 * nkv) * hd;
-  const long long total = (long long)T * nrot * half;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int i = idx % half;
-    const int head = (idx / half) % nrot;
-    const int n = idx / ((long long)half * nrot);
-    const int stream = i < sec_t ? 0 : (i < sec_t + sec_h ? 1 : 2);
-    const float p_ = (float)pos[(long long)stream * T + n];
-    const float inv_freq = 1.0f / powf(theta, (float)(2 * i) / (float)hd);
-    float sn, cs;
-    sincosf(p_ * inv_freq, &sn, &cs);
-    cs = bf16_round(cs);
-    sn = bf16_round(sn);
-    if (inverse) sn = -sn;
-    bf16* p = qkv + (long long)n * qkv_ld + head * hd;
-    const float a = __bfloat162float(p[i]), b = __bfloat162float(p[i + half]);
-    const float o1 = bf16_round(bf16_round(a * cs) + bf16_round(-b * sn));
-    const float o2 = bf16_round(bf16_round(b * cs) + bf16_round(a * sn));
-    p[i] = __float2bfloat16_rn(o1);
-    p[i + half] = __float2bfloat16_rn(o2);
-    if (k_out && head >= nh) {
-      bf16* kd = k_out + (long long)n * kv_ld + (head - nh) * hd;
-      kd[i] = __float2bfloat16_rn(o1);
-      kd[i + half] = __float2bfloat16_rn(o2);
+  for (int n = blockIdx.x; n < T; n += gridDim.x) {
+    if ((int)threadIdx.x < half) {
+      const int i = threadIdx.x;
+      const int stream = i < sec_t ? 0 : (i < sec_t + sec_h ? 1 : 2);
+      const float p_ = (float)pos[(long long)stream * T + n];
+      const float inv_freq = 1.0f / powf(theta, (float)(2 * i) / (float)hd);
+      float sn, cs;
+      sincosf(p_ * inv_freq, &sn, &cs);
+      s_cs[i] = bf16_round(cs);
+      sn = bf16_round(sn);
+      s_sn[i] = inverse ? -sn : sn;
     }
-  }
-  if (v_out) {
-    const int vw = nkv * hd / 8;
-    const long long vt = (long long)T * vw;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < vt;
-         idx += (long long)gridDim.x * blockDim.x) {
-      const int c = idx % vw;
-      const int n = idx / vw;
-      *reinterpret_cast<uint4*>(v_out + (long long)n * kv_ld + c * 8) =
-          *reinterpret_cast<const uint4*>(qkv + (long long)n * qkv_ld + (nh + nkv) * hd + c * 8);
+    __syncthreads();
+    bf16* row = qkv + (long long)n * qkv_ld;
+    for (int w = threadIdx.x; w < nrot * chunks; w += blockDim.x) {
+      const int c = w % chunks, head = w / chunks;
+      bf16* p = row + head * hd + c * 8;
+      float a[8], b[8], oa[8], ob[8];
+      ld8f(p, a);
+      ld8f(p + half, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float cs = s_cs[c * 8 + j], sn = s_sn[c * 8 + j];
+        oa[j] = bf16_round(bf16_round(a[j] * cs) + bf16_round(-b[j] * sn));
+        ob[j] = bf16_round(bf16_round(b[j] * cs) + bf16_round(a[j] * sn));
+      }
+      st8f(p, oa);
+      st8f(p + half, ob);
+      if (k_out && head >= nh) {
+        bf16* kd = k_out + (long long)n * kv_ld + (head - nh) * hd + c * 8;
+        st8f(kd, oa);
+        st8f(kd + half, ob);
+      }
     }
+    if (v_out) {
+      for (int c = threadIdx.x; c < nkv * hd / 8; c += blockDim.x)
+        *reinterpret_cast<uint4*>(v_out + (long long)n * kv_ld + c * 8) =
+            *reinterpret_cast<const uint4*>(row + (nh + nkv) * hd + c * 8);
+    }
+    __syncthreads();
   }
 }
 
@@ -541,23 +565,26 @@ extern "C" int sb_rmsnorm_bwd(const void* x, const void* w, const float* rstd, c
 
 extern "C" int sb_rope_vit(void* qkv, int T, int heads, int head_dim, const int* grids_dev, int n_grids, int merge,
                            int inverse, sb_stream_t stream) {
-  SB_REQUIRE(qkv && grids_dev && T > 0 && heads > 0 && head_dim % 4 == 0 && n_grids > 0 && merge > 0,
-             "sb_rope_vit: bad arguments");
-  const long long work = (long long)T * 2 * heads * (head_dim / 2);
-  rope_vit_kernel<<<grid_for(work, 256), 256, 0, STREAM(stream)>>>((bf16*)qkv, T, heads, head_dim, grids_dev, n_grids,
-                                                                  merge, inverse);
+  SB_REQUIRE(qkv && grids_dev && T > 0 && heads > 0 && head_dim % 16 == 0 && head_dim <= 256 && n_grids > 0 && merge > 0,
+             "sb_rope_vit: bad arguments (head_dim must be a multiple of 16, <= 256)");
+  int threads = (2 * heads * (head_dim / 16) + 31) / 32 * 32;
+  threads = threads < 64 ? 64 : (threads > 256 ? 256 : threads);
+  if (threads < head_dim / 2) threads = (head_dim / 2 + 31) / 32 * 32;
+  rope_vit_kernel<<<T, threads, 0, STREAM(stream)>>>((bf16*)qkv, T, heads, head_dim, grids_dev, n_grids, merge, inverse);
   return sb_check_launch("sb_rope_vit");
 }
 
 extern "C" int sb_mrope(void* qkv, const int* pos, int T, int n_heads, int n_kv_heads, int head_dim, float theta,
                         int sec_t, int sec_h, int inverse, void* k_out, void* v_out, long long kv_ld,
                         sb_stream_t stream) {
-  SB_REQUIRE(qkv && pos && T > 0 && head_dim % 8 == 0 && sec_t >= 0 && sec_h >= 0 && sec_t + sec_h <= head_dim / 2,
-             "sb_mrope: bad arguments");
-  const long long work = (long long)T * (n_heads + n_kv_heads) * (head_dim / 2);
-  mrope_kernel<<<grid_for(work, 256), 256, 0, STREAM(stream)>>>((bf16*)qkv, pos, T, n_heads, n_kv_heads, head_dim,
-                                                               theta, sec_t, sec_h, inverse, (bf16*)k_out,
-                                                               (bf16*)v_out, kv_ld);
+  SB_REQUIRE(qkv && pos && T > 0 && head_dim % 16 == 0 && head_dim <= 256 && sec_t >= 0 && sec_h >= 0 &&
+                 sec_t + sec_h <= head_dim / 2, "sb_mrope: bad arguments (head_dim must be a multiple of 16, <= 256)");
+  SB_REQUIRE(k_out == nullptr || kv_ld % 8 == 0, "sb_mrope: kv_ld must be a multiple of 8");
+  int threads = ((n_heads + n_kv_heads) * (head_dim / 16) + 31) / 32 * 32;
+  threads = threads < 64 ? 64 : (threads > 256 ? 256 : threads);
+  if (threads < head_dim / 2) threads = (head_dim / 2 + 31) / 32 * 32;
+  mrope_kernel<<<T, threads, 0, STREAM(stream)>>>((bf16*)qkv, pos, T, n_heads, n_kv_heads, head_dim, theta, sec_t, sec_h,
+                                                  inverse, (bf16*)k_out, (bf16*)v_out, kv_ld);
   return sb_check_launch("sb_mrope");
 }
 
