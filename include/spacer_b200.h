@@ -54,7 +54,7 @@ enum {
   SB_EPI_STORE = 0,     /* D = bf16(acc + bias) [+ residual]                                        */
   SB_EPI_QUICKGELU = 1, /* z = acc + bias; aux = z (optional); D = z * sigmoid(1.702 z)   (ViT fc1) */
   SB_EPI_GELU = 2,      /* z = acc + bias; aux = z (optional); D = gelu_erf(z)       (PatchMerger)  */
-  SB_EPI_SWIGLU = 3,    /* B rows interleaved [64 gate | 64 up]; D[M,N/2] = silu(g)*u; aux = raw    */
+  SB_EPI_SWIGLU = 3,    /* B rows (and bias, if any) interleaved [64 gate | 64 up]; D[M,N/2] = silu(g)*u; aux = raw */
   SB_EPI_F32T = 4,      /* D_f32[split][n][m] = partial acc (swap-AB decode GEMV with split-K)      */
   SB_EPI_LMHEAD = 5,    /* per-row (max, sumexp) per N tile of bf16-rounded logits + target gather  */
   SB_EPI_DLOGITS = 6,   /* D = bf16(coef[m] * (onehot(target[m]) - exp(logit - lse[m])))            */
@@ -132,6 +132,9 @@ int sb_rmsnorm_bwd(const void* x, const void* w, const float* rstd, const void* 
  * grids_dev: int32 [n_grids][3] (t,h,w) on the device; inverse=1 applies the transpose rotation (backward) */
 int sb_rope_vit(void* qkv, int T, int heads, int head_dim, const int* grids_dev, int n_grids, int merge, int inverse,
                 sb_stream_t stream);
+/* same rotation with an explicit (h, w) position per token, pos_hw int32 [T][2] on the device: the window-reordered
+ * sequence of Qwen2.5-VL's vision tower (modeling_qwen2_5_vl.py:382-409, 474-482) */
+int sb_rope_vit_pos(void* qkv, int T, int heads, int head_dim, const int* pos_hw, int inverse, sb_stream_t stream);
 /* apply_multimodal_rotary_pos_emb (MQ2:188-254) in place on q,k of qkv [T,(nh+2nkv)*hd]; pos int32 [3,T];
  * optionally copies the rotated k and v into a KV cache (row stride kv_ld elements) */
 int sb_mrope(void* qkv, const int* pos, int T, int n_heads, int n_kv_heads, int head_dim, float theta, int sec_t,

@@ -257,6 +257,87 @@ def tiny_case(d, G=4, C=12, grid=(2, 8, 8), seed=11):
     return dict(grid_thw=grid_thw, pixel_values=pix, prompt_ids=prompt, completion_ids=comp, input_ids=ids, rewards=rewards)
 
 
+def hf_config25(d):
+    from transformers import Qwen2_5_VLConfig
+
+    cfg = Qwen2_5_VLConfig(
+        text_config=dict(hidden_size=d.hidden, num_hidden_layers=d.layers, num_attention_heads=d.heads,
+                         num_key_value_heads=d.kv_heads, intermediate_size=d.inter, vocab_size=d.vocab,
+                         rms_norm_eps=d.rms_eps,
+                         rope_parameters={"rope_type": "default", "rope_theta": d.rope_theta,
+                                          "mrope_section": list(d.mrope_section)},
+                         tie_word_embeddings=d.tie, max_position_embeddings=32768, use_sliding_window=False,
+                         bos_token_id=d.pad_id, eos_token_id=d.eos_id, pad_token_id=d.pad_id),
+        vision_config=dict(depth=d.v_depth, hidden_size=d.v_embed, intermediate_size=d.v_mlp, num_heads=d.v_heads,
+                           out_hidden_size=d.hidden, patch_size=d.patch, temporal_patch_size=d.t_patch,
+                           spatial_merge_size=d.merge, in_channels=d.in_ch, hidden_act="silu",
+                           window_size=d.v_window, fullatt_block_indexes=list(d.v_fullatt),
+                           tokens_per_second=d.tokens_per_second),
+        image_token_id=d.image_token_id, video_token_id=d.video_token_id,
+        vision_start_token_id=d.vision_start_id, vision_end_token_id=d.vision_end_id, tie_word_embeddings=d.tie)
+    cfg._attn_implementation = "eager"
+    return cfg
+
+
+def tiny_case25(d, G=4, C=10, seed=23):
+    """Qwen2.5-VL case: grid (2, 12, 8) -> merged 6 x 4 per frame = one full 4x4 window + one ragged 2x4 window."""
+    return tiny_case(d, G=G, C=C, grid=(2, 12, 8), seed=seed)
+
+
+def gen_tiny_model25():
+    """tests/golden/tiny_model25.pt: the real HF Qwen2_5_VLForConditionalGeneration (transformers 5.5.0) on the tiny
+    Qwen2.5-VL case: vision embeddings, per-token log-probs with explicit classic position ids, GRPO loss, gradient
+    norms/samples, plus HF's own default position ids (second_per_grid_ts given and absent)."""
+    from transformers import Qwen2_5_VLForConditionalGeneration
+
+    from oracle import grpo_ref as GR
+    from oracle import qwen25vl_ref as R25
+    from oracle import qwen2vl_ref as R
+
+    d = R25.dims25_tiny()
+    w = R25.init_weights(d, seed=0)
+    m = Qwen2_5_VLForConditionalGeneration(hf_config25(d)).float()
+    m.load_state_dict(w, strict=True)
+    case = tiny_case25(d)
+    ids = case["input_ids"]
+    G, P = ids.shape[0], case["prompt_ids"].shape[1]
+    grid = case["grid_thw"].repeat(G, 1)
+    pix = case["pixel_values"].repeat(G, 1)
+    sec = [1.5]
+    pos = R25.rope_index_classic(ids, grid, d, second_per_grid_ts=sec * G)
+    mm = (ids == d.video_token_id).long() * 2 + (ids == d.image_token_id).long()
+    m.train()
+    logits = m(input_ids=ids, pixel_values_videos=pix, video_grid_thw=grid, position_ids=pos, mm_token_type_ids=mm).logits
+    lp = R.per_token_logps(logits, ids)[:, P - 1:]
+    with torch.no_grad():
+        ve = m.model.visual(case["pixel_values"], case["grid_thw"]).pooler_output
+        hf_pos_sec, _ = m.model.get_rope_index(ids[:1], mm[:1], video_grid_thw=grid[:1], second_per_grid_ts=torch.tensor([2.0]))
+        hf_pos_none, _ = m.model.get_rope_index(ids[:1], mm[:1], video_grid_thw=grid[:1])
+    mask = GR.completion_mask(case["completion_ids"], d.eos_id)
+    adv, _ = GR.advantages(case["rewards"][:G], G)
+    rlp = lp.detach() + 0.03 * torch.randn(lp.shape, generator=torch.Generator().manual_seed(9))
+    loss, mean_kl = GR.grpo_loss(lp, rlp, adv, mask, beta=0.04)
+    loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+    keep = ["model.visual.patch_embed.proj.weight", "model.visual.blocks.0.attn.qkv.weight",
+            "model.visual.blocks.0.mlp.gate_proj.weight", "model.visual.blocks.1.mlp.up_proj.bias",
+            "model.visual.blocks.1.mlp.down_proj.weight", "model.visual.blocks.0.norm2.weight",
+            "model.visual.merger.ln_q.weight", "model.visual.merger.mlp.2.weight",
+            "model.language_model.layers.0.self_attn.q_proj.weight", "lm_head.weight"]
+    out = {
+        "dims": "tiny25", "weights_seed": 0, "case_seed": 23, "beta": 0.04, "second_per_grid_ts": sec[0],
+        "vision_embeds": ve.detach().half(), "logps": lp.detach(), "ref_logps": rlp, "mask": mask, "advantages": adv,
+        "loss": loss.detach(), "mean_kl": mean_kl.detach(),
+        "grad_norms": {k: grads[k].norm() for k in grads},
+        "grad_samples": {k: grads[k].flatten()[:: max(1, grads[k].numel() // 64)][:64].clone() for k in keep},
+        "pos_classic": pos[:, 0].to(torch.int16), "pos_hf55_sec2": hf_pos_sec[:, 0].to(torch.int16),
+        "pos_hf55_none": hf_pos_none[:, 0].to(torch.int16),
+        "transformers_version": __import__("transformers").__version__,
+    }
+    torch.save(out, os.path.join(OUT, "tiny_model25.pt"))
+    print("tiny_model25.pt: loss", float(loss), "kl", float(mean_kl), "lp[0,:4]", lp[0, :4].tolist())
+
+
 def gen_tiny_model():
     from transformers import Qwen2VLForConditionalGeneration
 
@@ -365,7 +446,9 @@ def gen_vision():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["rewards", "tiny", "vision"]
+    which = sys.argv[1:] or ["rewards", "tiny", "tiny25", "vision"]
+    if "tiny25" in which:
+        gen_tiny_model25()
     if "vision" in which:
         gen_vision()
     if "rewards" in which:

@@ -180,7 +180,7 @@ norm_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const fl
 // (q|k, head, 8-element chunk) is rotated with 16-byte loads and stores
 __global__ void __launch_bounds__(256)
 rope_vit_kernel(bf16* __restrict__ qkv, int T, int heads, int hd, const int* __restrict__ grids, int n_grids, int merge,
-                int inverse) {
+                int inverse, const int* __restrict__ pos_hw) {
   __shared__ float s_cs[128], s_sn[128];
   const int half = hd / 2;      // 40: rotation pairs (i, i+half)
   const int quarter = hd / 4;   // 20: first quarter of freqs follows h, second follows w
@@ -188,19 +188,25 @@ rope_vit_kernel(bf16* __restrict__ qkv, int T, int heads, int hd, const int* __r
   for (int n = blockIdx.x; n < T; n += gridDim.x) {
     if ((int)threadIdx.x < half) {
       const int i = threadIdx.x;
-      // locate the grid this token belongs to
-      int base = 0, gh = 1, gw = 1;
-      for (int g = 0; g < n_grids; ++g) {
-        const int gt = grids[g * 3], h_ = grids[g * 3 + 1], w_ = grids[g * 3 + 2];
-        const int cnt = gt * h_ * w_;
-        if (n < base + cnt || g == n_grids - 1) { gh = h_; gw = w_; break; }
-        base += cnt;
+      int hpos, wpos;
+      if (pos_hw) {   // explicit (h, w) per token: Qwen2.5-VL's window-reordered sequence
+        hpos = pos_hw[2 * n];
+        wpos = pos_hw[2 * n + 1];
+      } else {
+        // locate the grid this token belongs to
+        int base = 0, gh = 1, gw = 1;
+        for (int g = 0; g < n_grids; ++g) {
+          const int gt = grids[g * 3], h_ = grids[g * 3 + 1], w_ = grids[g * 3 + 2];
+          const int cnt = gt * h_ * w_;
+          if (n < base + cnt || g == n_grids - 1) { gh = h_; gw = w_; break; }
+          base += cnt;
+        }
+        const int r = (n - base) % (gh * gw);
+        const int blk = r / (merge * merge), inner = r % (merge * merge);
+        const int bw_n = gw / merge;
+        hpos = (blk / bw_n) * merge + inner / merge;
+        wpos = (blk % bw_n) * merge + inner % merge;
       }
-      const int r = (n - base) % (gh * gw);
-      const int blk = r / (merge * merge), inner = r % (merge * merge);
-      const int bw_n = gw / merge;
-      const int hpos = (blk / bw_n) * merge + inner / merge;
-      const int wpos = (blk % bw_n) * merge + inner % merge;
       const int fi = i < quarter ? i : i - quarter;
       const float inv_freq = 1.0f / powf(10000.0f, (float)(2 * fi) / (float)half);
       const float ang = (float)(i < quarter ? hpos : wpos) * inv_freq;
@@ -570,8 +576,20 @@ extern "C" int sb_rope_vit(void* qkv, int T, int heads, int head_dim, const int*
   int threads = (2 * heads * (head_dim / 16) + 31) / 32 * 32;
   threads = threads < 64 ? 64 : (threads > 256 ? 256 : threads);
   if (threads < head_dim / 2) threads = (head_dim / 2 + 31) / 32 * 32;
-  rope_vit_kernel<<<T, threads, 0, STREAM(stream)>>>((bf16*)qkv, T, heads, head_dim, grids_dev, n_grids, merge, inverse);
+  rope_vit_kernel<<<T, threads, 0, STREAM(stream)>>>((bf16*)qkv, T, heads, head_dim, grids_dev, n_grids, merge, inverse,
+                                                     nullptr);
   return sb_check_launch("sb_rope_vit");
+}
+
+extern "C" int sb_rope_vit_pos(void* qkv, int T, int heads, int head_dim, const int* pos_hw, int inverse,
+                               sb_stream_t stream) {
+  SB_REQUIRE(qkv && pos_hw && T > 0 && heads > 0 && head_dim % 16 == 0 && head_dim <= 256,
+             "sb_rope_vit_pos: bad arguments (head_dim must be a multiple of 16, <= 256)");
+  int threads = (2 * heads * (head_dim / 16) + 31) / 32 * 32;
+  threads = threads < 64 ? 64 : (threads > 256 ? 256 : threads);
+  if (threads < head_dim / 2) threads = (head_dim / 2 + 31) / 32 * 32;
+  rope_vit_kernel<<<T, threads, 0, STREAM(stream)>>>((bf16*)qkv, T, heads, head_dim, nullptr, 0, 1, inverse, pos_hw);
+  return sb_check_launch("sb_rope_vit_pos");
 }
 
 extern "C" int sb_mrope(void* qkv, const int* pos, int T, int n_heads, int n_kv_heads, int head_dim, float theta,

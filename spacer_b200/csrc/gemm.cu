@@ -487,8 +487,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               float vg[32], vu[32], o[32];
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                vg[j] = bf16_round(__uint_as_float(rg[j]));
-                vu[j] = bf16_round(__uint_as_float(ru[j]));
+                vg[j] = __uint_as_float(rg[j]);
+                vu[j] = __uint_as_float(ru[j]);
+              }
+              if (p.bias) {   // interleaved like the rows: bias[gcol..] = gate bias, bias[gcol + 64..] = up bias
+#pragma unroll
+                for (int j8 = 0; j8 < 32; j8 += 8) {
+                  float bg[8], bu[8];
+                  ld8(p.bias + gcol + j8, bg);
+                  ld8(p.bias + gcol + 64 + j8, bu);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) { vg[j8 + j] += bg[j]; vu[j8 + j] += bu[j]; }
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                vg[j] = bf16_round(vg[j]);
+                vu[j] = bf16_round(vu[j]);
                 o[j] = bf16_round(silu(vg[j])) * vu[j];
               }
               if (p.aux) {

@@ -38,12 +38,16 @@ F32 = torch.float32
 # ------------------------------------------------------------------------------------------------
 # position ids (host integer work)
 # ------------------------------------------------------------------------------------------------
-def rope_index(input_ids: torch.Tensor, grid_thw, dims: ModelDims, convention: str = "classic"):
+def rope_index(input_ids: torch.Tensor, grid_thw, dims: ModelDims, convention: str = "classic", second_per_grid_ts=None):
     """3-stream M-RoPE position ids for ONE row: int64 [3, L] and the next free position.
 
     "classic" is the formula of the transformers release the reference was written against and the released
     Qwen2-VL weights were trained with (per-frame raster t/h/w); "hf55" reproduces transformers 5.5.0
-    (modeling_qwen2_vl.py:934-988).  See SURVEY.md 8(c) drift #2."""
+    (modeling_qwen2_vl.py:934-988).  See SURVEY.md 8(c) drift #2.
+    Qwen2.5-VL (dims.variant == "qwen2_5_vl") spaces the temporal index of a video by
+    second_per_grid_t * tokens_per_second (modeling_qwen2_5_vl.py:1024-1135); `second_per_grid_ts` defaults to 1.0 per
+    video, which is what the reference's scoring forward uses after deleting the key (SG_RLVR_trainer.py:519-520)."""
+    v25 = dims.variant == "qwen2_5_vl"
     ids = input_ids.reshape(-1).cpu()
     L = ids.numel()
     is_v = (ids == dims.video_token_id) | (ids == dims.image_token_id)
@@ -55,23 +59,33 @@ def rope_index(input_ids: torch.Tensor, grid_thw, dims: ModelDims, convention: s
     while i < L:
         if isv[i]:
             t, h, w = grids[min(gi, len(grids) - 1)]
+            sec = 1.0
+            if second_per_grid_ts is not None and len(second_per_grid_ts) > 0:
+                sec = float(second_per_grid_ts[min(gi, len(second_per_grid_ts) - 1)])
+            is_video = ids[i].item() == dims.video_token_id
             gi += 1
             gh, gw = h // m, w // m
             n = t * gh * gw
             if convention == "classic":
-                tt = torch.arange(t).view(-1, 1).expand(-1, gh * gw).flatten()
+                tt = torch.arange(t).view(-1, 1).expand(-1, gh * gw)
+                if v25:
+                    tt = (tt * (sec * dims.tokens_per_second if is_video else 0.0)).long()
+                tt = tt.flatten()
                 hh = torch.arange(gh).view(1, -1, 1).expand(t, -1, gw).flatten()
                 ww = torch.arange(gw).view(1, 1, -1).expand(t, gh, -1).flatten()
                 blk = torch.stack([tt, hh, ww]) + nxt
+                after = int(blk.max()) + 1
             else:
                 ww = torch.arange(nxt, nxt + gw).repeat(gh * t)
                 hh = torch.arange(nxt, nxt + gh).repeat_interleave(gw * t)
-                tt = torch.full((n,), nxt, dtype=torch.long)
+                t0 = nxt * dims.tokens_per_second * int(sec) if v25 else nxt
+                tt = torch.full((n,), t0, dtype=torch.long)
                 blk = torch.stack([tt, hh, ww])
+                after = nxt + max(h, w) // m if v25 else int(blk.max()) + 1
             if i + n > L:
                 raise SpacerError("placeholder tokens do not match video_grid_thw (truncated prompt?)")
             pos[:, i:i + n] = blk
-            nxt = int(blk.max()) + 1
+            nxt = after
             i += n
         else:
             # run of text tokens
@@ -98,6 +112,48 @@ def slab_meta(grid_thw, device):
     return ops.make_meta(z, torch.tensor(starts), torch.tensor(ends), device)
 
 
+def window_plan(grid_thw, dims: ModelDims, device):
+    """Host integer work of Qwen2.5-VL's windowed vision tower (modeling_qwen2_5_vl.py:411-453, 474-497): the order of
+    the merged 2x2 token groups that makes every attention window contiguous (`widx`, applied to the patch rows BEFORE
+    the patch-embed GEMM, which is row-wise), the (h, w) rotary position of every reordered patch row, and the two
+    visibility tables: windows (most blocks) and whole frames (dims.v_fullatt blocks)."""
+    import torch.nn.functional as Fn
+    grids = [list(map(int, g)) for g in (grid_thw.tolist() if torch.is_tensor(grid_thw) else grid_thw)]
+    m, unit = dims.merge, dims.merge * dims.merge
+    win = dims.v_window // dims.merge // dims.patch
+    index, cu, base, pos_hw = [], [0], 0, []
+    for t, h, w in grids:
+        gh, gw = h // m, w // m
+        idx = torch.arange(t * gh * gw).reshape(t, gh, gw)
+        ph, pw = win - gh % win, win - gw % win
+        nh, nw = (gh + ph) // win, (gw + pw) // win
+        pad = Fn.pad(idx, (0, pw, 0, ph), "constant", -100)
+        pad = pad.reshape(t, nh, win, nw, win).permute(0, 1, 3, 2, 4).reshape(t, nh * nw, win, win)
+        seqlens = (pad != -100).sum([2, 3]).reshape(-1)
+        flat = pad.reshape(-1)
+        index.append(flat[flat != -100] + base)
+        cu.extend((seqlens.cumsum(0) * unit + cu[-1]).tolist())
+        base += t * gh * gw
+        hp = torch.arange(h).unsqueeze(1).expand(-1, w).reshape(gh, m, gw, m).permute(0, 2, 1, 3).flatten()
+        wp = torch.arange(w).unsqueeze(0).expand(h, -1).reshape(gh, m, gw, m).permute(0, 2, 1, 3).flatten()
+        pos_hw.append(torch.stack([hp, wp], dim=-1).repeat(t, 1))
+    widx = torch.cat(index)
+    cu = torch.unique_consecutive(torch.tensor(cu)).tolist()
+    pos_hw = torch.cat(pos_hw)
+    N = pos_hw.shape[0]
+    row_perm = (widx[:, None] * unit + torch.arange(unit)[None]).reshape(-1)     # patch-row permutation
+    pos_hw = pos_hw[row_perm]
+    starts = torch.zeros(N, dtype=torch.long)
+    ends = torch.zeros(N, dtype=torch.long)
+    for a, b in zip(cu[:-1], cu[1:]):
+        starts[a:b] = a
+        ends[a:b] = b
+    z = torch.zeros(N, dtype=torch.long)
+    return dict(widx=widx.to(I32).to(device), rev=torch.argsort(widx).to(I32).to(device),
+                row_perm=row_perm.to(I32).to(device), pos_hw=pos_hw.to(I32).contiguous().to(device),
+                meta_win=ops.make_meta(z, starts, ends, device), meta_full=slab_meta(grids, device), cu_window=cu)
+
+
 def causal_meta(T, device):
     t = torch.arange(T)
     return ops.make_meta(torch.zeros(T, dtype=torch.long), torch.zeros(T, dtype=torch.long), t + 1, device)
@@ -117,11 +173,12 @@ class PackedBatch:
     C: int
 
 
-def pack_prompt_completions(prompt_ids, completion_ids, grid_thw, dims: ModelDims, device, convention="classic"):
+def pack_prompt_completions(prompt_ids, completion_ids, grid_thw, dims: ModelDims, device, convention="classic",
+                            second_per_grid_ts=None):
     prompt_ids = prompt_ids.reshape(-1).cpu().long()
     comp = completion_ids.cpu().long()
     P, (G, C) = prompt_ids.numel(), comp.shape
-    ppos, nxt = rope_index(prompt_ids, grid_thw, dims, convention)
+    ppos, nxt = rope_index(prompt_ids, grid_thw, dims, convention, second_per_grid_ts)
     cpos = (torch.arange(C) + nxt).repeat(G)
     pos = torch.cat([ppos, cpos[None].expand(3, -1)], dim=1)
     ids = torch.cat([prompt_ids, comp.reshape(-1)])
@@ -191,6 +248,8 @@ class Qwen2VLB200:
     # ---- vision tower ----------------------------------------------------------------------------
     def vit_forward(self, pixel_values, grid_thw, tape: dict | None = None):
         """Qwen2VisionTransformerPretrainedModel.forward (MQ2:757-795).  pixel_values [N_p, 1176] fp32/bf16."""
+        if self.dims.variant == "qwen2_5_vl":
+            return self._vit25_forward(pixel_values, grid_thw, tape)
         d, W = self.dims, self.params
         grid_list = grid_thw.tolist() if torch.is_tensor(grid_thw) else grid_thw
         pix = pixel_values if pixel_values.dtype == BF16 else ops.cast_f32_bf16(pixel_values.contiguous())
@@ -229,7 +288,112 @@ class Qwen2VLB200:
             tape.update(x_last=x, mm=rm[1], sm=rm[2], zm=zm)
         return out
 
+    # ---- Qwen2.5-VL vision tower -------------------------------------------------------
+    def _vit25_forward(self, pixel_values, grid_thw, tape: dict | None = None):
+        """Qwen2_5_VisionTransformerPretrainedModel.forward (modeling_qwen2_5_vl.py:455-518): RMSNorm blocks with a
+        biased SwiGLU MLP, attention inside 112-pixel windows except in the full-attention blocks, merged tokens
+        restored to the original order at the end.  The window reorder is applied to the patch rows before the
+        (row-wise) patch-embed GEMM, so no activation is ever permuted and the backward needs no scatter."""
+        d, W = self.dims, self.params
+        grid_list = grid_thw.tolist() if torch.is_tensor(grid_thw) else grid_thw
+        pix = pixel_values if pixel_values.dtype == BF16 else ops.cast_f32_bf16(pixel_values.contiguous())
+        T = pix.shape[0]
+        if T != sum(int(t) * int(h) * int(w) for t, h, w in grid_list):
+            raise SpacerError("pixel_values rows do not match video_grid_thw")
+        plan = window_plan(grid_list, d, self.device)
+        pixp = torch.empty_like(pix)
+        ops.call("sb_gather_rows", pix, plan["row_perm"], pixp, T, pix.shape[1])
+        E, nh, hd, Mp = d.v_embed, d.v_heads, d.v_head_dim, d.v_mlp_pad
+        x = ops.gemm(pixp, W["v.patch_w"])
+        save = tape is not None
+        if save:
+            tape.update(pix=pixp, plan=plan, blocks=[])
+        for i in range(d.v_depth):
+            p = f"v.{i}."
+            meta = plan["meta_full"] if i in d.v_fullatt else plan["meta_win"]
+            r1 = ops.rmsnorm_fwd(x, W[p + "ln1_w"], 1e-6, save_stats=save)
+            h = r1[0] if save else r1
+            qkv = ops.gemm(h, W[p + "qkv_w"], bias=W[p + "qkv_b"])
+            ops.call("sb_rope_vit_pos", qkv, T, nh, hd, plan["pos_hw"], 0)
+            r2 = ops.attn_fwd(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], meta, nh, nh, hd, save_lse=save)
+            a = r2[0] if save else r2
+            x2 = ops.gemm(a, W[p + "proj_w"], bias=W[p + "proj_b"], residual=x)
+            r3 = ops.rmsnorm_fwd(x2, W[p + "ln2_w"], 1e-6, save_stats=save, out=h)
+            gu = torch.empty((T, 2 * Mp), device=self.device, dtype=BF16) if save else None
+            act = ops.gemm(r3[0] if save else r3, W[p + "gu_w"], bias=W[p + "gu_b"], epilogue=EPI_SWIGLU, aux=gu)
+            x3 = ops.gemm(act, W[p + "down_w"], bias=W[p + "down_b"], residual=x2)
+            if save:
+                tape["blocks"].append(dict(x=x, s1=r1[1], qkv=qkv, a=a, lse=r2[1], x2=x2, s2=r3[1], gu=gu))
+            x = x3
+        rm = ops.rmsnorm_fwd(x, W["v.m.ln_w"], 1e-6, save_stats=save)
+        hm = (rm[0] if save else rm).view(T // (d.merge * d.merge), d.merge_dim)
+        zm = torch.empty_like(hm) if save else None
+        fm = ops.gemm(hm, W["v.m.fc0_w"], bias=W["v.m.fc0_b"], epilogue=EPI_GELU, aux=zm)
+        merged = ops.gemm(fm, W["v.m.fc2_w"], bias=W["v.m.fc2_b"])
+        out = torch.empty_like(merged)
+        ops.call("sb_gather_rows", merged, plan["rev"], out, merged.shape[0], merged.shape[1])
+        if save:
+            tape.update(x_last=x, sm=rm[1], zm=zm)
+        return out
+
+    def _vit25_backward(self, tape: dict, d_out, grads: GradStore):
+        d, W, G = self.dims, self.params, grads
+        E, nh, hd, Mp = d.v_embed, d.v_heads, d.v_head_dim, d.v_mlp_pad
+        T = tape["pix"].shape[0]
+        plan = tape["plan"]
+        # out = merged[rev]  =>  d_merged = d_out[widx]
+        d_m = torch.empty_like(d_out)
+        ops.call("sb_gather_rows", d_out.contiguous(), plan["widx"], d_m, d_out.shape[0], d_out.shape[1])
+        fm = torch.empty_like(tape["zm"])
+        ops.call("sb_act_fwd", tape["zm"], fm, fm.numel(), 1)
+        ops.gemm(d_m, fm, a_mn=True, b_mn=True, out=G["v.m.fc2_w"])
+        ops.call("sb_colsum", d_m, G["v.m.fc2_b"], d_m.shape[0], d_m.shape[1], d_m.stride(0))
+        d_fm = ops.gemm(d_m, W["v.m.fc2_w"], b_mn=True)
+        d_zm = fm
+        ops.call("sb_act_bwd", tape["zm"], d_fm, d_zm, d_zm.numel(), 1)
+        hm = ops.rmsnorm_fwd(tape["x_last"], W["v.m.ln_w"], 1e-6).view(-1, d.merge_dim)
+        ops.gemm(d_zm, hm, a_mn=True, b_mn=True, out=G["v.m.fc0_w"])
+        ops.call("sb_colsum", d_zm, G["v.m.fc0_b"], d_zm.shape[0], d_zm.shape[1], d_zm.stride(0))
+        d_hm = ops.gemm(d_zm, W["v.m.fc0_w"], b_mn=True).view(T, E)
+        dx = ops.rmsnorm_bwd(tape["x_last"], W["v.m.ln_w"], tape["sm"], d_hm, G["v.m.ln_w"])
+        del fm, d_fm, d_zm, hm, d_hm, d_m
+        for i in reversed(range(d.v_depth)):
+            p = f"v.{i}."
+            t = tape["blocks"][i]
+            meta = plan["meta_full"] if i in d.v_fullatt else plan["meta_win"]
+            # MLP: x3 = x2 + down(swiglu(gu)) ; gu = raw [gate|up] incl. bias
+            act = torch.empty((T, Mp), device=self.device, dtype=BF16)
+            ops.call("sb_swiglu_bwd", t["gu"], None, None, act, T, Mp)
+            ops.gemm(dx, act, a_mn=True, b_mn=True, out=G[p + "down_w"])
+            ops.call("sb_colsum", dx, G[p + "down_b"], T, E, E)
+            d_act = ops.gemm(dx, W[p + "down_w"], b_mn=True, out=act)
+            d_gu = torch.empty_like(t["gu"])
+            ops.call("sb_swiglu_bwd", t["gu"], d_act, d_gu, None, T, Mp)
+            h2 = ops.rmsnorm_fwd(t["x2"], W[p + "ln2_w"], 1e-6)
+            ops.gemm(d_gu, h2, a_mn=True, b_mn=True, out=G[p + "gu_w"])
+            ops.call("sb_colsum", d_gu, G[p + "gu_b"], T, 2 * Mp, 2 * Mp)
+            d_h2 = ops.gemm(d_gu, W[p + "gu_w"], b_mn=True, out=h2)
+            dx2 = ops.rmsnorm_bwd(t["x2"], W[p + "ln2_w"], t["s2"], d_h2, G[p + "ln2_w"], dres=dx)
+            del d_gu, act
+            ops.gemm(dx2, t["a"], a_mn=True, b_mn=True, out=G[p + "proj_w"])
+            ops.call("sb_colsum", dx2, G[p + "proj_b"], T, E, E)
+            d_a = ops.gemm(dx2, W[p + "proj_w"], b_mn=True)
+            qkv = t["qkv"]
+            d_qkv = torch.empty_like(qkv)
+            ops.attn_bwd(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], t["a"], t["lse"], d_a, meta, nh, nh, hd,
+                         d_qkv[:, :E], d_qkv[:, E:2 * E], d_qkv[:, 2 * E:])
+            ops.call("sb_rope_vit_pos", d_qkv, T, nh, hd, plan["pos_hw"], 1)
+            h = ops.rmsnorm_fwd(t["x"], W[p + "ln1_w"], 1e-6)
+            ops.gemm(d_qkv, h, a_mn=True, b_mn=True, out=G[p + "qkv_w"])
+            ops.call("sb_colsum", d_qkv, G[p + "qkv_b"], T, 3 * E, 3 * E)
+            d_h = ops.gemm(d_qkv, W[p + "qkv_w"], b_mn=True, out=h)
+            dx = ops.rmsnorm_bwd(t["x"], W[p + "ln1_w"], t["s1"], d_h, G[p + "ln1_w"], dres=dx2)
+            tape["blocks"][i] = None
+        ops.gemm(dx, tape["pix"], a_mn=True, b_mn=True, out=G["v.patch_w"])
+
     def vit_backward(self, tape: dict, d_out, grads: GradStore):
+        if self.dims.variant == "qwen2_5_vl":
+            return self._vit25_backward(tape, d_out, grads)
         d, W, G = self.dims, self.params, grads
         E, nh, hd = d.v_embed, d.v_heads, d.v_head_dim
         T = tape["pix"].shape[0]
@@ -702,7 +866,7 @@ class Qwen2VLB200:
     def generate(self, input_ids, pixel_values_videos=None, video_grid_thw=None, *, max_new_tokens=1024,
                  num_return_sequences=1, top_p=0.95, temperature=1.0, do_sample=True, seed=0, min_new_tokens=0,
                  pixel_values_videos_2=None, num_return_sequences_2=0, use_graph=True, attention_mask=None,
-                 return_stats=False, **unused):
+                 return_stats=False, second_per_grid_ts=None, **unused):
         """Sampled rollout: `num_return_sequences` completions of ONE prompt (TRN:463-467; generate() with
         do_sample, top_p, temperature 1).  Returns LongTensor [G, P + C'] (prompt echoed, finished rows padded).
 
@@ -723,7 +887,7 @@ class Qwen2VLB200:
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         ev[0].record()
         ids_dev = ids.to(self.device, I32)
-        pos, nxt = rope_index(ids, video_grid_thw, d, self.rope_convention)
+        pos, nxt = rope_index(ids, video_grid_thw, d, self.rope_convention, second_per_grid_ts)
         pos_dev = pos.to(I32).contiguous().to(self.device)
         meta = causal_meta(P, self.device)
         pixel_sets = [pixel_values_videos] + ([pixel_values_videos_2] if G2 > 0 else [])

@@ -21,9 +21,19 @@ ALIGN = 128  # elements
 def _layout(d: ModelDims):
     """[(internal name, shape, arena)] in arena order."""
     E, M, H, I = d.v_embed, d.v_mlp, d.hidden, d.inter
+    v25 = d.variant == "qwen2_5_vl"
+    Mp = d.v_mlp_pad
     out = [("v.patch_w", (E, d.patch_dim), "mat")]
     for i in range(d.v_depth):
         p = f"v.{i}."
+        if v25:   # RMSNorm, SwiGLU MLP with biases; gate|up interleaved and zero-padded to a multiple of 64 columns
+            out += [(p + "ln1_w", (E,), "vec"),
+                    (p + "qkv_w", (3 * E, E), "mat"), (p + "qkv_b", (3 * E,), "vec"),
+                    (p + "proj_w", (E, E), "mat"), (p + "proj_b", (E,), "vec"),
+                    (p + "ln2_w", (E,), "vec"),
+                    (p + "gu_w", (2 * Mp, E), "mat"), (p + "gu_b", (2 * Mp,), "vec"),
+                    (p + "down_w", (E, Mp), "mat"), (p + "down_b", (E,), "vec")]
+            continue
         out += [(p + "ln1_w", (E,), "vec"), (p + "ln1_b", (E,), "vec"),
                 (p + "qkv_w", (3 * E, E), "mat"), (p + "qkv_b", (3 * E,), "vec"),
                 (p + "proj_w", (E, E), "mat"), (p + "proj_b", (E,), "vec"),
@@ -31,8 +41,8 @@ def _layout(d: ModelDims):
                 (p + "fc1_w", (M, E), "mat"), (p + "fc1_b", (M,), "vec"),
                 (p + "fc2_w", (E, M), "mat"), (p + "fc2_b", (E,), "vec")]
     mh = d.merge_dim
-    out += [("v.m.ln_w", (E,), "vec"), ("v.m.ln_b", (E,), "vec"),
-            ("v.m.fc0_w", (mh, mh), "mat"), ("v.m.fc0_b", (mh,), "vec"),
+    out += [("v.m.ln_w", (E,), "vec")] + ([] if v25 else [("v.m.ln_b", (E,), "vec")])
+    out += [("v.m.fc0_w", (mh, mh), "mat"), ("v.m.fc0_b", (mh,), "vec"),
             ("v.m.fc2_w", (H, mh), "mat"), ("v.m.fc2_b", (H,), "vec")]
     out.append(("embed", (d.vocab, H), "mat"))
     for i in range(d.layers):
@@ -104,6 +114,17 @@ class ParamStore:
         for name in self.index:
             if name.endswith(("ln1_w", "ln2_w", "ln_w", "norm_w")):
                 self.views[name].fill_(1.0)
+        if self.dims.variant == "qwen2_5_vl" and self.dims.v_mlp_pad != self.dims.v_mlp:
+            M, Mp = self.dims.v_mlp, self.dims.v_mlp_pad
+            for i in range(self.dims.v_depth):     # the padded SwiGLU columns are structurally zero
+                p = f"v.{i}."
+                g, u = self._deinterleave(self.views[p + "gu_w"])
+                g[M:] = 0; u[M:] = 0
+                self.views[p + "gu_w"].copy_(self._interleave(g, u))
+                gb, ub = self._deinterleave(self.views[p + "gu_b"].view(-1, 1))
+                gb[M:] = 0; ub[M:] = 0
+                self.views[p + "gu_b"].copy_(self._interleave(gb, ub).view(-1))
+                self.views[p + "down_w"][:, M:] = 0
 
     # -------------------------------------------------------------------------------------------
     @staticmethod
@@ -122,15 +143,32 @@ class ParamStore:
         d = self.dims
         V = views if views is not None else self.views
         yield "model.visual.patch_embed.proj.weight", V["v.patch_w"].view(d.v_embed, d.in_ch, d.t_patch, d.patch, d.patch)
+        v25 = d.variant == "qwen2_5_vl"
         hf_v = {"ln1_w": "norm1.weight", "ln1_b": "norm1.bias", "qkv_w": "attn.qkv.weight", "qkv_b": "attn.qkv.bias",
                 "proj_w": "attn.proj.weight", "proj_b": "attn.proj.bias", "ln2_w": "norm2.weight",
                 "ln2_b": "norm2.bias", "fc1_w": "mlp.fc1.weight", "fc1_b": "mlp.fc1.bias",
                 "fc2_w": "mlp.fc2.weight", "fc2_b": "mlp.fc2.bias"}
+        if v25:
+            hf_v = {k: hf_v[k] for k in ("ln1_w", "qkv_w", "qkv_b", "proj_w", "proj_b", "ln2_w")}
         for i in range(d.v_depth):
             for k, hk in hf_v.items():
                 yield f"model.visual.blocks.{i}.{hk}", V[f"v.{i}.{k}"]
-        for k, hk in {"ln_w": "ln_q.weight", "ln_b": "ln_q.bias", "fc0_w": "mlp.0.weight", "fc0_b": "mlp.0.bias",
-                      "fc2_w": "mlp.2.weight", "fc2_b": "mlp.2.bias"}.items():
+            if v25:
+                M = d.v_mlp
+                b, p = f"model.visual.blocks.{i}.mlp.", f"v.{i}."
+                g, u = self._deinterleave(V[p + "gu_w"])
+                gb, ub = self._deinterleave(V[p + "gu_b"].view(-1, 1))
+                yield b + "gate_proj.weight", g[:M]
+                yield b + "gate_proj.bias", gb[:M].reshape(-1)
+                yield b + "up_proj.weight", u[:M]
+                yield b + "up_proj.bias", ub[:M].reshape(-1)
+                yield b + "down_proj.weight", V[p + "down_w"][:, :M]
+                yield b + "down_proj.bias", V[p + "down_b"]
+        merger = {"ln_w": "ln_q.weight", "ln_b": "ln_q.bias", "fc0_w": "mlp.0.weight", "fc0_b": "mlp.0.bias",
+                  "fc2_w": "mlp.2.weight", "fc2_b": "mlp.2.bias"}
+        if v25:
+            merger.pop("ln_b")
+        for k, hk in merger.items():
             yield f"model.visual.merger.{hk}", V[f"v.m.{k}"]
         L = "model.language_model."
         yield L + "embed_tokens.weight", V["embed"]
@@ -171,7 +209,27 @@ class ParamStore:
             return sd[k]
 
         put("v.patch_w", get("model.visual.patch_embed.proj.weight"))
-        for i in range(d.v_depth):
+        v25 = d.variant == "qwen2_5_vl"
+        for i in range(d.v_depth if v25 else 0):
+            b, p = f"model.visual.blocks.{i}.", f"v.{i}."
+            for k, hk in [("ln1_w", "norm1.weight"), ("qkv_w", "attn.qkv.weight"), ("qkv_b", "attn.qkv.bias"),
+                          ("proj_w", "attn.proj.weight"), ("proj_b", "attn.proj.bias"), ("ln2_w", "norm2.weight"),
+                          ("down_b", "mlp.down_proj.bias")]:
+                put(p + k, get(b + hk))
+            M, Mp, E = d.v_mlp, d.v_mlp_pad, d.v_embed
+
+            def padr(t, rows):   # zero-pad rows (dim 0)
+                t = t.to(self.device, torch.bfloat16)
+                out = torch.zeros((rows,) + tuple(t.shape[1:]), device=self.device, dtype=torch.bfloat16)
+                out[:t.shape[0]] = t
+                return out
+            put(p + "gu_w", self._interleave(padr(get(b + "mlp.gate_proj.weight"), Mp), padr(get(b + "mlp.up_proj.weight"), Mp)))
+            put(p + "gu_b", self._interleave(padr(get(b + "mlp.gate_proj.bias").reshape(-1, 1), Mp),
+                                             padr(get(b + "mlp.up_proj.bias").reshape(-1, 1), Mp)).reshape(-1))
+            dw = torch.zeros((E, Mp), device=self.device, dtype=torch.bfloat16)
+            dw[:, :M] = get(b + "mlp.down_proj.weight").to(self.device, torch.bfloat16)
+            put(p + "down_w", dw)
+        for i in range(0 if v25 else d.v_depth):
             b, p = f"model.visual.blocks.{i}.", f"v.{i}."
             for k, hk in [("ln1_w", "norm1.weight"), ("ln1_b", "norm1.bias"), ("qkv_w", "attn.qkv.weight"),
                           ("qkv_b", "attn.qkv.bias"), ("proj_w", "attn.proj.weight"), ("proj_b", "attn.proj.bias"),
@@ -180,6 +238,8 @@ class ParamStore:
                 put(p + k, get(b + hk))
         for k, hk in [("ln_w", "ln_q.weight"), ("ln_b", "ln_q.bias"), ("fc0_w", "mlp.0.weight"), ("fc0_b", "mlp.0.bias"),
                       ("fc2_w", "mlp.2.weight"), ("fc2_b", "mlp.2.bias")]:
+            if v25 and k == "ln_b":
+                continue
             put("v.m." + k, get("model.visual.merger." + hk))
         L = "model.language_model."
         put("embed", get(L + "embed_tokens.weight"))

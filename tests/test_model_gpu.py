@@ -202,3 +202,90 @@ def test_trainer_step_runs_and_updates():
     mt2 = tr.training_step(ex)
     assert mt2["kl"] >= 0.0
     assert set(tr.log()) >= {"reward", "kl", "loss"}
+
+
+# ------------------------------------------------------------------------------------------------
+# Qwen2.5-VL: windowed RMSNorm/SwiGLU vision tower + temporal M-RoPE spacing on the CUDA path
+# ------------------------------------------------------------------------------------------------
+def _setup25():
+    from oracle import qwen25vl_ref as R25
+    from oracle.make_golden import tiny_case25
+    from spacer_b200 import config
+    from spacer_b200.model import Qwen2VLB200
+    d_or, d = R25.dims25_tiny(), config.tiny25()
+    w = R25.init_weights(d_or, seed=0)
+    m = Qwen2VLB200(d, "cuda:0").load_state_dict(w)
+    return R25, d_or, d, w, m, tiny_case25(d_or)
+
+
+def test_qwen25_state_dict_roundtrip_and_host_logic():
+    from spacer_b200.model import rope_index, window_plan
+    R25, d_or, d, w, m, case = _setup25()
+    sd = m.state_dict()
+    assert set(sd) == set(w)
+    for k in w:
+        assert torch.equal(sd[k].cpu().float(), w[k].bfloat16().float()), k
+    ids = case["prompt_ids"]
+    for sec in (None, [1.5], [2.0]):
+        pos, _ = rope_index(ids, case["grid_thw"], d, "classic", sec)
+        assert torch.equal(pos, R25.rope_index_classic(ids, case["grid_thw"], d_or, sec)[:, 0])
+        pos, _ = rope_index(ids, case["grid_thw"], d, "hf55", sec)
+        assert torch.equal(pos, R25.rope_index_hf55(ids, case["grid_thw"], d_or, sec)[:, 0])
+    plan = window_plan(case["grid_thw"], d, "cuda:0")
+    widx, cu = R25.window_index(case["grid_thw"], d_or)
+    assert torch.equal(plan["widx"].cpu().long(), widx) and plan["cu_window"] == cu.tolist()
+
+
+def test_qwen25_vit_and_logps_vs_oracle_and_hf_golden():
+    from oracle import qwen2vl_ref as R
+    from spacer_b200.model import pack_prompt_completions
+    R25, d_or, d, w, m, case = _setup25()
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "tiny_model25.pt"), weights_only=False)
+    wb = {k: v.bfloat16().float() for k, v in w.items()}
+    grid, pix = case["grid_thw"], case["pixel_values"]
+    ve = m.vit_forward(pix.cuda(), grid).float().cpu()
+    ve_or = R25.vit_forward(wb, pix.bfloat16().float(), grid, d_or)
+    assert (ve - ve_or).abs().max() < 3e-2 * ve_or.abs().max()
+    assert (ve - gold["vision_embeds"].float()).abs().max() < 4e-2 * ve_or.abs().max()
+    sec = [gold["second_per_grid_ts"]]
+    batch = pack_prompt_completions(case["prompt_ids"], case["completion_ids"], grid, d, m.device, second_per_grid_ts=sec)
+    lp = m.per_token_logps(batch, pix.cuda(), grid).cpu()
+    err = (lp - gold["logps"]).abs()
+    assert err.max() < 2e-2 and err.mean() < 3e-3, (err.max().item(), err.mean().item())
+
+
+def test_qwen25_gradients_vs_oracle():
+    from oracle import grpo_ref as GR
+    from oracle import qwen2vl_ref as R
+    from spacer_b200.model import GradStore, pack_prompt_completions
+    R25, d_or, d, w, m, case = _setup25()
+    wb = {k: v.bfloat16().float().requires_grad_() for k, v in w.items()}
+    grid, pix = case["grid_thw"], case["pixel_values"]
+    ids = case["input_ids"]
+    G, P = ids.shape[0], case["prompt_ids"].shape[1]
+    sec = [1.5]
+    pos = R25.rope_index_classic(ids, grid.repeat(G, 1), d_or, sec * G)
+    logits = R25.model_logits(wb, ids, pix.bfloat16().float().repeat(G, 1), grid.repeat(G, 1), pos, d_or)
+    lp = R.per_token_logps(logits, ids)[:, P - 1:]
+    ref_lp = lp.detach() + 0.05
+    adv, _ = GR.advantages(case["rewards"][:G], G)
+    mask = GR.completion_mask(case["completion_ids"], d_or.eos_id)
+    loss, _ = GR.grpo_loss(lp, ref_lp, adv, mask, 0.04)
+    loss.backward()
+    batch = pack_prompt_completions(case["prompt_ids"], case["completion_ids"], grid, d, m.device, second_per_grid_ts=sec)
+    grads = GradStore(m.params)
+    out = m.grpo_forward_backward(batch, pix.cuda(), grid, ref_lp.cuda(), adv.cuda(), 0.04, grads)
+    assert abs(float(out["loss"]) - float(loss)) < 5e-4 + 0.05 * abs(float(loss))
+    gsd = dict(m.params.hf_items({n: grads[n] for n in m.params.index}))
+    checked = 0
+    for k, t in wb.items():
+        if not k.startswith("model.visual.") or t.grad is None:
+            continue
+        a, b = gsd[k].float().cpu().flatten(), t.grad.flatten()
+        if b.norm() < 1e-9:
+            continue
+        cos = torch.dot(a, b) / (a.norm() * b.norm() + 1e-20)
+        assert cos > 0.99, (k, float(cos))
+        assert 0.85 < float(a.norm() / b.norm()) < 1.15, (k, float(a.norm() / b.norm()))
+        checked += 1
+    assert checked >= 20

@@ -174,3 +174,56 @@ def test_top_p_filter_semantics():
     assert torch.isinf(out[0, 3]) and torch.isinf(out[0, 4]) and not torch.isinf(out[0, :3]).any()
     one = R.top_p_filter(torch.tensor([[0.0, -50.0]]), 0.0001)
     assert not torch.isinf(one[0, 0])  # top-1 always kept
+
+
+# ---------------------------------------------------------------------------------------------
+# Qwen2.5-VL: oracle/qwen25vl_ref.py against the real HF Qwen2_5_VLForConditionalGeneration
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def tiny25_gold():
+    return torch.load(os.path.join(GOLD, "tiny_model25.pt"), weights_only=False)
+
+
+def test_oracle_qwen25_matches_hf_golden(tiny25_gold):
+    """Windowed ViT (RMSNorm, SwiGLU with biases, window reorder and its inverse), temporal M-RoPE spacing, log-probs,
+    loss and gradients of the plain-torch restatement equal HF 5.5.0's on the committed tiny Qwen2.5-VL case."""
+    from oracle import grpo_ref as GR
+    from oracle import qwen25vl_ref as R25
+    from oracle import qwen2vl_ref as R
+    from oracle.make_golden import tiny_case25
+    d = R25.dims25_tiny()
+    w = R25.init_weights(d, seed=0)
+    for v in w.values():
+        v.requires_grad_()
+    case = tiny_case25(d)
+    ids = case["input_ids"]
+    G, P = ids.shape[0], case["prompt_ids"].shape[1]
+    grid = case["grid_thw"].repeat(G, 1)
+    sec = [tiny25_gold["second_per_grid_ts"]] * G
+    pos = R25.rope_index_classic(ids, grid, d, second_per_grid_ts=sec)
+    assert torch.equal(pos[:, 0].to(torch.int16), tiny25_gold["pos_classic"])
+    # temporal spacing really is 1.5 s x 2 tokens/s = 3 per temporal patch for the classic formula
+    vis = (ids[0] == d.video_token_id).nonzero().flatten()
+    assert pos[0, 0, vis[-1]] - pos[0, 0, vis[0]] == 3
+    # HF 5.5.0's own default position ids (explicit-input convention, SURVEY 8(c) drift #2)
+    assert torch.equal(R25.rope_index_hf55(ids[:1], grid[:1], d, [2.0])[:, 0].to(torch.int16), tiny25_gold["pos_hf55_sec2"])
+    assert torch.equal(R25.rope_index_hf55(ids[:1], grid[:1], d)[:, 0].to(torch.int16), tiny25_gold["pos_hf55_none"])
+    widx, cu = R25.window_index(case["grid_thw"], d)
+    assert sorted(widx.tolist()) == list(range(case["pixel_values"].shape[0] // 4))
+    assert cu.tolist() == [0, 64, 96, 160, 192]          # per frame: a full 4x4 window and a ragged 2x4 one
+    ve = R25.vit_forward(w, case["pixel_values"], case["grid_thw"], d)
+    assert (ve.detach() - tiny25_gold["vision_embeds"].float()).abs().max() < 2e-3   # fixture stored as fp16
+    logits = R25.model_logits(w, ids, case["pixel_values"].repeat(G, 1), grid, pos, d)
+    lp = R.per_token_logps(logits, ids)[:, P - 1:]
+    assert (lp.detach() - tiny25_gold["logps"]).abs().max() < 2e-5
+    mask = GR.completion_mask(case["completion_ids"], d.eos_id)
+    adv, _ = GR.advantages(case["rewards"][:G], G)
+    loss, kl = GR.grpo_loss(lp, tiny25_gold["ref_logps"], adv, mask, tiny25_gold["beta"])
+    assert abs(float(loss) - float(tiny25_gold["loss"])) < 1e-6
+    loss.backward()
+    for k, gn in tiny25_gold["grad_norms"].items():
+        mine = w[k].grad.norm()
+        assert abs(float(mine) - float(gn)) <= 1e-4 * float(gn) + 1e-7, k
+    for k, smp in tiny25_gold["grad_samples"].items():
+        gk = w[k].grad.flatten()
+        assert torch.allclose(gk[:: max(1, gk.numel() // 64)][:64], smp, rtol=1e-3, atol=1e-7), k
