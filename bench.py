@@ -30,6 +30,8 @@ CONFIGS = {
     # name: (preset, frames, res, G, text tokens, C)
     "c3": dict(preset="7b", frames=16, res=448, G=8, text=256, C=512,
                workload="cfg3: Qwen2-VL-7B random-init, 16 frames x 448^2 (grid 8x32x32, 2048 vision tokens), P=2304, G=8 (+4 frame-shuffled, T-GRPO), C=512 (EOS disabled), beta=0.04"),
+    "c3q25": dict(preset="25-7b", frames=16, res=448, G=8, text=256, C=512,
+                  workload="cfg3 on Qwen2.5-VL-7B random-init (the family run_SpaceR_SG_RLVR.sh trains; windowed ViT): 16 frames x 448^2, P=2304, G=8 (+4 frame-shuffled), C=512 (EOS disabled), beta=0.04"),
     "c2": dict(preset="2b", frames=8, res=336, G=4, text=256, C=512,
                workload="cfg2: Qwen2-VL-2B random-init, 8 frames x 336^2 (grid 4x24x24, 576 vision tokens), P=832, G=4 (+2 shuffled), C=512"),
     "tiny": dict(preset="tiny", frames=2, res=112, G=4, text=24, C=16,
@@ -131,7 +133,8 @@ def cpu_reference_sample(cfg_name, threads=None):
     from oracle import qwen2vl_ref as R
     import torch.nn.functional as F
     cfg = CONFIGS[cfg_name]
-    full = {"7b": R.dims_7b, "2b": R.dims_2b, "tiny": R.dims_tiny}[cfg["preset"]]()
+    # (the Qwen2.5-VL presets differ from Qwen2-VL only in the ViT MLP shape: the CPU sample uses the Qwen2-VL block)
+    full = {"7b": R.dims_7b, "2b": R.dims_2b, "tiny": R.dims_tiny, "25-7b": R.dims_7b}[cfg["preset"]]()
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
     d1 = R.Dims(**{**full.__dict__, "layers": 1, "v_depth": 1})
