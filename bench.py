@@ -387,8 +387,18 @@ def main():
     rows = cfg["G"] + (cfg["G"] // 2 if tcfg.temporal else 0)
     prof = policy.profile_decode_gemv(rows=rows, reps=3)
     ach = stats.get("decode_gbs") or 0.0
+    # DRAM bytes of one decode step measured under ncu (--cache-control none), committed with the profile it came from
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", f"r01_decode_traffic_{args.config}.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        if tj.get("rows") == rows:
+            traffic = tj["dram_read_bytes"] + tj["dram_write_bytes"]
+            traffic_src = f"profiles/{os.path.basename(tpath)}: dram read + write summed over the {tj['kernels']} kernels of one step"
     roofline = {"bound": "hbm", "kernel": "decode step (one CUDA-graph launch; dominated by gemm_kernel<K-major,K-major,BN=16,F32T>)",
-                "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
+                "traffic_source": traffic_src,
                 "peak_source": peak_src + ", sustained HBM copy bandwidth",
                 "bytes_per_launch": stats.get("decode_bytes_per_step"), "avg_launch_us": (stats.get("decode_ms_per_step") or 0) * 1e3,
                 "kernels_per_launch": stats.get("graph_nodes"),
@@ -411,7 +421,8 @@ def main():
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": cfg["workload"], "parallelism": f"dp{world}", "inputs": "larger than L2 (14 GB of weights streamed per decode step); step input = uint8 video frames",
                        "adam_moments": "bf16" if args.moments_bf16 else "fp32", "temporal": tcfg.temporal,
-                       "rollout_tok_per_s": world * toks / (ms_res / 1000.0),
+                       "rollout_tok_per_s": (world * (toks / K) / (stats["rollout_ms"] / 1000.0)) if stats.get("rollout_ms") else None,
+                       "tok_per_s_of_step": world * toks / (ms_res / 1000.0),
                        "rollout_ms_per_step": stats.get("rollout_ms"), "prefill_ms": stats.get("prefill_ms"),
                        "decode_ms_per_token_step": stats.get("decode_ms_per_step"), "phase_ms": phase_ms},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},

@@ -241,6 +241,12 @@ int sb_sample_top_p(const float* logits, long long ld, int R, int V, float top_p
                     const int* step_ptr, int* finished, int* out_tokens, int* out_ids, long long out_ld,
                     float* out_logprob, int eos_id, int pad_id, int suppress_eos, const long long* seed_dev,
                     sb_stream_t stream);
+/* greedy decoding: argmax of the bf16-rounded logits, lowest index on ties (do_sample=False; SpaceR-Eval's
+ * `generate(..., temperature=0.01)` over a top_k = 1 generation config, SpaceR-Eval/data_utils/vsibench.py:174);
+ * same EOS / pad / out_ids bookkeeping as sb_sample_top_p */
+int sb_sample_greedy(const float* logits, long long ld, int R, int V, const int* step_ptr, int* finished,
+                     int* out_tokens, int* out_ids, long long out_ld, int eos_id, int pad_id, int suppress_eos,
+                     sb_stream_t stream);
 int sb_step_advance(int* step_ptr, sb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------

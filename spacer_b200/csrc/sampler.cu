@@ -313,6 +313,60 @@ sample_kernel(const SampleParams p) {
   sb_trace_mark(tr, 2);
 }
 
+// Greedy decoding (SpaceR-Eval: `model.generate(..., temperature=0.01)` on top of the checkpoint's top_k = 1 generation
+// config, data_utils/vsibench.py:174; HF `do_sample=False`): token = argmax of the bf16-rounded logits, lowest index on
+// ties (torch.argmax); EOS / pad bookkeeping identical to sample_kernel.  One CTA per row.
+__global__ void __launch_bounds__(1024)
+greedy_kernel(const float* __restrict__ logits, long long ld, int V, const int* __restrict__ step_ptr,
+              int* __restrict__ finished, int* __restrict__ out_tokens, int* __restrict__ out_ids, long long out_ld,
+              int eos_id, int pad_id, int suppress_eos) {
+  pdl_launch_dependents();
+  const int tr = (blockIdx.x == 0 && threadIdx.x == 0) ? sb_trace_begin(SB_TR_SAMPLE) : -1;
+  pdl_wait();
+  sb_trace_mark(tr, 1);
+  __shared__ float s_v[32];
+  __shared__ int s_i[32];
+  const int row = blockIdx.x;
+  const float* lg = logits + (long long)row * ld;
+  float best = -INFINITY;
+  int best_i = 0x7fffffff;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    float v = bf16_round(lg[i]);
+    if (suppress_eos && i == eos_id) v = -INFINITY;
+    if (v > best) { best = v; best_i = i; }       // ascending i per thread: the first maximum is kept
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { s_v[w] = best; s_i[w] = best_i; }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    best = lane < nw ? s_v[lane] : -INFINITY;
+    best_i = lane < nw ? s_i[lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+      if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+    }
+    if (lane == 0) {
+      const int step = *step_ptr;
+      int tok = best_i;
+      const int fin = finished ? finished[row] : 0;
+      if (fin) tok = pad_id;
+      else if (tok == eos_id && finished) finished[row] = 1;
+      out_tokens[row] = tok;
+      if (out_ids) out_ids[(long long)row * out_ld + step] = tok;
+    }
+  }
+  sb_trace_mark(tr, 2);
+}
+
 __global__ void step_advance_kernel(int* step_ptr) {
   pdl_launch_dependents();
   const int tr = sb_trace_begin(SB_TR_ADVANCE);
@@ -325,6 +379,15 @@ __global__ void step_advance_kernel(int* step_ptr) {
 }  // namespace
 
 SB_DEFINE_TRACE_SETTER(sb_trace_set_sampler)
+
+extern "C" int sb_sample_greedy(const float* logits, long long ld, int R, int V, const int* step_ptr, int* finished,
+                                int* out_tokens, int* out_ids, long long out_ld, int eos_id, int pad_id, int suppress_eos,
+                                sb_stream_t stream) {
+  SB_REQUIRE(logits && step_ptr && out_tokens && R > 0 && V > 0, "sb_sample_greedy: bad arguments");
+  SB_CUDA(sb_launch(greedy_kernel, dim3(R), dim3(1024), 0, reinterpret_cast<cudaStream_t>(stream), sb_pdl_enabled(), logits,
+                    ld, V, step_ptr, finished, out_tokens, out_ids, out_ld, eos_id, pad_id, suppress_eos));
+  return sb_check_launch("sb_sample_greedy");
+}
 
 extern "C" int sb_sample_top_p(const float* logits, long long ld, int R, int V, float top_p, unsigned long long seed,
                                const int* step_ptr, int* finished, int* out_tokens, int* out_ids, long long out_ld,

@@ -740,6 +740,17 @@ class Qwen2VLB200:
     # tops out at ~48 GB/s -- the step gets slower (3.30 vs 3.16 ms, profiles/r01_decode_fused_epilogues.md).
     decode_fused = os.environ.get("SB_DECODE_FUSED") is not None
 
+    def _sample(self, st, top_p, suppress_eos):
+        """Next token per row from st["logits"]: top-p sampling (TRN:277-302 generation configs) or, for top_p <= 0,
+        greedy argmax (evaluation, SpaceR-Eval/data_utils/vsibench.py:174)."""
+        d, R = self.dims, st["R"]
+        if top_p <= 0.0:
+            ops.call("sb_sample_greedy", st["logits"], d.vocab, R, d.vocab, st["step"], st["finished"], st["tokens"],
+                     st["out_ids"], st["c_max"], d.eos_id, d.pad_id, int(suppress_eos))
+        else:
+            ops.call("sb_sample_top_p", st["logits"], d.vocab, R, d.vocab, float(top_p), 0, st["step"], st["finished"],
+                     st["tokens"], st["out_ids"], st["c_max"], None, d.eos_id, d.pad_id, int(suppress_eos), st["seed"])
+
     def _decode_step(self, st, rope_base, rows_group0, top_p, suppress_eos):
         """Enqueue one decode step (feeds tokens at slot *step, samples the next token into slot *step + 1)."""
         if self.decode_fused:
@@ -778,8 +789,7 @@ class Qwen2VLB200:
         ops.call("sb_dec_residual_rmsnorm", st["x"], parts, sp, RP * H, H, W["norm_w"], st["xn"], R, H, d.rms_eps)
         self._gemv(W["lm_head"], st["xn"], st["logits"], 1, next_w=W["l.0.qkv_w"])   # warms L2 for the next step
         ops.call("sb_step_advance", st["step"])
-        ops.call("sb_sample_top_p", st["logits"], d.vocab, R, d.vocab, float(top_p), 0, st["step"], st["finished"],
-                 st["tokens"], st["out_ids"], st["c_max"], None, d.eos_id, d.pad_id, int(suppress_eos), st["seed"])
+        self._sample(st, top_p, suppress_eos)
 
     def _decode_step_fused(self, st, rope_base, rows_group0, top_p, suppress_eos):
         """One decode step with the fused GEMV epilogues: per layer qkv GEMV (+ bias, M-RoPE, KV append) -> attention ->
@@ -832,8 +842,7 @@ class Qwen2VLB200:
                        epilogue=ops.EPI_DEC_RESID)
         self._gemv(W["lm_head"], st["xw"], st["logits"], 1, next_w=W["l.0.qkv_w"], dec=scaled())
         ops.call("sb_step_advance", st["step"])
-        ops.call("sb_sample_top_p", st["logits"], d.vocab, R, d.vocab, float(top_p), 0, st["step"], st["finished"],
-                 st["tokens"], st["out_ids"], st["c_max"], None, d.eos_id, d.pad_id, int(suppress_eos), st["seed"])
+        self._sample(st, top_p, suppress_eos)
 
     def _decode_graph(self, st, rope_base, rows_group0, top_p, suppress_eos):
         """Capture one decode step into a CUDA graph (cached per decode state and step arguments).  Captured with the
@@ -874,8 +883,13 @@ class Qwen2VLB200:
         the same text with another video (T-GRPO's frame-shuffled rollout, TRN:442-458, 469-475); the result is
         then a tuple (ids_main, ids_second)."""
         d = self.dims
-        if not do_sample or temperature != 1.0:
-            raise SpacerError("generate: only do_sample=True with temperature 1 (the reference's configuration)")
+        if not do_sample or temperature <= 0.05:
+            # evaluation mode (SpaceR-Eval: temperature 0.01 over the checkpoint's top_k = 1 config): greedy argmax.
+            # (repetition_penalty of the released generation_config.json is not applied.)
+            top_p = 0.0
+        elif temperature != 1.0:
+            raise SpacerError("generate: sampling is implemented for temperature 1 (the reference's training configuration); "
+                              "temperature <= 0.05 or do_sample=False selects greedy decoding")
         if min_new_tokens not in (0, max_new_tokens):
             raise SpacerError("generate: min_new_tokens must be 0 or max_new_tokens")
         ids = input_ids.reshape(-1)
@@ -903,8 +917,7 @@ class Qwen2VLB200:
             del hf, vis
         self._gemv(self.params["lm_head"], st["xn"], st["logits"], 1)
         suppress = min_new_tokens > 0
-        ops.call("sb_sample_top_p", st["logits"], d.vocab, R, d.vocab, float(top_p), 0, st["step"], st["finished"],
-                 st["tokens"], st["out_ids"], st["c_max"], None, d.eos_id, d.pad_id, int(suppress), st["seed"])
+        self._sample(st, top_p, suppress)
         n_steps = max_new_tokens - 1
         graph, graph_nodes, replays = None, 0, 0
         if n_steps > 0 and use_graph:

@@ -289,3 +289,25 @@ def test_qwen25_gradients_vs_oracle():
         assert 0.85 < float(a.norm() / b.norm()) < 1.15, (k, float(a.norm() / b.norm()))
         checked += 1
     assert checked >= 20
+
+
+def test_greedy_generation_for_eval():
+    """Evaluation reuse of the rollout engine: do_sample=False / temperature 0.01 -> argmax with the
+    lowest index on ties, independent of the seed, graph == eager, EOS stops a row."""
+    R, d_or, d, m, w, wb = _setup()
+    case = _case(d_or)
+    grid, prompt = case["grid_thw"], case["prompt_ids"]
+    P = prompt.shape[1]
+    pix = case["pixel_values"].cuda()
+    a = m.generate(prompt, pix, grid, max_new_tokens=8, num_return_sequences=1, do_sample=False, seed=1, min_new_tokens=8)
+    st = m._last_decode_state
+    last_logits = st["logits"][0, :1].float().bfloat16().float()
+    assert int(a[0, -1]) == int(last_logits[0].argmax())       # torch.argmax returns the first maximum
+    b = m.generate(prompt, pix, grid, max_new_tokens=8, num_return_sequences=1, temperature=0.01, seed=99, min_new_tokens=8)
+    c = m.generate(prompt, pix, grid, max_new_tokens=8, num_return_sequences=1, do_sample=False, seed=5, min_new_tokens=8,
+                   use_graph=False)
+    assert torch.equal(a, b) and torch.equal(a, c)
+    rows = m.generate(prompt, pix, grid, max_new_tokens=8, num_return_sequences=3, do_sample=False, min_new_tokens=8)
+    assert torch.equal(rows[0], rows[1]) and torch.equal(rows[0], rows[2]) and torch.equal(rows[:1], a)
+    free = m.generate(prompt, pix, grid, max_new_tokens=30, num_return_sequences=1, do_sample=False)
+    assert free.shape[1] <= P + 30 and torch.equal(free[:, :P].cpu(), prompt)
