@@ -34,6 +34,10 @@ CONFIGS = {
                   workload="cfg3 on Qwen2.5-VL-7B random-init (the family run_SpaceR_SG_RLVR.sh trains; windowed ViT): 16 frames x 448^2, P=2304, G=8 (+4 frame-shuffled), C=512 (EOS disabled), beta=0.04"),
     "c2": dict(preset="2b", frames=8, res=336, G=4, text=256, C=512,
                workload="cfg2: Qwen2-VL-2B random-init, 8 frames x 336^2 (grid 4x24x24, 576 vision tokens), P=832, G=4 (+2 shuffled), C=512"),
+    "c4": dict(preset="7b", frames=32, res=448, G=8, text=256, C=512,
+               workload="cfg4: Qwen2-VL-7B random-init, 32 frames x 448^2 (grid 16x32x32, 4096 vision tokens), P=4352, G=8 (+4 shuffled), C=512 -- long-context attention / KV stress"),
+    "c5": dict(preset="7b", frames=16, res=448, G=16, text=256, C=512,
+               workload="cfg5: Qwen2-VL-7B random-init, 16 frames x 448^2, P=2304, G=16 (+8 shuffled), C=512, ref-policy KL on"),
     "tiny": dict(preset="tiny", frames=2, res=112, G=4, text=24, C=16,
                  workload="tiny: structural miniature (smoke only)"),
 }

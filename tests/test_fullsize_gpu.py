@@ -116,3 +116,61 @@ def test_loss_identities_and_backward_linearity(full):
     print("norm/bias grad linearity: cosine %.6f, norm ratio %.5f" % (vcos, vratio))
     assert vcos > 0.9999 and abs(vratio - 2.0) < 2e-3, (vcos, vratio)
     del g1, g2, grads
+
+
+def _rollout_vs_scoring(m, dims, cfg, seed, C=5):
+    """Two-group rollout exactly as the trainer issues it (G main rows + G/2 rows on the frame-shuffled video in one
+    batch), then: graph == eager, and the decode path's last-step log-prob of every main row == the scoring forward's."""
+    import bench
+    from spacer_b200.model import pack_prompt_completions
+    ex = bench.synth_example(dims, cfg, seed)
+    pix, grid, ids = ex["pixel_values_host"].cuda(), ex["video_grid_thw"], ex["input_ids"]
+    G = cfg["G"]
+    P = ids.shape[1]
+    pix2 = pix.flip(0).contiguous()
+    kw = dict(max_new_tokens=C, num_return_sequences=G, top_p=0.95, seed=11, min_new_tokens=C,
+              pixel_values_videos_2=pix2, num_return_sequences_2=G // 2)
+    a, b = m.generate(ids, pix, grid, **kw)
+    assert a.shape == (G, P + C) and b.shape == (G // 2, P + C)
+    st = m._last_decode_state
+    logits_last = st["logits"][0, :G].float().clone()
+    a2, b2 = m.generate(ids, pix, grid, use_graph=False, **kw)
+    assert torch.equal(a, a2) and torch.equal(b, b2)
+    comp = a[:, P:].cpu()
+    batch = pack_prompt_completions(ids, comp, grid, dims, m.device)
+    lp = m.per_token_logps(batch, pix, grid)
+    lp_dec = torch.log_softmax(logits_last.bfloat16().float(), -1).gather(1, a[:, -1:].to(logits_last.device))[:, 0]
+    dd = (lp[:, -1] - lp_dec).abs()
+    print("%s: P=%d rows=%d decode vs scoring |d logprob| max %.4f mean %.4f" % (cfg["workload"][:5], P, G + G // 2,
+                                                                                dd.max().item(), dd.mean().item()))
+    assert dd.max().item() < TOL_MAX and dd.mean().item() < TOL_MEAN, (dd.max().item(), dd.mean().item())
+    return batch, pix, grid, lp
+
+
+@pytest.mark.parametrize("name", ["c4", "c5"])
+def test_cfg4_cfg5_rollout_scoring_consistency(full, name):
+    """BASELINE configs[3] (32 frames, P = 4352: long prompt cache, 34 prompt splits) and configs[4] (G = 16 + 8 rows:
+    32-row decode tiles, two 64-query blocks per group in the decode attention) on the 7B dims."""
+    import bench
+    _rollout_vs_scoring(full["m"], full["dims"], bench.CONFIGS[name], seed=77)
+
+
+def test_cfg2_2b_bringup():
+    """BASELINE configs[1]: Qwen2-VL-2B dims (tied embeddings, 12 q / 2 kv heads), 8 x 336^2, G = 4: rollout <-> scoring
+    consistency plus the loss identities on one GRPO forward/backward."""
+    import bench
+    from spacer_b200 import config
+    from spacer_b200.model import GradStore, Qwen2VLB200
+    dims = config.qwen2_vl_2b()
+    m = Qwen2VLB200(dims, "cuda")
+    m.params.init_random(seed=0)
+    cfg = bench.CONFIGS["c2"]
+    batch, pix, grid, lp = _rollout_vs_scoring(m, dims, cfg, seed=5)
+    assert batch.P == 832 and pix.shape == (2304, 1176)
+    adv = torch.tensor([1.0, -1.0, 0.5, -0.5])
+    grads = GradStore(m.params)
+    out = m.grpo_forward_backward(batch, pix, grid, lp, adv, 0.04, grads)
+    assert out["mean_kl"].item() == 0.0 and abs(out["loss"].item() + adv.mean().item()) < 1e-6
+    assert torch.isfinite(grads.mat.float().sum()) and float(grads.mat.float().abs().sum()) > 0
+    del m, grads
+    torch.cuda.empty_cache()
