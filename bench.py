@@ -286,6 +286,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--moments-bf16", action="store_true")
     ap.add_argument("--no-temporal", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="gradient all-reduce after the backward instead of overlapped")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -321,7 +322,8 @@ def main():
         dist.broadcast(policy.params.vec, 0)
     RW.set_map_data(SYN_MAP)
     tcfg = GRPOConfig(num_generations=cfg["G"], max_completion_length=cfg["C"], min_new_tokens=cfg["C"],
-                      temporal=not args.no_temporal, moments_bf16=args.moments_bf16, max_steps=1000)
+                      temporal=not args.no_temporal, moments_bf16=args.moments_bf16, max_steps=1000,
+                      overlap_allreduce=not args.no_overlap)
     trainer = SGRLVRTrainerB200(policy, ref, [RW.accuracy_reward, RW.format_reward], tcfg, synth_decode)
     ex = synth_example(dims, cfg, 1234 + rank)
     ex.pop("pixel_values_host")        # (the fp32 patch matrix the HF processor would hand over; not used here)
@@ -410,6 +412,15 @@ def main():
                               "bytes_per_kernel": prof["bytes_per_launch"], "kernels": prof["launches"],
                               "note": "the 113 weight-streaming GEMVs of one step timed back to back outside the graph"}}
 
+    # data-parallel invariant: after the timed steps every rank holds the same weights (same seed, summed gradients)
+    in_sync = None
+    if world > 1:
+        chk = torch.stack([policy.params.mat.float().sum(), policy.params.mat[::4097].float().abs().sum(),
+                           policy.params.vec.float().sum()]).double()
+        allc = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        in_sync = all(torch.equal(allc[0], c) for c in allc)
+
     line = None
     if rank == 0:
         cpu_b = None
@@ -431,6 +442,7 @@ def main():
                        "decode_ms_per_token_step": stats.get("decode_ms_per_step"), "phase_ms": phase_ms},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_b,
+            "ranks_in_sync": in_sync,
             "last_step_metrics": {k: (round(v, 6) if isinstance(v, float) else v) for k, v in (mt or {}).items()},
         }
         print(json.dumps(line))

@@ -69,3 +69,67 @@ def gather_rows(t: torch.Tensor, group=None) -> torch.Tensor:
     out = [torch.empty_like(t) for _ in range(w)]
     dist.all_gather(out, t.contiguous(), group=group)
     return torch.stack(out)
+
+
+class OverlappedGradReducer:
+    """Gradient all-reduce overlapped with the backward pass ("bucketed + overlapped with backward").
+
+    The model announces `[start, end)` ranges of the flat matrix-gradient arena as soon as they are final (one decoder
+    layer = 466 MB of bf16 at 7B, in backward order: lm_head, layers L-1..0, embedding, vision tower).  Each range is
+    all-reduced (SUM) asynchronously on a side stream that first waits for the kernels that produced it; `finish()`
+    reduces whatever was not announced (and the small fp32 vector arena) and makes the compute stream wait for all of
+    it.  Every rank announces the same ranges in the same order, so the collectives line up.  On CPU tensors (gloo, the
+    unit tests) the same calls run synchronously."""
+
+    def __init__(self, mat: torch.Tensor, vec: torch.Tensor, group=None):
+        self.mat, self.vec, self.group = mat, vec, group
+        self.works, self.done = [], []
+        self.stream = torch.cuda.Stream(device=mat.device) if mat.is_cuda else None
+
+    def begin_step(self):
+        self.works, self.done = [], []
+
+    def ready(self, start: int, end: int):
+        if world_size(self.group) == 1 or end <= start:
+            return
+        self.done.append((start, end))
+        chunk = self.mat[start:end]
+        if self.stream is None:
+            dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group)
+            return
+        ev = torch.cuda.Event()
+        ev.record()                                   # everything enqueued so far on the compute stream
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ev)
+            self.works.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def missing_ranges(self):
+        """Ranges of the matrix arena nobody announced (alignment gaps are zero everywhere and need no reduction, but
+        reducing them keeps this independent of the layout)."""
+        out, pos = [], 0
+        for s0, e0 in sorted(self.done):
+            if s0 > pos:
+                out.append((pos, s0))
+            pos = max(pos, e0)
+        if pos < self.mat.numel():
+            out.append((pos, self.mat.numel()))
+        return out
+
+    def finish(self):
+        if world_size(self.group) == 1:
+            return
+        rest = [self.mat[a:b] for a, b in self.missing_ranges()] + [self.vec]
+        if self.stream is None:
+            for t in rest:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ev)
+            for t in rest:
+                self.works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        for w in self.works:
+            w.wait()                                  # the compute stream waits for the collectives
+        torch.cuda.current_stream().wait_stream(self.stream)
+        self.works = []

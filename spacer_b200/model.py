@@ -213,6 +213,28 @@ class GradStore:
         self.vec.zero_()
         self.views["embed"].zero_()
 
+    # -- gradient-ready notifications (data-parallel overlap, dist.OverlappedGradReducer) -----------------------
+    on_ready = None     # callable(start, end): elements [start, end) of the matrix arena are final for this step
+
+    def mat_range(self, prefix: str):
+        """[start, end) of the matrix-arena elements of every tensor whose name starts with `prefix`
+        (tensors of one layer are contiguous in the arena, params._layout)."""
+        lo, hi = None, None
+        for name, (arena, off, shape) in self.params.index.items():
+            if arena == "mat" and name.startswith(prefix):
+                n = 1
+                for x in shape:
+                    n *= x
+                lo = off if lo is None else min(lo, off)
+                hi = off + n if hi is None else max(hi, off + n)
+        return lo, hi
+
+    def ready(self, prefix: str):
+        if self.on_ready is not None:
+            lo, hi = self.mat_range(prefix)
+            if lo is not None:
+                self.on_ready(lo, hi)
+
 
 class Qwen2VLB200:
     def __init__(self, dims: ModelDims, device="cuda", params: ParamStore | None = None,
@@ -525,10 +547,12 @@ class Qwen2VLB200:
             dx = ops.rmsnorm_bwd(t["x"], W[p + "ln1_w"], t["s1"], d_h, G[p + "ln1_w"], dres=dx2)
             tape["layers"][i] = None
             del dx2
+            G.ready(p)
         d_vis = None
         if tape["n_vis"] > 0 and want_d_vis:
             d_vis = torch.zeros((tape["n_vis"], H), device=self.device, dtype=BF16)
         ops.call("sb_embed_bwd", tape["ids"], tape["vis_idx"], dx, G["embed"], d_vis, T, H, tape["n_vis"])
+        G.ready("embed")
         return d_vis
 
     # ---- scoring -----------------------------------------------------------------------------------
@@ -594,6 +618,8 @@ class Qwen2VLB200:
             ops.gemm(dl, hsel[r0:r1], a_mn=True, b_mn=True, out=g_lm, residual=None if (first and not d.tie) else g_lm)
             first = False
             del dl
+        if not d.tie:
+            grads.ready("lm_head")
         d_hf = torch.zeros_like(hf)
         ops.call("sb_scatter_add_rows", d_hsel, batch.rows, d_hf, R, H)
         del hsel, d_hsel, hf
@@ -601,6 +627,7 @@ class Qwen2VLB200:
         del ltape, d_hf
         if vis is not None:
             self.vit_backward(vtape, d_vis, grads)
+        grads.ready("v.")         # the whole vision tower as one bucket (1.3 GB of bf16 at 7B)
         return dict(loss=out2[0], mean_kl=out2[1], logps=lp.view(G_, C), mask=mask.view(G_, C), lengths=row_len)
 
     # ---- rollout -----------------------------------------------------------------------------------

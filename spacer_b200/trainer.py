@@ -53,6 +53,7 @@ class GRPOConfig:
     seed: int = 42
     moments_bf16: bool = False      # fp32 moments like DeepSpeed unless memory forces otherwise
     min_new_tokens: int = 0         # = max_completion_length disables EOS (timing runs)
+    overlap_allreduce: bool = True  # per-layer gradient buckets all-reduced during the backward (N > 1)
 
 
 class AdamW:
@@ -114,6 +115,10 @@ class SGRLVRTrainerB200:
         self.grads = GradStore(model.params)
         self.opt = AdamW(model.params, cfg)
         self.pg = process_group
+        # data parallel: per-layer gradient buckets are all-reduced while the backward is still running
+        self.reducer = D.OverlappedGradReducer(self.grads.mat, self.grads.vec, process_group) if cfg.overlap_allreduce else None
+        if self.reducer is not None:
+            self.grads.on_ready = self.reducer.ready
         self._metrics = defaultdict(list)
         self.global_step = 0
         self.last_rollout_stats = None
@@ -123,7 +128,10 @@ class SGRLVRTrainerB200:
         return D.world_size(self.pg)
 
     def _allreduce_grads(self):
-        D.allreduce_sum_([self.grads.mat, self.grads.vec], group=self.pg)
+        if self.reducer is not None:
+            self.reducer.finish()
+        else:
+            D.allreduce_sum_([self.grads.mat, self.grads.vec], group=self.pg)
 
     def _gather(self, t: torch.Tensor) -> torch.Tensor:
         return D.gather_rows(t, group=self.pg)
@@ -145,7 +153,9 @@ class SGRLVRTrainerB200:
         ids = example["input_ids"]
         if c.max_prompt_length is not None and ids.shape[-1] > c.max_prompt_length:
             ids = ids[..., -c.max_prompt_length:]                    # TRN:432-440
-        kw = dict(max_new_tokens=c.max_completion_length, top_p=TOP_P, seed=seed, min_new_tokens=c.min_new_tokens)
+        # Qwen2.5-VL: the rollout sees the processor's second_per_grid_ts; the scoring forwards do not (TRN:519-520)
+        kw = dict(max_new_tokens=c.max_completion_length, top_p=TOP_P, seed=seed, min_new_tokens=c.min_new_tokens,
+                  second_per_grid_ts=example.get("second_per_grid_ts"))
         if c.temporal and pix is not None:
             if frames is not None:
                 g = torch.Generator(device="cpu").manual_seed(int(seed) + 7919)
@@ -243,6 +253,8 @@ class SGRLVRTrainerB200:
         std = rewards.std()                                                         # unbiased, TRN:633
         adv = (rewards - mean) / (std + STD_EPS)                                    # TRN:638
         mark("rewards")
+        if self.reducer is not None:
+            self.reducer.begin_step()
         out = m.grpo_forward_backward(batch, pix, grid, ref_lp, adv, c.beta, self.grads)
         mark("policy_fwd_bwd")
         # data parallel: sum gradients over ranks, average inside the optimizer

@@ -78,3 +78,42 @@ def test_dp_collectives_gloo_world2(tmp_path):
         assert torch.equal(r[i]["t2"], torch.full((300,), 3.0)) and r[i]["n_works"] == 3
     # the optimizer's 1/W gradient scale turns the summed gradient into the mean over prompts (HF DDP semantics)
     assert torch.allclose(exp_mat / world, (r[0]["mine"][0] + r[1]["mine"][0]) / 2)
+
+
+def _reducer_worker(rank, world, port, out_q):
+    import torch
+    import torch.distributed as dist
+    from spacer_b200 import dist as D
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(100 + rank)
+        mat = torch.randn(1000, generator=g)
+        vec = torch.randn(37, generator=g)
+        mat0, vec0 = mat.clone(), vec.clone()
+        red = D.OverlappedGradReducer(mat, vec)
+        red.begin_step()
+        for a, b in [(900, 1000), (600, 850), (128, 600)]:      # backward order, with an unannounced gap and head
+            red.ready(a, b)
+        assert red.missing_ranges() == [(0, 128), (850, 900)]
+        red.finish()
+        full_m, full_v = mat0.clone(), vec0.clone()
+        dist.all_reduce(full_m)
+        dist.all_reduce(full_v)
+        out_q.put((rank, bool(torch.allclose(mat, full_m)) and bool(torch.allclose(vec, full_v))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_overlapped_grad_reducer_equals_full_allreduce():
+    """Announced ranges + finish() == one all-reduce of both arenas (gloo, world size 2)."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_reducer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=120) for _ in ps]
+    for p in ps:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
