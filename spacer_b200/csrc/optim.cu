@@ -16,7 +16,7 @@ template <>
 SB_DEVICE float ldg<bf16>(const bf16* p, long long i) { return __bfloat162float(p[i]); }
 
 template <typename GT>
-__global__ void __launch_bounds__(256) sumsq_kernel(const GT* __restrict__ g, long long n, float* __restrict__ out) {
+__global__ void __launch_bounds__(256) sumsq_kernel(const GT* __restrict__ g, long long n, float* __restrict__ partials) {
   __shared__ float red[32];
   float s = 0.f;
   if constexpr (sizeof(GT) == 2) {
@@ -35,8 +35,25 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const GT* __restrict__ g, lo
     }
   }
   s = block_sum(s, red);
-  if (threadIdx.x == 0) atomicAdd(out, s);
+  if (threadIdx.x == 0) partials[blockIdx.x] = s;     // no float atomics: the total must be bit-identical on every
+}                                                     // data-parallel rank (it scales the update when clipping)
+
+// total += sum of the per-block partials, in a fixed order (double accumulation)
+__global__ void __launch_bounds__(256) sumsq_final_kernel(const float* __restrict__ partials, int n, float* __restrict__ out) {
+  __shared__ double red[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) s += (double)partials[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = (float)((double)*out + red[0]);
 }
+
+constexpr int SUMSQ_GRID = 148 * 8;
+float* g_sumsq_partials[64] = {nullptr};   // per device
 
 struct AdamArgs {
   float lr, beta1, beta2, eps, wd, bc1, bc2, max_norm;
@@ -125,10 +142,16 @@ __global__ void bf16_to_f32_kernel(const bf16* __restrict__ s, float* __restrict
 
 extern "C" int sb_grad_sumsq(const void* g, long long n, int grad_is_f32, float* total_sq, sb_stream_t stream) {
   SB_REQUIRE(g && total_sq && n > 0, "sb_grad_sumsq: bad arguments");
-  const int grid = 148 * 8;
-  if (grad_is_f32) sumsq_kernel<float><<<grid, 256, 0, STREAM(stream)>>>((const float*)g, n, total_sq);
-  else sumsq_kernel<bf16><<<grid, 256, 0, STREAM(stream)>>>((const bf16*)g, n, total_sq);
-  return sb_check_launch("sb_grad_sumsq");
+  int dev = 0;
+  SB_CUDA(cudaGetDevice(&dev));
+  SB_REQUIRE(dev >= 0 && dev < 64, "sb_grad_sumsq: device ordinal %d out of range", dev);
+  if (g_sumsq_partials[dev] == nullptr) SB_CUDA(cudaMalloc(&g_sumsq_partials[dev], SUMSQ_GRID * sizeof(float)));
+  float* part = g_sumsq_partials[dev];
+  if (grad_is_f32) sumsq_kernel<float><<<SUMSQ_GRID, 256, 0, STREAM(stream)>>>((const float*)g, n, part);
+  else sumsq_kernel<bf16><<<SUMSQ_GRID, 256, 0, STREAM(stream)>>>((const bf16*)g, n, part);
+  if (sb_check_launch("sb_grad_sumsq")) return 1;
+  sumsq_final_kernel<<<1, 256, 0, STREAM(stream)>>>(part, SUMSQ_GRID, total_sq);
+  return sb_check_launch("sb_grad_sumsq(final)");
 }
 
 extern "C" int sb_adamw_step(void* param_bf16, float* master, void* m, void* v, const void* grad, long long n,
