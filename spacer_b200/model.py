@@ -248,6 +248,7 @@ class Qwen2VLB200:
         self.rope_convention = rope_convention
         self.training = False
         self._dec = None
+        self.phase_marks = None
 
     # ---- HF-like surface -------------------------------------------------------------------------
     def state_dict(self):
@@ -587,8 +588,19 @@ class Qwen2VLB200:
         G_, C = batch.G, batch.C
         R = G_ * C
         vtape, ltape = {}, {}
+        marks = self.phase_marks      # optional list: (name, CUDA event) per sub-phase (tools/profile_phases.py)
+
+        def mark(name):
+            if marks is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((name, e))
+
+        mark("start")
         vis = self.vit_forward(pixel_values, grid_thw, vtape) if pixel_values is not None else None
+        mark("vit_fwd")
         hf = self.llm_forward(batch.ids, vis, batch.pos, batch.meta, ltape)
+        mark("llm_fwd")
         hsel = torch.empty((R, H), device=self.device, dtype=BF16)
         ops.call("sb_gather_rows", hf, batch.rows, hsel, R, H)
         part, tl, nt = self._lmhead_partials(hsel, batch.targets)
@@ -605,6 +617,7 @@ class Qwen2VLB200:
         ops.call("sb_grpo_loss", part, nt, tl, batch.comp_ids, G_, C, d.eos_id, ref, adv, float(beta), lp, lse, coef,
                  mask, row_loss, row_kl, row_len, out2, ops.grpo_loss_workspace(G_, C, self.device))
         del part
+        mark("lm_head_loss")
         # backward through lm_head: recompute logits tile by tile, emit dlogits, two GEMMs
         grads.zero_for_step()
         d_hsel = torch.empty((R, H), device=self.device, dtype=BF16)
@@ -623,10 +636,13 @@ class Qwen2VLB200:
         d_hf = torch.zeros_like(hf)
         ops.call("sb_scatter_add_rows", d_hsel, batch.rows, d_hf, R, H)
         del hsel, d_hsel, hf
+        mark("lm_head_bwd")
         d_vis = self.llm_backward(ltape, d_hf, grads)
+        mark("llm_bwd")
         del ltape, d_hf
         if vis is not None:
             self.vit_backward(vtape, d_vis, grads)
+        mark("vit_bwd")
         grads.ready("v.")         # the whole vision tower as one bucket (1.3 GB of bf16 at 7B)
         return dict(loss=out2[0], mean_kl=out2[1], logps=lp.view(G_, C), mask=mask.view(G_, C), lengths=row_len)
 
@@ -902,7 +918,7 @@ class Qwen2VLB200:
     def generate(self, input_ids, pixel_values_videos=None, video_grid_thw=None, *, max_new_tokens=1024,
                  num_return_sequences=1, top_p=0.95, temperature=1.0, do_sample=True, seed=0, min_new_tokens=0,
                  pixel_values_videos_2=None, num_return_sequences_2=0, use_graph=True, attention_mask=None,
-                 return_stats=False, second_per_grid_ts=None, **unused):
+                 return_stats=False, second_per_grid_ts=None, pixel_values=None, image_grid_thw=None, **unused):
         """Sampled rollout: `num_return_sequences` completions of ONE prompt (TRN:463-467; generate() with
         do_sample, top_p, temperature 1).  Returns LongTensor [G, P + C'] (prompt echoed, finished rows padded).
 
@@ -910,6 +926,12 @@ class Qwen2VLB200:
         the same text with another video (T-GRPO's frame-shuffled rollout, TRN:442-458, 469-475); the result is
         then a tuple (ids_main, ids_second)."""
         d = self.dims
+        if pixel_values is not None:
+            # image prompt (`pixel_values` / `image_grid_thw`, the other visual input the reference's processor can
+            # produce, TRN:417-425): same tower, grids with t = 1, image placeholder tokens
+            if pixel_values_videos is not None:
+                raise SpacerError("generate: one visual input per prompt (image or video)")
+            pixel_values_videos, video_grid_thw = pixel_values, image_grid_thw
         if not do_sample or temperature <= 0.05:
             # evaluation mode (SpaceR-Eval: temperature 0.01 over the checkpoint's top_k = 1 config): greedy argmax.
             # (repetition_penalty of the released generation_config.json is not applied.)

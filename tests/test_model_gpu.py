@@ -311,3 +311,26 @@ def test_greedy_generation_for_eval():
     assert torch.equal(rows[0], rows[1]) and torch.equal(rows[0], rows[2]) and torch.equal(rows[:1], a)
     free = m.generate(prompt, pix, grid, max_new_tokens=30, num_return_sequences=1, do_sample=False)
     assert free.shape[1] <= P + 30 and torch.equal(free[:, :P].cpu(), prompt)
+
+
+def test_image_prompt_matches_oracle():
+    """`pixel_values` / `image_grid_thw` prompts (image placeholder tokens, grid t = 1): last-step decode logits vs the
+    oracle's teacher-forced forward, as for video prompts."""
+    R, d_or, d, m, w, wb = _setup()
+    g = torch.Generator().manual_seed(41)
+    grid = torch.tensor([[1, 8, 12]])
+    n_p = 96
+    pix = torch.randn(n_p, d_or.patch_dim, generator=g)
+    text = torch.randint(10, 2000, (9,), generator=g)
+    prompt = torch.cat([text[:4], torch.tensor([d_or.vision_start_id]), torch.full((n_p // 4,), d_or.image_token_id),
+                        torch.tensor([d_or.vision_end_id]), text[4:]])[None]
+    P, G, C = prompt.shape[1], 3, 5
+    out = m.generate(prompt, pixel_values=pix.cuda(), image_grid_thw=grid, max_new_tokens=C, num_return_sequences=G,
+                     top_p=0.95, seed=2, min_new_tokens=C)
+    assert out.shape == (G, P + C) and torch.equal(out[:, :P].cpu(), prompt.expand(G, -1))
+    ids = out.cpu()
+    pos = R.rope_index_classic(ids, grid.repeat(G, 1), d_or)
+    ref = R.model_logits(wb, ids, pix.bfloat16().float().repeat(G, 1), grid.repeat(G, 1), pos, d_or)
+    last = m._last_decode_state["logits"][0, :G].float().cpu()
+    err = (last - ref[:, P + C - 2]).abs().max().item()
+    assert err < 3e-2 * ref[:, P + C - 2].abs().max().item() + 5e-3, err

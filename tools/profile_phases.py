@@ -83,6 +83,31 @@ def main():
         torch.cuda.synchronize()
         prof.stop()
         return
+    if a.phase == "train_timing":
+        # sub-phase CUDA-event times of the policy forward/backward vs the host time spent enqueueing it
+        import json
+        import time
+        grads = GradStore(m.params)
+        adv = torch.linspace(-1, 1, G)
+        ref = torch.zeros(G, C) - 11.0
+        for _ in range(2):
+            m.grpo_forward_backward(batch, pix, grid, ref, adv, 0.04, grads)
+        torch.cuda.synchronize()
+        res = []
+        for _ in range(3):
+            m.phase_marks = []
+            t0 = time.perf_counter()
+            m.grpo_forward_backward(batch, pix, grid, ref, adv, 0.04, grads)
+            t_enq = (time.perf_counter() - t0) * 1e3
+            torch.cuda.synchronize()
+            t_all = (time.perf_counter() - t0) * 1e3
+            mk = m.phase_marks
+            res.append({"host_enqueue_ms": round(t_enq, 1), "host_total_ms": round(t_all, 1),
+                        **{mk[i][0] + "_ms": round(mk[i - 1][1].elapsed_time(mk[i][1]), 2) for i in range(1, len(mk))},
+                        "gpu_total_ms": round(mk[0][1].elapsed_time(mk[-1][1]), 2)})
+        m.phase_marks = None
+        print(json.dumps(res))
+        return
     raise SystemExit(f"unknown phase {a.phase}")
 
 
