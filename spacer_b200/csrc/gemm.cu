@@ -23,6 +23,9 @@
 
 namespace {
 
+#ifndef SB_GEMV_STAGES
+#define SB_GEMV_STAGES 10
+#endif
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int GEMM_THREADS = 192;
@@ -62,7 +65,10 @@ struct Cfg {
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int NSTAGES_RAW = (196 * 1024) / STAGE_BYTES;
-  static constexpr int NSTAGES = NSTAGES_RAW > 8 ? 8 : NSTAGES_RAW;
+  // the narrow decode tiles (BN <= 32) are latency-bound: throughput per CTA = bytes in flight / slot round trip
+  // (tools/labs/ingest_mma_lab.cu), so they take every stage that fits; the wide tiles are MMA-bound at 4-8 stages
+  static constexpr int NSTAGES_CAP = BN <= 32 ? SB_GEMV_STAGES : 8;
+  static constexpr int NSTAGES = NSTAGES_RAW > NSTAGES_CAP ? NSTAGES_CAP : NSTAGES_RAW;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   // gate/up exchange of the fused decode SwiGLU epilogue / rotary-partner exchange of DEC_QKV / cross-warp scratch of
   // DEC_RESID, then 32 per-row scales of the fused decode epilogues
