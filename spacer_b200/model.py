@@ -646,6 +646,65 @@ class Qwen2VLB200:
         grads.ready("v.")         # the whole vision tower as one bucket (1.3 GB of bf16 at 7B)
         return dict(loss=out2[0], mean_kl=out2[1], logps=lp.view(G_, C), mask=mask.view(G_, C), lengths=row_len)
 
+    # ---- supervised fine-tuning ---------------------------------------------
+    def sft_forward_backward(self, input_ids, labels, pixel_values, grid_thw, grads: GradStore, lm_chunk: int = 4096,
+                             second_per_grid_ts=None):
+        """Token cross-entropy of ONE causal sequence + backward, on the same kernels as the GRPO step: what trl's
+        SFTTrainer computes for the reference's SFT stage (open_r1/sft.py:147-182: labels = input_ids with pad and
+        visual tokens set to -100; HF causal-LM loss: predict token t+1 from position t, mean over labels != -100).
+        input_ids / labels: [L] (or [1, L]).  Returns dict(loss, n_tokens); gradients land in `grads`."""
+        d = self.dims
+        H = d.hidden
+        ids = input_ids.reshape(-1).cpu().long()
+        lab = labels.reshape(-1).cpu().long()
+        L = ids.numel()
+        if lab.numel() != L:
+            raise SpacerError("sft_forward_backward: labels and input_ids differ in length")
+        keep = torch.nonzero(lab[1:] != -100, as_tuple=True)[0]          # position t predicts label t + 1
+        R = int(keep.numel())
+        if R == 0:
+            raise SpacerError("sft_forward_backward: every label is masked")
+        rows = keep.to(I32).to(self.device)
+        targets = lab[1:][keep].to(I32).to(self.device)
+        pos, _ = rope_index(ids, grid_thw, d, self.rope_convention, second_per_grid_ts)
+        ids_dev = ids.to(I32).to(self.device)
+        pos_dev = pos.to(I32).contiguous().to(self.device)
+        meta = causal_meta(L, self.device)
+        vtape, ltape = {}, {}
+        vis = self.vit_forward(pixel_values, grid_thw, vtape) if pixel_values is not None else None
+        hf = self.llm_forward(ids_dev, vis, pos_dev, meta, ltape)
+        hsel = torch.empty((R, H), device=self.device, dtype=BF16)
+        ops.call("sb_gather_rows", hf, rows, hsel, R, H)
+        part, tl, nt = self._lmhead_partials(hsel, targets)
+        lp = torch.empty(R, device=self.device, dtype=F32)
+        ops.call("sb_logprob_from_partials", part, nt, tl, lp, R)
+        del part
+        loss = -lp.mean()
+        lse = tl - lp                                                     # log-sum-exp of the bf16-rounded logits
+        coef = torch.full((R,), -1.0 / R, device=self.device, dtype=F32)  # dLoss / dlogprob
+        grads.zero_for_step()
+        d_hsel = torch.empty((R, H), device=self.device, dtype=BF16)
+        g_lm = grads["lm_head"]
+        first = True
+        for r0 in range(0, R, lm_chunk):
+            r1 = min(r0 + lm_chunk, R)
+            dl = ops.gemm(hsel[r0:r1], self.params["lm_head"], epilogue=EPI_DLOGITS, targets=targets[r0:r1],
+                          lse=lse[r0:r1], coef=coef[r0:r1])
+            ops.gemm(dl, self.params["lm_head"], b_mn=True, out=d_hsel[r0:r1])
+            ops.gemm(dl, hsel[r0:r1], a_mn=True, b_mn=True, out=g_lm, residual=None if (first and not d.tie) else g_lm)
+            first = False
+            del dl
+        if not d.tie:
+            grads.ready("lm_head")
+        d_hf = torch.zeros_like(hf)
+        ops.call("sb_scatter_add_rows", d_hsel, rows, d_hf, R, H)
+        del hsel, d_hsel, hf
+        d_vis = self.llm_backward(ltape, d_hf, grads)
+        if vis is not None:
+            self.vit_backward(vtape, d_vis, grads)
+        grads.ready("v.")
+        return dict(loss=loss, n_tokens=R, logps=lp)
+
     # ---- rollout -----------------------------------------------------------------------------------
     def decode_weight_bytes(self) -> int:
         """bf16 bytes of the weights one decode step must stream: 28 x (qkv, o, gate|up, down) + lm_head."""

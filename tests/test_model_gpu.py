@@ -334,3 +334,37 @@ def test_image_prompt_matches_oracle():
     last = m._last_decode_state["logits"][0, :G].float().cpu()
     err = (last - ref[:, P + C - 2]).abs().max().item()
     assert err < 3e-2 * ref[:, P + C - 2].abs().max().item() + 5e-3, err
+
+
+def test_sft_loss_and_gradients_vs_oracle():
+    """SFT stage reuse (open_r1/sft.py:147-182): token cross-entropy with pad / visual labels masked
+    (-100), HF causal-LM shift, vs torch.nn.functional.cross_entropy on the oracle's logits; every gradient by cosine."""
+    from spacer_b200.model import GradStore
+    R, d_or, d, m, w, wb = _setup()
+    case = _case(d_or)
+    grid, pix = case["grid_thw"], case["pixel_values"]
+    ids = case["input_ids"][0]                                  # one full sequence: prompt + completion
+    ids = torch.cat([ids, torch.full((3,), d_or.pad_id)])       # padded tail, as the processor would produce
+    labels = ids.clone()
+    labels[labels == d_or.pad_id] = -100
+    for vt in (d_or.vision_start_id, d_or.vision_end_id, d_or.video_token_id):
+        labels[labels == vt] = -100
+    wg = {k: v.clone().requires_grad_() for k, v in wb.items()}
+    pos = R.rope_index_classic(ids[None], grid, d_or)
+    logits = R.model_logits(wg, ids[None], pix.bfloat16().float(), grid, pos, d_or)[0]
+    loss_ref = torch.nn.functional.cross_entropy(logits[:-1], labels[1:], ignore_index=-100)
+    loss_ref.backward()
+    grads = GradStore(m.params)
+    out = m.sft_forward_backward(ids, labels, pix.cuda(), grid, grads)
+    assert out["n_tokens"] == int((labels[1:] != -100).sum())
+    assert abs(float(out["loss"]) - float(loss_ref)) < 2e-2, (float(out["loss"]), float(loss_ref))
+    got = dict(m.params.hf_items({n: grads[n] for n in m.params.index}))
+    for k, t in wg.items():
+        gref = t.grad
+        if gref is None or gref.norm() < 1e-9:
+            continue
+        g = got[k].float().cpu().reshape(gref.shape)
+        cos = torch.nn.functional.cosine_similarity(g.flatten(), gref.flatten(), dim=0).item()
+        rel = (g.norm() / gref.norm()).item()
+        assert cos > 0.99, f"{k}: cosine {cos:.5f}"
+        assert 0.9 < rel < 1.1, f"{k}: norm ratio {rel:.3f}"
