@@ -23,6 +23,12 @@
 
 namespace {
 
+// 1 = decode GEMVs with the activations as the A operand (M = 64) instead of swap-AB.  Parity-tested; measured in the
+// decode graph: split-K GEMVs unchanged (qkv 5.3, o 4.9, down 19.8 us), fused-SwiGLU gate|up 50 us instead of 41 us
+// (one epilogue warp owns all 16 rows), step 3.46 vs 3.16 ms -- off.  profiles/r01_ingest_labs.md
+#ifndef SB_GEMV_ACT_A
+#define SB_GEMV_ACT_A 0
+#endif
 #ifndef SB_GEMV_STAGES
 #define SB_GEMV_STAGES 10
 #endif
@@ -184,6 +190,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   constexpr int NSTAGES = C::NSTAGES;
   // the swap-AB weight-streaming GEMVs of the decode step (PDL launch, early weight ring, L2 prefetch of the next matrix)
   constexpr bool kDec = EPI == SB_EPI_F32T || EPI == SB_EPI_F32T_SWIGLU || EPI == SB_EPI_DEC_QKV || EPI == SB_EPI_DEC_RESID;
+  // kActA: the <= 16 decode rows are the A operand (M = 64, rows 16.. are whatever follows in shared memory and produce
+  // ignored accumulator rows) and the 128-row weight tile is the B operand (N = 128).  Same TMA boxes and smem layout as
+  // the swap-AB form, but the slot round trip (TMA -> MMA -> commit -> refill) is shorter: 6.70 vs 5.89 TB/s at 148
+  // CTAs (tools/labs/ingest_mma_lab.cu, profiles/r01_ingest_labs.md), and each epilogue thread owns one decode row.
+  constexpr bool kActA = (EPI == SB_EPI_F32T || EPI == SB_EPI_F32T_SWIGLU) && BN == 16 && SB_GEMV_ACT_A;
+  constexpr int ACC_COLS = kActA ? BM : BN;                 // TMEM columns of one accumulator
+  constexpr int TMEM_COLS = kActA ? 2 * BM : C::TMEM_COLS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -221,7 +234,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if constexpr (kClu) mbar_init(redbar, csize > 1 ? csize - 1 : 1);
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), C::TMEM_COLS);
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -314,7 +327,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ------------------------------ MMA issuer ------------------------------
     pdl_wait();
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+      constexpr uint32_t idesc = kActA ? umma_idesc_bf16(64, BM, false, false) : umma_idesc_bf16(BM, BN, A_MN, B_MN);
       // per-UMMA_K(16) start-address advance inside a stage, in 16-byte units
       constexpr uint32_t a_adv = A_MN ? (2048 >> 4) : (32 >> 4);
       constexpr uint32_t b_adv = B_MN ? (2048 >> 4) : (32 >> 4);
@@ -328,7 +341,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int kb1 = min(kb0 + p.k_iters_per_split, p.k_iters);
         mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full0 + 8 * stage, phase);
           tc_fence_after();
@@ -338,8 +351,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const uint64_t bdesc = umma_desc_sw128(sb, B_MN ? 8192 : 0, 1024);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * a_adv), bdesc + (uint64_t)(k * b_adv), idesc,
-                        (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (kActA)   // D[decode row][weight row] = X * W^T
+              tc_mma_bf16(d_tmem, bdesc + (uint64_t)(k * b_adv), adesc + (uint64_t)(k * a_adv), idesc,
+                          (kb > kb0 || k > 0) ? 1u : 0u);
+            else
+              tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * a_adv), bdesc + (uint64_t)(k * b_adv), idesc,
+                          (kb > kb0 || k > 0) ? 1u : 0u);
           }
           tc_commit(empty0 + 8 * stage);  // frees the smem slot when these MMAs retire
           if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
@@ -375,12 +392,60 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int ks = t / (p.m_tiles * p.n_tiles);
       mbar_wait(tfull0 + 8 * acc, acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS;
       const int row = mt * BM + row_in_tile;
       const bool row_ok = row < p.M;
       const int col_base = nt * BN;
 
-      if constexpr (EPI == SB_EPI_F32T) {
+      if constexpr (kActA && EPI == SB_EPI_F32T) {
+        // accumulator lane = decode row, column = weight row of the tile: only the warp that owns TMEM lanes 0..31 works;
+        // out[ks][decode row][weight row] fp32, 128 consecutive floats per thread
+        if (q == 0) {
+          float* out = reinterpret_cast<float*>(p.D);
+          const float sc = (scaled && lane < BN) ? sscale[lane] : 1.f;
+#pragma unroll 1
+          for (int c = 0; c < BM / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + c * 32, r);
+            tmem_ld_wait();
+            const int n0 = mt * BM + c * 32;
+            if (lane < p.N && lane < BN) {
+              float* o = out + ((long long)ks * p.N + lane) * p.ldd + n0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                if (n0 + j < p.M)
+                  *reinterpret_cast<float4*>(o + j) = make_float4(__uint_as_float(r[j]) * sc, __uint_as_float(r[j + 1]) * sc,
+                                                                  __uint_as_float(r[j + 2]) * sc, __uint_as_float(r[j + 3]) * sc);
+              }
+            }
+          }
+        }
+      } else if constexpr (kActA && EPI == SB_EPI_F32T_SWIGLU) {
+        // tile columns [0, 64) = gate, [64, 128) = up of activation columns [64 mt, 64 mt + 64): SwiGLU is thread-local
+        if (q == 0) {
+          bf16* Dp = reinterpret_cast<bf16*>(p.D);
+          const float sc = (scaled && lane < BN) ? sscale[lane] : 1.f;
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t rg[32], ru[32];
+            tmem_ld_32x32(taddr + c * 32, rg);
+            tmem_ld_32x32(taddr + 64 + c * 32, ru);
+            tmem_ld_wait();
+            if (lane < p.N && lane < BN) {
+              float o[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float g = bf16_round(__uint_as_float(rg[j]) * sc);
+                const float u = bf16_round(__uint_as_float(ru[j]) * sc);
+                o[j] = bf16_round(silu(g)) * u;
+              }
+              bf16* dr = Dp + (long long)lane * p.ldd + mt * 64 + c * 32;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) st8(dr + j, o + j);
+            }
+          }
+        }
+      } else if constexpr (EPI == SB_EPI_F32T) {
         // split-K / swap-AB partial: out[ks][col][row] fp32 (row = weight row, col = decode row)
         static_assert(BN == 16 || BN == 32, "F32T epilogue is for the narrow decode tiles");
         uint32_t r[BN];
@@ -625,7 +690,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if constexpr (kDec) {
     if (blockIdx.x == 0 && threadIdx.x == 0) sb_trace_mark(*reinterpret_cast<volatile int*>(tmem_slot + 1), 2);
   }
-  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------
