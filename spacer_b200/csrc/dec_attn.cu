@@ -69,7 +69,13 @@ Plan make_plan(int R, int rows_group0, int P, int c_max, int nh, int nkv, int sm
   pl.p_chunk = chunk;
   pl.n_psplit = P > 0 ? (P + chunk - 1) / chunk : 0;
   int cs = (c_max + 127) / 128;
-  pl.n_csplit = cs < 1 ? 1 : (cs > 8 ? 8 : cs);
+  cs = cs < 1 ? 1 : (cs > 8 ? 8 : cs);
+  // two CTAs fit per SM (87 KB of shared memory each): keep the whole launch in ONE wave when possible -- a 40-CTA
+  // second wave showed up as a 3 us gap before the combine kernel (profiles/r01_decode_trace_unfused.txt)
+  const int room = 2 * sms - base * (P > 0 ? (P + chunk - 1) / chunk : 0);
+  const int per_split = R * nkv;
+  if (per_split > 0 && room >= per_split && cs > room / per_split) cs = room / per_split;
+  pl.n_csplit = cs;
   pl.NS = pl.n_psplit + pl.n_csplit;
   pl.n_prefix_items = base * pl.n_psplit;
   pl.n_items = pl.n_prefix_items + R * nkv * pl.n_csplit;
