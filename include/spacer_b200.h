@@ -167,6 +167,16 @@ int sb_f32_to_bf16_2d(const float* src, void* dst, int T, int W, long long ldd, 
  * at MQ2:306.  mean_host/std_host: C floats on the HOST, already divided by the rescale factor (mean*255, std*255).
  * out_f32 is bit-exact with the HF CPU path; out_bf16 is what sb_gemm consumes.  Either output may be NULL.
  * ------------------------------------------------------------------------------------------------ */
+/* Bicubic antialiased resize of `planes` = F*C images [H][W] -> [OH][OW]: the arithmetic of
+ * torchvision.transforms.functional.resize(uint8 video, [OH, OW], BICUBIC, antialias=True) in qwen-vl-utils' fetch_video
+ * (vision_process.py:310-315; float32 separable passes, horizontal first, then round-half-even + clamp to [0, 255]).
+ * wh/xmin_h/xsize_h: per output column the normalised weights [OW][taps_h], first source column and tap count (device
+ * tables, built by spacer_b200/vision.py:aa_weight_table with ATen's formula); wv/...: the same per output row.
+ * tmp: fp32 scratch [planes][H][OW].  dst float32 (what fetch_video returns after .float()) or uint8. */
+int sb_resize_bicubic_aa(const void* src, int src_is_u8, int planes, int H, int W, float* tmp, void* dst, int dst_is_u8,
+                         int OH, int OW, const float* wh, const int* xmin_h, const int* xsize_h, int taps_h,
+                         const float* wv, const int* xmin_v, const int* xsize_v, int taps_v, int round_u8, int use_fma,
+                         sb_stream_t stream);
 int sb_video_patchify(const void* frames, int frames_are_u8, int F, int C, int H, int W, const int* perm,
                       const float* mean_host, const float* std_host, int patch, int t_patch, int merge, float* out_f32,
                       void* out_bf16, sb_stream_t stream);

@@ -56,7 +56,91 @@ __global__ void __launch_bounds__(256) patchify_kernel(const PatchifyParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Bicubic antialiased resize (separable, horizontal pass then vertical pass with an fp32 intermediate), the arithmetic of
+// torchvision.transforms.functional.resize(video_uint8, [h, w], BICUBIC, antialias=True) as qwen-vl-utils calls it
+// (vision_process.py:310-315): torchvision converts the uint8 tensor to float32, runs ATen's _upsample_bicubic2d_aa
+// (per output index a window [xmin, xmin + xsize) and normalised cubic weights, a = -0.5, support 2 * max(scale, 1)),
+// then rounds (half to even) and clamps to [0, 255].  The per-index windows and weights are computed on the host
+// (vision.py:aa_weight_table, fp32 like ATen) and passed in as tables.
+// ------------------------------------------------------------------------------------------------------------------
+struct ResizeParams {
+  const void* src; int src_is_u8;
+  float* tmp;                 // [planes][H][OW]
+  void* dst; int dst_is_u8;   // [planes][OH][OW]
+  int planes, H, W, OH, OW;
+  const float* wh; const int* xmin_h; const int* xsize_h; int taps_h;   // [OW][taps_h]
+  const float* wv; const int* xmin_v; const int* xsize_v; int taps_v;   // [OH][taps_v]
+  int round_u8, use_fma;
+};
+
+SB_DEVICE float acc_step(float t, float v, float w, int use_fma) {
+  return use_fma ? __fmaf_rn(v, w, t) : __fadd_rn(t, __fmul_rn(v, w));
+}
+
+__global__ void __launch_bounds__(256) resize_h_kernel(const ResizeParams p) {
+  const long long total = (long long)p.planes * p.H * p.OW;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(idx % p.OW);
+    const long long row = idx / p.OW;                     // plane * H + y
+    const int x0 = p.xmin_h[ox], n = p.xsize_h[ox];
+    const float* w = p.wh + (long long)ox * p.taps_h;
+    const long long base = row * p.W + x0;
+    float t = 0.f;
+    if (p.src_is_u8) {
+      const uint8_t* s = reinterpret_cast<const uint8_t*>(p.src) + base;
+      t = __fmul_rn((float)s[0], w[0]);
+      for (int j = 1; j < n; ++j) t = acc_step(t, (float)s[j], w[j], p.use_fma);
+    } else {
+      const float* s = reinterpret_cast<const float*>(p.src) + base;
+      t = __fmul_rn(s[0], w[0]);
+      for (int j = 1; j < n; ++j) t = acc_step(t, s[j], w[j], p.use_fma);
+    }
+    p.tmp[idx] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) resize_v_kernel(const ResizeParams p) {
+  const long long total = (long long)p.planes * p.OH * p.OW;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(idx % p.OW);
+    const int oy = (int)((idx / p.OW) % p.OH);
+    const long long plane = idx / ((long long)p.OW * p.OH);
+    const int y0 = p.xmin_v[oy], n = p.xsize_v[oy];
+    const float* w = p.wv + (long long)oy * p.taps_v;
+    const float* s = p.tmp + (plane * p.H + y0) * p.OW + ox;
+    float t = __fmul_rn(s[0], w[0]);
+    for (int j = 1; j < n; ++j) t = acc_step(t, s[(long long)j * p.OW], w[j], p.use_fma);
+    if (p.round_u8) t = fminf(fmaxf(rintf(t), 0.f), 255.f);
+    if (p.dst_is_u8) reinterpret_cast<uint8_t*>(p.dst)[idx] = (uint8_t)t;
+    else reinterpret_cast<float*>(p.dst)[idx] = t;
+  }
+}
+
 }  // namespace
+
+extern "C" int sb_resize_bicubic_aa(const void* src, int src_is_u8, int planes, int H, int W, float* tmp, void* dst,
+                                    int dst_is_u8, int OH, int OW, const float* wh, const int* xmin_h,
+                                    const int* xsize_h, int taps_h, const float* wv, const int* xmin_v,
+                                    const int* xsize_v, int taps_v, int round_u8, int use_fma, sb_stream_t stream) {
+  SB_REQUIRE(src && tmp && dst && wh && xmin_h && xsize_h && wv && xmin_v && xsize_v, "sb_resize_bicubic_aa: null pointer");
+  SB_REQUIRE(planes > 0 && H > 0 && W > 0 && OH > 0 && OW > 0 && taps_h > 0 && taps_v > 0, "sb_resize_bicubic_aa: bad sizes");
+  SB_REQUIRE(!dst_is_u8 || round_u8, "sb_resize_bicubic_aa: a uint8 destination needs round_u8");
+  ResizeParams p;
+  p.src = src; p.src_is_u8 = src_is_u8; p.tmp = tmp; p.dst = dst; p.dst_is_u8 = dst_is_u8;
+  p.planes = planes; p.H = H; p.W = W; p.OH = OH; p.OW = OW;
+  p.wh = wh; p.xmin_h = xmin_h; p.xsize_h = xsize_h; p.taps_h = taps_h;
+  p.wv = wv; p.xmin_v = xmin_v; p.xsize_v = xsize_v; p.taps_v = taps_v;
+  p.round_u8 = round_u8; p.use_fma = use_fma;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  auto blocks = [](long long total) { long long b = (total + 255) / 256; return (unsigned)(b > 148 * 32 ? 148 * 32 : b); };
+  resize_h_kernel<<<blocks((long long)planes * H * OW), 256, 0, st>>>(p);
+  if (sb_check_launch("sb_resize_bicubic_aa(h)")) return 1;
+  resize_v_kernel<<<blocks((long long)planes * OH * OW), 256, 0, st>>>(p);
+  return sb_check_launch("sb_resize_bicubic_aa(v)");
+}
 
 extern "C" int sb_video_patchify(const void* frames, int frames_are_u8, int F, int C, int H, int W, const int* perm,
                                  const float* mean_host, const float* std_host, int patch, int t_patch, int merge,

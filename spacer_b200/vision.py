@@ -8,8 +8,8 @@ Host side (pure Python integers, checked against the reference's own functions v
     frame_indices     QVU:246       torch.linspace(0, total - 1, nframes).round().long()
 Device side:
     patchify(frames[, perm])  ->  pixel_values_videos (bf16 for the ViT and/or fp32 bit-exact with HF), video_grid_thw
-Video decoding (decord) and the bicubic-antialias resize (QVU:310-315) are not part of this module: frames arrive
-decoded and resized, as uint8 or float TCHW.
+    resize_frames(frames, h, w)  ->  the bicubic-antialias resize of fetch_video (QVU:310-315) on the GPU
+Video decoding (decord) is not part of this module: frames arrive decoded, as uint8 or float TCHW.
 """
 from __future__ import annotations
 
@@ -114,3 +114,71 @@ def patchify(frames: torch.Tensor, perm: torch.Tensor | None = None, *, patch=14
     ops.call("sb_video_patchify", frames, int(frames.dtype == torch.uint8), F_, Cc, H, W, perm,
              C.cast(mh, C.c_void_p), C.cast(sh, C.c_void_p), patch, t_patch, merge, o32, o16)
     return o16, o32, torch.tensor([[gt, gh, gw]])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# bicubic antialiased resize (QVU:310-315 -> torchvision resize -> ATen _upsample_bicubic2d_aa)
+# ------------------------------------------------------------------------------------------------------------------
+_AA_CACHE: dict = {}
+
+
+def aa_weight_table(in_size: int, out_size: int):
+    """Per output index: first source index, tap count and normalised cubic weights (a = -0.5), computed like ATen's
+    HelperInterpBase::_compute_indices_min_size_weights_aa for float32 tensors: scale, support, centre and the weights
+    in fp32, the filter argument in double.  Returns (weights float32 [out, taps], xmin int32 [out], xsize int32 [out])."""
+    import numpy as np
+    f32 = np.float32
+    scale = f32(in_size) / f32(out_size)
+    support = f32(2.0) * scale if scale >= 1.0 else f32(2.0)
+    invscale = f32(1.0) / scale if scale >= 1.0 else f32(1.0)
+    taps = int(math.ceil(float(support))) * 2 + 1
+    w = np.zeros((out_size, taps), dtype=np.float32)
+    xmin = np.zeros(out_size, dtype=np.int32)
+    xsize = np.zeros(out_size, dtype=np.int32)
+    a = f32(-0.5)
+
+    def filt(x):
+        x = f32(abs(x))
+        if x < 1.0:
+            return ((a + f32(2.0)) * x - (a + f32(3.0))) * x * x + f32(1.0)
+        if x < 2.0:
+            return (((x - f32(5.0)) * x + f32(8.0)) * x - f32(4.0)) * a
+        return f32(0.0)
+
+    for i in range(out_size):
+        center = scale * f32(i + 0.5)
+        lo = max(int(center - support + f32(0.5)), 0)
+        n = min(int(center + support + f32(0.5)), in_size) - lo
+        total = f32(0.0)
+        for j in range(n):
+            arg = (float(f32(j + lo) - center) + 0.5) * float(invscale)       # promoted to double by the 0.5 literal
+            w[i, j] = filt(f32(arg))
+            total = f32(total + w[i, j])
+        if total != 0.0:
+            w[i, :n] = w[i, :n] / total
+        xmin[i], xsize[i] = lo, n
+    return w, xmin, xsize
+
+
+def resize_frames(frames: torch.Tensor, height: int, width: int, *, out_u8: bool = False, use_fma: bool = True):
+    """frames: CUDA uint8 or float32 [F, C, H, W] -> [F, C, height, width], float32 holding integers in 0..255 (what
+    fetch_video returns) or uint8.  Bicubic, antialias, round-half-even + clamp as torchvision does for uint8 input."""
+    if not frames.is_cuda or frames.dtype not in (torch.uint8, torch.float32) or frames.dim() != 4:
+        raise SpacerError("resize_frames: frames must be a CUDA uint8/float32 tensor [F, C, H, W]")
+    frames = frames.contiguous()
+    F_, Cc, H, W = frames.shape
+    dev = frames.device
+    tabs = []
+    for in_size, out_size in ((W, width), (H, height)):
+        key = (in_size, out_size, str(dev))
+        if key not in _AA_CACHE:
+            w, lo, n = aa_weight_table(in_size, out_size)
+            _AA_CACHE[key] = (torch.from_numpy(w).to(dev), torch.from_numpy(lo).to(dev), torch.from_numpy(n).to(dev), w.shape[1])
+        tabs.append(_AA_CACHE[key])
+    (wh, xh, nh, th), (wv, xv, nv, tv) = tabs
+    tmp = torch.empty((F_ * Cc, H, width), device=dev, dtype=torch.float32)
+    out = torch.empty((F_, Cc, height, width), device=dev, dtype=torch.uint8 if out_u8 else torch.float32)
+    round_u8 = int(frames.dtype == torch.uint8 or out_u8)
+    ops.call("sb_resize_bicubic_aa", frames, int(frames.dtype == torch.uint8), F_ * Cc, H, W, tmp, out, int(out_u8), height,
+             width, wh, xh, nh, th, wv, xv, nv, tv, round_u8, int(use_fma))
+    return out

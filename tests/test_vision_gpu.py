@@ -40,3 +40,33 @@ def test_patchify_frame_permutation_and_full_size():
     assert torch.equal(p32.cpu(), ref_p) and torch.equal(p16.cpu(), ref_p.bfloat16())
     with pytest.raises(SpacerError):
         V.patchify(torch.zeros(2, 3, 30, 56, dtype=torch.uint8, device="cuda"))   # not a multiple of 28: resize first
+
+
+@pytest.mark.parametrize("H,W,oh,ow", [(180, 320, 252, 448), (90, 160, 56, 84), (37, 53, 56, 84), (448, 448, 448, 448),
+                                       (240, 426, 252, 448)])
+def test_resize_frames_matches_torchvision(H, W, oh, ow):
+    """the resize of qwen-vl-utils' fetch_video (vision_process.py:310-315),
+    torchvision.transforms.functional.resize(uint8 video, BICUBIC, antialias=True).float(), on the GPU.  fp32 summation
+    order differs from ATen's vectorised CPU loop, so a pixel whose exact value sits within ~1e-4 of .5 may round the
+    other way: at most one grey level, in < 0.1 % of the pixels."""
+    import torchvision.transforms.functional as TF
+    from torchvision.transforms import InterpolationMode
+    from spacer_b200 import vision
+    g = torch.Generator().manual_seed(H * 1000 + W)
+    x = torch.randint(0, 256, (4, 3, H, W), generator=g, dtype=torch.uint8)
+    ref = TF.resize(x, [oh, ow], interpolation=InterpolationMode.BICUBIC, antialias=True).float()
+    best = None
+    for fma in (True, False):
+        out = vision.resize_frames(x.cuda(), oh, ow, use_fma=fma).cpu()
+        assert out.shape == ref.shape and out.dtype == torch.float32
+        d = (out - ref).abs()
+        assert d.max().item() <= 1.0, d.max().item()
+        frac = (d > 0).float().mean().item()
+        assert frac < 1e-3, (fma, frac)
+        best = frac if best is None else min(best, frac)
+    u8 = vision.resize_frames(x.cuda(), oh, ow, out_u8=True).cpu()
+    assert u8.dtype == torch.uint8 and (u8.float() - ref).abs().max().item() <= 1.0
+    # front-end chain: resize -> patchify consumes the float frames directly
+    if oh % 28 == 0 and ow % 28 == 0:
+        pv, _, grid = vision.patchify(vision.resize_frames(x.cuda(), oh, ow))
+        assert grid.tolist() == [[2, oh // 14, ow // 14]] and pv.shape == (2 * (oh // 14) * (ow // 14), 1176)
