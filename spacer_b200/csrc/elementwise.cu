@@ -101,12 +101,14 @@ norm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const bf
 
 // backward: dx = [dres +] rstd * (g - mean(g) - xhat * mean(g*xhat))   (LayerNorm; g = dy*w)
 //           dx = [dres +] rstd * (g - xhat * mean(g*xhat))             (RMSNorm)
-// dw/db accumulate in fp32 via per-CTA partial sums over a row group + atomics.
+// dw/db: every CTA writes the partial sums of its row group to a scratch row; reduce_partials_kernel then adds them to
+// dw/db in CTA order (deterministic; the remaining atomics of the backward are the bf16 adds of duplicate rows in
+// embed_bwd / scatter_add_rows).
 template <bool RMS>
 __global__ void __launch_bounds__(NORM_THREADS)
 norm_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const float* __restrict__ mean_in,
                 const float* __restrict__ rstd_in, const bf16* __restrict__ dy, const bf16* __restrict__ dres,
-                bf16* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db, int T, int E,
+                bf16* __restrict__ dx, float* __restrict__ part_w, float* __restrict__ part_b, int T, int E,
                 int rows_per_cta) {
   extern __shared__ float sm[];
   float* red = sm;            // 32
@@ -166,9 +168,30 @@ norm_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const fl
   }
   __syncthreads();
   for (int i = threadIdx.x; i < E; i += NORM_THREADS) {
-    atomicAdd(dw + i, dw_acc[i]);
-    if (!RMS) atomicAdd(db + i, db_acc[i]);
+    part_w[(long long)blockIdx.x * E + i] = dw_acc[i];
+    if (!RMS) part_b[(long long)blockIdx.x * E + i] = db_acc[i];
   }
+}
+
+// out[i] += sum_p part[p * stride + i], p ascending: the deterministic second stage of the column reductions
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ part, int n_parts, long long stride, float* __restrict__ out, int N) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= N) return;
+  float s = 0.f;
+  for (int p = 0; p < n_parts; ++p) s += part[p * stride + i];
+  out[i] += s;
+}
+
+// per-device scratch for the partial rows (norm backward: up to 296 CTAs x 2 x 12000 floats; colsum: 1 M floats)
+constexpr size_t COL_SCRATCH_FLOATS = (size_t)296 * 2 * 12000 + (1u << 20);
+float* g_col_scratch[64] = {nullptr};
+static float* col_scratch() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (g_col_scratch[dev] == nullptr && cudaMalloc(&g_col_scratch[dev], COL_SCRATCH_FLOATS * sizeof(float)) != cudaSuccess)
+    g_col_scratch[dev] = nullptr;
+  return g_col_scratch[dev];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -470,7 +493,7 @@ __global__ void scatter_add_rows_kernel(const bf16* __restrict__ src, const int*
 // column sums (bias gradients): out_f32[n] += sum_t dy[t][n]
 // grid (ceil(N/64), row_groups); 256 threads = 8 column-octets x 32 row lanes
 // ------------------------------------------------------------------------------------------
-__global__ void colsum_kernel(const bf16* __restrict__ dy, float* __restrict__ out, int T, int N, long long ld,
+__global__ void colsum_kernel(const bf16* __restrict__ dy, float* __restrict__ part, int T, int N, long long ld,
                               int rows_per_cta) {
   __shared__ float acc[32][65];
   const int c8 = threadIdx.x & 7;        // which 8-column group of this 64-column slab
@@ -494,7 +517,7 @@ __global__ void colsum_kernel(const bf16* __restrict__ dy, float* __restrict__ o
     float t = 0.f;
     for (int r = 0; r < 32; ++r) t += acc[r][threadIdx.x];
     const int cc = blockIdx.x * 64 + threadIdx.x;
-    if (cc < N) atomicAdd(out + cc, t);
+    if (cc < N) part[(long long)blockIdx.y * N + cc] = t;    // row-group partial; reduce_partials_kernel sums them in order
   }
 }
 
@@ -540,20 +563,28 @@ static int norm_bwd_launch(bool rms, const void* x, const void* w, const float* 
   const int rows_per = (T + ctas - 1) / ctas;
   const int grid = (T + rows_per - 1) / rows_per;
   const size_t smem = (32 + 2 * (size_t)E) * sizeof(float);
+  float* scratch = col_scratch();
+  SB_REQUIRE(scratch != nullptr, "sb_norm_bwd: could not allocate the reduction scratch");
+  SB_REQUIRE((size_t)grid * 2 * E <= COL_SCRATCH_FLOATS, "sb_norm_bwd: reduction scratch too small for %d x %d", grid, E);
+  float* part_w = scratch;
+  float* part_b = scratch + (size_t)grid * E;
   if (rms) {
     static bool done = false;
     if (!done) { SB_CUDA(cudaFuncSetAttribute(norm_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); done = true; }
     norm_bwd_kernel<true><<<grid, NORM_THREADS, smem, st>>>((const bf16*)x, (const bf16*)w, nullptr, rstd,
-                                                            (const bf16*)dy, (const bf16*)dres, (bf16*)dx, dw, nullptr,
+                                                            (const bf16*)dy, (const bf16*)dres, (bf16*)dx, part_w, nullptr,
                                                             T, E, rows_per);
   } else {
     static bool done = false;
     if (!done) { SB_CUDA(cudaFuncSetAttribute(norm_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); done = true; }
     norm_bwd_kernel<false><<<grid, NORM_THREADS, smem, st>>>((const bf16*)x, (const bf16*)w, mean, rstd,
-                                                             (const bf16*)dy, (const bf16*)dres, (bf16*)dx, dw, db, T,
-                                                             E, rows_per);
+                                                             (const bf16*)dy, (const bf16*)dres, (bf16*)dx, part_w, part_b,
+                                                             T, E, rows_per);
   }
-  return sb_check_launch("sb_norm_bwd");
+  if (sb_check_launch("sb_norm_bwd")) return 1;
+  reduce_partials_kernel<<<(E + 255) / 256, 256, 0, st>>>(part_w, grid, E, dw, E);
+  if (!rms) reduce_partials_kernel<<<(E + 255) / 256, 256, 0, st>>>(part_b, grid, E, db, E);
+  return sb_check_launch("sb_norm_bwd(reduce)");
 }
 
 extern "C" int sb_layernorm_bwd(const void* x, const void* w, const float* mean, const float* rstd, const void* dy,
@@ -664,6 +695,11 @@ extern "C" int sb_colsum(const void* dy, float* out, int T, int N, long long ld,
   if (gy < 1) gy = 1;
   const int rows_per = (T + gy - 1) / gy;
   gy = (T + rows_per - 1) / rows_per;
-  colsum_kernel<<<dim3(gx, gy), 256, 0, STREAM(stream)>>>((const bf16*)dy, out, T, N, ld, rows_per);
-  return sb_check_launch("sb_colsum");
+  float* scratch = col_scratch();
+  SB_REQUIRE(scratch != nullptr, "sb_colsum: could not allocate the reduction scratch");
+  SB_REQUIRE((size_t)gy * N <= COL_SCRATCH_FLOATS, "sb_colsum: reduction scratch too small for %d x %d", gy, N);
+  colsum_kernel<<<dim3(gx, gy), 256, 0, STREAM(stream)>>>((const bf16*)dy, scratch, T, N, ld, rows_per);
+  if (sb_check_launch("sb_colsum")) return 1;
+  reduce_partials_kernel<<<(N + 255) / 256, 256, 0, STREAM(stream)>>>(scratch, gy, N, out, N);
+  return sb_check_launch("sb_colsum(reduce)");
 }

@@ -44,8 +44,6 @@ def main():
     G, C = cfg["G"], cfg["C"]
     pix2 = pix.flip(0).contiguous()
     lib = ops._lib.load()
-    m.generate(ids, pix, grid, max_new_tokens=C, num_return_sequences=G, pixel_values_videos_2=pix2,
-               num_return_sequences_2=G // 2, min_new_tokens=C, use_graph=False, seed=1, **{"max_steps_debug": 0}) if False else None
     # build the decode state with a short rollout (full prefill, 3 decode steps)
     st = m._decode_state(G + G // 2, ids.numel(), C, 2)
     m.generate(ids, pix, grid, max_new_tokens=C, num_return_sequences=G, pixel_values_videos_2=pix2,
