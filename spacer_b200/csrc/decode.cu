@@ -74,11 +74,19 @@ dec_residual_rmsnorm_kernel(bf16* __restrict__ x, const float* __restrict__ part
   pdl_launch_dependents();
   const bool tr_on = blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
   const int tr = tr_on ? sb_trace_begin(SB_TR_RMSNORM) : -1;
+  constexpr int MAXV = 4;                      // up to 4 passes of 4096 elements (H <= 16384)
+  constexpr int MAXS = 8;                      // split-K partials gathered in one round trip (more: extra rounds)
+  // the norm weight does not depend on the preceding kernels: fetch it before the dependency wait
+  uint2 wreg[MAXV];
+#pragma unroll
+  for (int np = 0; np < MAXV; ++np) {
+    const int i = (np * RN_THREADS + threadIdx.x) * 4;
+    wreg[np] = (xn && i < H) ? *reinterpret_cast<const uint2*>(w + i) : make_uint2(0u, 0u);
+  }
   pdl_wait();
   sb_trace_mark(tr, 1);
   __shared__ float red[32];
   const int r = blockIdx.x;
-  constexpr int MAXV = 4;                      // up to 4 passes of 4096 elements (H <= 16384)
   float v[MAXV][4];
   float ss = 0.f;
 #pragma unroll
@@ -86,22 +94,30 @@ dec_residual_rmsnorm_kernel(bf16* __restrict__ x, const float* __restrict__ part
     const int i = (np * RN_THREADS + threadIdx.x) * 4;
     if (i >= H) break;
     const uint2 xu = *reinterpret_cast<const uint2*>(x + (long long)r * H + i);
-    const float2 x01 = unpack_bf16(xu.x), x23 = unpack_bf16(xu.y);
-    float c[4] = {x01.x, x01.y, x23.x, x23.y};
+    float c[4];
     if (parts) {
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int s = 0; s < S; ++s) {
-        const float4 t = *reinterpret_cast<const float4*>(parts + s * part_stride_s + r * part_stride_r + i);
-        a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+      for (int s0 = 0; s0 < S; s0 += MAXS) {
+        float4 t[MAXS];
+#pragma unroll
+        for (int s = 0; s < MAXS; ++s)          // every load of the round is issued before the first add
+          t[s] = (s0 + s < S) ? *reinterpret_cast<const float4*>(parts + (s0 + s) * part_stride_s + r * part_stride_r + i)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int s = 0; s < MAXS; ++s) { a.x += t[s].x; a.y += t[s].y; a.z += t[s].z; a.w += t[s].w; }
       }
-      c[0] = bf16_round(bf16_round(a.x) + c[0]);
-      c[1] = bf16_round(bf16_round(a.y) + c[1]);
-      c[2] = bf16_round(bf16_round(a.z) + c[2]);
-      c[3] = bf16_round(bf16_round(a.w) + c[3]);
+      const float2 x01 = unpack_bf16(xu.x), x23 = unpack_bf16(xu.y);
+      c[0] = bf16_round(bf16_round(a.x) + x01.x);
+      c[1] = bf16_round(bf16_round(a.y) + x01.y);
+      c[2] = bf16_round(bf16_round(a.z) + x23.x);
+      c[3] = bf16_round(bf16_round(a.w) + x23.y);
       uint2 o;
       o.x = pack_bf16(c[0], c[1]);
       o.y = pack_bf16(c[2], c[3]);
       *reinterpret_cast<uint2*>(x + (long long)r * H + i) = o;
+    } else {
+      const float2 x01 = unpack_bf16(xu.x), x23 = unpack_bf16(xu.y);
+      c[0] = x01.x; c[1] = x01.y; c[2] = x23.x; c[3] = x23.y;
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) { v[np][j] = c[j]; ss += c[j] * c[j]; }
@@ -113,8 +129,7 @@ dec_residual_rmsnorm_kernel(bf16* __restrict__ x, const float* __restrict__ part
     for (int np = 0; np < MAXV; ++np) {
       const int i = (np * RN_THREADS + threadIdx.x) * 4;
       if (i >= H) break;
-      const uint2 wu = *reinterpret_cast<const uint2*>(w + i);
-      const float2 w01 = unpack_bf16(wu.x), w23 = unpack_bf16(wu.y);
+      const float2 w01 = unpack_bf16(wreg[np].x), w23 = unpack_bf16(wreg[np].y);
       uint2 o;
       o.x = pack_bf16(w01.x * bf16_round(v[np][0] * rstd), w01.y * bf16_round(v[np][1] * rstd));
       o.y = pack_bf16(w23.x * bf16_round(v[np][2] * rstd), w23.y * bf16_round(v[np][3] * rstd));
@@ -134,28 +149,44 @@ dec_qkv_post_kernel(const float* __restrict__ parts, int S, long long stride_s, 
   pdl_launch_dependents();
   const bool tr_on = blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
   const int tr = tr_on ? sb_trace_begin(SB_TR_QKVPOST) : -1;
+  const int r = blockIdx.x, head = blockIdx.y;
+  const int half = hd / 2;
+  const int i = threadIdx.x;
+  const int c0 = head * hd + i, c1 = c0 + half;
+  // constants (bias, rotary frequency) do not depend on the preceding kernels: computed before the dependency wait
+  float bias0 = 0.f, bias1 = 0.f, inv_freq = 0.f;
+  if (i < half) {
+    bias0 = __bfloat162float(bias[c0]);
+    bias1 = __bfloat162float(bias[c1]);
+    inv_freq = 1.0f / powf(theta, (float)(2 * i) / (float)hd);
+  }
   pdl_wait();
   sb_trace_mark(tr, 1);
-  const int r = blockIdx.x, head = blockIdx.y;
   const int step = *step_ptr;
-  const int half = hd / 2;
   const float* pr = parts + r * stride_r;
   const int slot = min(step, c_max - 1);
-  const int i = threadIdx.x;
   if (i >= half) return;
-  const int c0 = head * hd + i, c1 = c0 + half;
   float a = 0.f, b = 0.f;
-  for (int s = 0; s < S; ++s) { a += pr[s * stride_s + c0]; b += pr[s * stride_s + c1]; }
+  constexpr int MAXS = 8;
+  for (int s0 = 0; s0 < S; s0 += MAXS) {
+    float ta[MAXS], tb[MAXS];
+#pragma unroll
+    for (int s = 0; s < MAXS; ++s) {            // every load of the round is issued before the first add
+      ta[s] = (s0 + s < S) ? pr[(s0 + s) * stride_s + c0] : 0.f;
+      tb[s] = (s0 + s < S) ? pr[(s0 + s) * stride_s + c1] : 0.f;
+    }
+#pragma unroll
+    for (int s = 0; s < MAXS; ++s) { a += ta[s]; b += tb[s]; }
+  }
   if (head >= nh + nkv) {   // v: bias only
     bf16* vd = v_cache + r * cache_stride_r + (long long)slot * nkv * hd + (head - nh - nkv) * hd;
-    vd[i] = __float2bfloat16_rn(a + __bfloat162float(bias[c0]));
-    vd[i + half] = __float2bfloat16_rn(b + __bfloat162float(bias[c1]));
+    vd[i] = __float2bfloat16_rn(a + bias0);
+    vd[i + half] = __float2bfloat16_rn(b + bias1);
     return;
   }
-  a = bf16_round(a + __bfloat162float(bias[c0]));
-  b = bf16_round(b + __bfloat162float(bias[c1]));
+  a = bf16_round(a + bias0);
+  b = bf16_round(b + bias1);
   const float pos = (float)(rope_base + step);
-  const float inv_freq = 1.0f / powf(theta, (float)(2 * i) / (float)hd);
   float sn, cs;
   sincosf(pos * inv_freq, &sn, &cs);
   cs = bf16_round(cs); sn = bf16_round(sn);
