@@ -368,3 +368,25 @@ def test_sft_loss_and_gradients_vs_oracle():
         rel = (g.norm() / gref.norm()).item()
         assert cos > 0.99, f"{k}: cosine {cos:.5f}"
         assert 0.9 < rel < 1.1, f"{k}: norm ratio {rel:.3f}"
+
+
+def test_sft_overfits_one_sequence():
+    """End-to-end sanity of backward + clip + AdamW: repeated SFT steps on one sequence drive its loss down."""
+    from spacer_b200.model import GradStore
+    from spacer_b200.trainer import AdamW, GRPOConfig
+    R, d_or, d, m, w, wb = _setup()
+    case = _case(d_or)
+    grid, pix = case["grid_thw"], case["pixel_values"].cuda()
+    ids = case["input_ids"][0]
+    labels = ids.clone()
+    for vt in (d_or.vision_start_id, d_or.vision_end_id, d_or.video_token_id):
+        labels[labels == vt] = -100
+    opt = AdamW(m.params, GRPOConfig(learning_rate=2e-3, weight_decay=0.0, lr_scheduler_type="constant", max_steps=100))
+    grads = GradStore(m.params)
+    losses = []
+    for _ in range(8):
+        out = m.sft_forward_backward(ids, labels, pix, grid, grads)
+        losses.append(float(out["loss"]))
+        opt.step(grads)
+    assert all(l == l for l in losses), losses
+    assert losses[-1] < 0.7 * losses[0], losses
