@@ -154,6 +154,10 @@ int sb_embed_bwd(const int* ids, const int* vis_idx, const void* dx, void* d_emb
                  int n_vision, sb_stream_t stream);
 int sb_gather_rows(const void* src, const int* rows, void* dst, int R, int H, sb_stream_t stream);
 int sb_scatter_add_rows(const void* src, const int* rows, void* dst, int R, int H, sb_stream_t stream);
+/* deterministic scatter-add: dst[seg_dst[s]] (+)= sum_{k in [seg_off[s], seg_off[s+1])} src[order[k]], fp32 accumulation in
+ * list order, one rounding (embedding gradient by token id, d_hidden of repeated lm_head rows); int32 device arrays */
+int sb_segment_sum_rows(const void* src, const int* order, const int* seg_off, const int* seg_dst, int n_seg, void* dst,
+                        int H, int accumulate, sb_stream_t stream);
 /* out_f32[n] += sum_t dy[t][n]   (bias gradients) */
 int sb_colsum(const void* dy, float* out, int T, int N, long long ld, sb_stream_t stream);
 int sb_f32_to_bf16_2d(const float* src, void* dst, int T, int W, long long ldd, sb_stream_t stream);

@@ -489,6 +489,32 @@ __global__ void scatter_add_rows_kernel(const bf16* __restrict__ src, const int*
   }
 }
 
+// Deterministic scatter-add: dst[seg_dst[s]] (+)= sum over k in [seg_off[s], seg_off[s+1]) of src[order[k]], summed in
+// fp32 in list order and rounded once (the atomic versions above round after every add, in arrival order).  Used for
+// the embedding gradient (segments = distinct token ids) and for d_hidden of the lm_head rows (the last prompt row
+// feeds every completion's first token).  One thread per (segment, 8 columns).
+__global__ void __launch_bounds__(256)
+segment_sum_rows_kernel(const bf16* __restrict__ src, const int* __restrict__ order, const int* __restrict__ seg_off,
+                        const int* __restrict__ seg_dst, int n_seg, bf16* __restrict__ dst, int H, int accumulate) {
+  const int nv = H / 8;
+  const long long total = (long long)n_seg * nv;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % nv);
+    const int sgm = (int)(idx / nv);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    bf16* d = dst + (long long)seg_dst[sgm] * H + c * 8;
+    if (accumulate) ld8f(d, acc);
+    for (int k = seg_off[sgm]; k < seg_off[sgm + 1]; ++k) {
+      float v[8];
+      ld8f(src + (long long)order[k] * H + c * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+    st8f(d, acc);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // column sums (bias gradients): out_f32[n] += sum_t dy[t][n]
 // grid (ceil(N/64), row_groups); 256 threads = 8 column-octets x 32 row lanes
@@ -686,6 +712,13 @@ extern "C" int sb_scatter_add_rows(const void* src, const int* rows, void* dst, 
   scatter_add_rows_kernel<<<grid_for((long long)R * H / 2, 256), 256, 0, STREAM(stream)>>>((const bf16*)src, rows,
                                                                                          (bf16*)dst, R, H);
   return sb_check_launch("sb_scatter_add_rows");
+}
+extern "C" int sb_segment_sum_rows(const void* src, const int* order, const int* seg_off, const int* seg_dst, int n_seg,
+                                   void* dst, int H, int accumulate, sb_stream_t stream) {
+  SB_REQUIRE(src && order && seg_off && seg_dst && dst && n_seg > 0 && H % 8 == 0, "sb_segment_sum_rows: bad arguments");
+  segment_sum_rows_kernel<<<grid_for((long long)n_seg * H / 8, 256), 256, 0, STREAM(stream)>>>(
+      (const bf16*)src, order, seg_off, seg_dst, n_seg, (bf16*)dst, H, accumulate);
+  return sb_check_launch("sb_segment_sum_rows");
 }
 extern "C" int sb_colsum(const void* dy, float* out, int T, int N, long long ld, sb_stream_t stream) {
   SB_REQUIRE(dy && out && T > 0 && N > 0 && N % 8 == 0 && ld % 8 == 0, "sb_colsum: bad arguments");

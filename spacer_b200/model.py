@@ -159,6 +159,31 @@ def causal_meta(T, device):
     return ops.make_meta(torch.zeros(T, dtype=torch.long), torch.zeros(T, dtype=torch.long), t + 1, device)
 
 
+def embed_plan(ids: torch.Tensor, dims: ModelDims, device):
+    """Deterministic embedding backward: text positions grouped by token id (segment_plan over the text rows only) and the
+    positions of the vision placeholders in order (their gradient rows are a plain gather)."""
+    ids = ids.reshape(-1).cpu().long()
+    is_v = (ids == dims.video_token_id) | (ids == dims.image_token_id)
+    text_pos = torch.nonzero(~is_v, as_tuple=True)[0]
+    order, off, dst, n = segment_plan(ids[text_pos], device)
+    # `order` indexes the text rows; translate to sequence positions so the kernel reads dx directly
+    order_pos = text_pos.to(device)[order.long()].to(I32)
+    vis_pos = torch.nonzero(is_v, as_tuple=True)[0].to(I32).to(device)
+    return (order_pos, off, dst, n, vis_pos)
+
+
+def segment_plan(keys: torch.Tensor, device):
+    """Host side of sb_segment_sum_rows: for int keys [n] (destination row of source row i) returns device int32 tensors
+    (order, seg_off, seg_dst, n_seg): sources grouped by key in their original order (stable sort)."""
+    keys = keys.reshape(-1).cpu().long()
+    order = torch.argsort(keys, stable=True)
+    sk = keys[order]
+    uniq, counts = torch.unique_consecutive(sk, return_counts=True)
+    off = torch.zeros(uniq.numel() + 1, dtype=torch.long)
+    off[1:] = counts.cumsum(0)
+    return (order.to(I32).to(device), off.to(I32).to(device), uniq.to(I32).to(device), int(uniq.numel()))
+
+
 @dataclass
 class PackedBatch:
     """[prompt | completion_0 | ... | completion_{G-1}] with everything the kernels need."""
@@ -171,6 +196,8 @@ class PackedBatch:
     P: int
     G: int
     C: int
+    rows_plan: tuple = None    # segment_plan(rows): deterministic d_hidden scatter of the lm_head rows
+    embed_plan: tuple = None   # (text positions, segment_plan(token id of the text positions), vision positions)
 
 
 def pack_prompt_completions(prompt_ids, completion_ids, grid_thw, dims: ModelDims, device, convention="classic",
@@ -191,7 +218,8 @@ def pack_prompt_completions(prompt_ids, completion_ids, grid_thw, dims: ModelDim
     rows = torch.cat([torch.full((G, 1), P - 1), starts[:, None] + torch.arange(C - 1)[None]], dim=1).reshape(-1)
     return PackedBatch(ids=ids.to(I32).to(device), pos=pos.to(I32).contiguous().to(device), meta=meta,
                        rows=rows.to(I32).to(device), targets=comp.reshape(-1).to(I32).to(device),
-                       comp_ids=comp.to(I32).contiguous().to(device), P=P, G=G, C=C)
+                       comp_ids=comp.to(I32).contiguous().to(device), P=P, G=G, C=C,
+                       rows_plan=segment_plan(rows, device), embed_plan=embed_plan(ids, dims, device))
 
 
 class GradStore:
@@ -552,7 +580,15 @@ class Qwen2VLB200:
         d_vis = None
         if tape["n_vis"] > 0 and want_d_vis:
             d_vis = torch.zeros((tape["n_vis"], H), device=self.device, dtype=BF16)
-        ops.call("sb_embed_bwd", tape["ids"], tape["vis_idx"], dx, G["embed"], d_vis, T, H, tape["n_vis"])
+        plan = tape.get("embed_plan")
+        if plan is None:      # atomic fallback (order of duplicate tokens not fixed)
+            ops.call("sb_embed_bwd", tape["ids"], tape["vis_idx"], dx, G["embed"], d_vis, T, H, tape["n_vis"])
+        else:
+            order_pos, off, dst, n_seg, vis_pos = plan
+            if n_seg > 0:
+                ops.call("sb_segment_sum_rows", dx, order_pos, off, dst, n_seg, G["embed"], H, 1)
+            if d_vis is not None and vis_pos.numel() > 0:
+                ops.call("sb_gather_rows", dx, vis_pos, d_vis, vis_pos.numel(), H)
         G.ready("embed")
         return d_vis
 
@@ -634,7 +670,12 @@ class Qwen2VLB200:
         if not d.tie:
             grads.ready("lm_head")
         d_hf = torch.zeros_like(hf)
-        ops.call("sb_scatter_add_rows", d_hsel, batch.rows, d_hf, R, H)
+        if batch.rows_plan is not None:    # deterministic: repeated rows (the last prompt row) summed in fp32, fixed order
+            order, off, dst, n_seg = batch.rows_plan
+            ops.call("sb_segment_sum_rows", d_hsel, order, off, dst, n_seg, d_hf, H, 0)
+        else:
+            ops.call("sb_scatter_add_rows", d_hsel, batch.rows, d_hf, R, H)
+        ltape["embed_plan"] = batch.embed_plan
         del hsel, d_hsel, hf
         mark("lm_head_bwd")
         d_vis = self.llm_backward(ltape, d_hf, grads)
@@ -697,7 +738,8 @@ class Qwen2VLB200:
         if not d.tie:
             grads.ready("lm_head")
         d_hf = torch.zeros_like(hf)
-        ops.call("sb_scatter_add_rows", d_hsel, rows, d_hf, R, H)
+        ops.call("sb_scatter_add_rows", d_hsel, rows, d_hf, R, H)      # rows are distinct here: no accumulation order
+        ltape["embed_plan"] = embed_plan(ids, d, self.device)
         del hsel, d_hsel, hf
         d_vis = self.llm_backward(ltape, d_hf, grads)
         if vis is not None:

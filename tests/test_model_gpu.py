@@ -390,3 +390,26 @@ def test_sft_overfits_one_sequence():
         opt.step(grads)
     assert all(l == l for l in losses), losses
     assert losses[-1] < 0.7 * losses[0], losses
+
+
+def test_grpo_backward_is_bit_reproducible():
+    """No floating-point atomics on the training path: two runs of the same forward/backward give bit-identical
+    gradient arenas (what makes data-parallel ranks and repeated runs agree exactly)."""
+    from oracle import grpo_ref as GR
+    from spacer_b200.model import GradStore, pack_prompt_completions
+    R, d_or, d, m, w, wb = _setup()
+    case = _case(d_or)
+    comp = case["completion_ids"].clone()
+    comp[:, 0] = comp[0, 0]                      # repeated tokens: the embedding rows that accumulate
+    comp[2, 3:6] = comp[0, 1]
+    batch = pack_prompt_completions(case["prompt_ids"], comp, case["grid_thw"], d, m.device)
+    G = comp.shape[0]
+    adv, _ = GR.advantages(case["rewards"][:G], G)
+    ref_lp = torch.full(comp.shape, -7.0)
+    outs = []
+    for _ in range(2):
+        grads = GradStore(m.params)
+        m.grpo_forward_backward(batch, case["pixel_values"].cuda(), case["grid_thw"], ref_lp.cuda(), adv.cuda(), 0.04, grads)
+        outs.append((grads.mat.clone(), grads.vec.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert float(outs[0][0].float().abs().sum()) > 0
