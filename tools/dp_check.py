@@ -2,8 +2,8 @@
 """Data-parallel invariants on N GPUs (torchrun): after K trainer steps on different prompts per rank
   (1) every rank holds bit-identical weights (the invariant data parallelism rests on), with the all-reduce after the
       backward and with the overlapped per-layer all-reduce;
-  (2) reported, not asserted: distance between the two modes' weights (norm/bias gradients are accumulated with fp32
-      atomics, so two runs agree to rounding noise, which AdamW turns into +-lr per step for noise-level gradients).
+  (2) the two modes end with bit-identical weights (the training path has no floating-point atomics: a whole
+      rollout + update step is reproducible), reported as overlap_equals_no_overlap / max_abs_diff_overlap_vs_not.
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/dp_check.py [--preset tiny|2b]"""
 import argparse
 import contextlib
