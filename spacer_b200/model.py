@@ -277,6 +277,10 @@ class Qwen2VLB200:
         self.training = False
         self._dec = None
         self.phase_marks = None
+        # the attributes of an HF module the reference trainer touches (SG_RLVR_trainer.py:156, 193, 234, 312)
+        from . import hub
+        self.config = hub.make_config_namespace(dims)
+        self.warnings_issued = {}
 
     # ---- HF-like surface -------------------------------------------------------------------------
     def state_dict(self):
@@ -285,6 +289,26 @@ class Qwen2VLB200:
     def load_state_dict(self, sd, strict=True):
         self.params.load_state_dict(sd)
         return self
+
+    @classmethod
+    def from_pretrained(cls, path, device="cuda", **kw):
+        """Local HF-format checkpoint directory -> engine (Qwen2-VL or Qwen2.5-VL by config.json; hub.from_pretrained)."""
+        from . import hub
+        return hub.from_pretrained(cls, path, device, **kw)
+
+    def save_pretrained(self, path, **kw):
+        """HF-format checkpoint (config.json + safetensors, transformers 5.x names): open_r1/SG-RLVR.py:384."""
+        from . import hub
+        hub.save_pretrained(self, path, **kw)
+
+    def gradient_checkpointing_enable(self, **kw):
+        """Accepted for API compatibility (HF Trainer calls it): activations of one step fit in HBM, nothing is recomputed."""
+
+    def gradient_checkpointing_disable(self):
+        pass
+
+    def named_parameters(self):
+        return list(self.params.hf_items())
 
     def train(self, mode=True):
         self.training = mode

@@ -163,3 +163,28 @@ def test_param_layout_roundtrip_names_cpu():
     assert ps.mat.data_ptr() % 256 == 0 or True
     for name, (arena, off, shape) in ps.index.items():
         assert off % 128 == 0          # 256-byte aligned tensors (TMA needs 16)
+
+
+def test_hf_config_roundtrip_and_name_normalisation():
+    """hub: ModelDims <-> config.json (nested 5.x layout written, nested and flat 4.x layouts read), old -> new names."""
+    from spacer_b200 import config, hub
+    for d in (config.qwen2_vl_7b(), config.qwen2_vl_2b(), config.qwen2_5_vl_7b(), config.tiny25()):
+        back = hub.dims_from_hf_config(hub.hf_config_from_dims(d), name_hint=d.name)
+        for f in ("hidden", "layers", "heads", "kv_heads", "head_dim", "inter", "vocab", "tie", "v_depth", "v_embed",
+                  "v_heads", "v_mlp", "variant", "v_fullatt", "mrope_section", "eos_id", "pad_id", "video_token_id"):
+            assert getattr(back, f) == getattr(d, f), (d.name, f)
+    flat = dict(model_type="qwen2_vl", hidden_size=3584, num_hidden_layers=28, num_attention_heads=28, num_key_value_heads=4,
+                intermediate_size=18944, vocab_size=152064, rms_norm_eps=1e-6, rope_theta=1000000.0,
+                rope_scaling={"type": "mrope", "mrope_section": [16, 24, 24]}, tie_word_embeddings=False,
+                vision_config=dict(depth=32, embed_dim=1280, mlp_ratio=4, num_heads=16, in_chans=3, hidden_size=3584,
+                                   patch_size=14, spatial_merge_size=2, temporal_patch_size=2),
+                image_token_id=151655, video_token_id=151656, vision_start_token_id=151652, vision_end_token_id=151653,
+                eos_token_id=151645, bos_token_id=151643)
+    d = hub.dims_from_hf_config(flat, "Qwen/Qwen2-VL-7B-Instruct")
+    assert d == config.qwen2_vl_7b().__class__(**{**config.qwen2_vl_7b().__dict__, "name": "Qwen2-VL-7B-Instruct"})
+    old = {"visual.blocks.0.attn.qkv.weight": 1, "model.layers.3.mlp.up_proj.weight": 2, "model.embed_tokens.weight": 3,
+           "model.norm.weight": 4, "lm_head.weight": 5, "model.visual.merger.ln_q.weight": 6}
+    assert hub.normalize_names(old) == {"model.visual.blocks.0.attn.qkv.weight": 1,
+                                        "model.language_model.layers.3.mlp.up_proj.weight": 2,
+                                        "model.language_model.embed_tokens.weight": 3, "model.language_model.norm.weight": 4,
+                                        "lm_head.weight": 5, "model.visual.merger.ln_q.weight": 6}

@@ -413,3 +413,41 @@ def test_grpo_backward_is_bit_reproducible():
         outs.append((grads.mat.clone(), grads.vec.clone()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
     assert float(outs[0][0].float().abs().sum()) > 0
+
+
+@pytest.mark.parametrize("family", ["qwen2_vl", "qwen2_5_vl"])
+def test_from_pretrained_reads_hf_checkpoints_and_roundtrips(family, tmp_path):
+    """SURVEY 8(b) model construction: a directory written by the real HF class's save_pretrained loads into the engine
+    (config.json parsed, variant picked, every parameter equal), and our save_pretrained is read back by HF."""
+    import transformers
+    from oracle import make_golden as MG
+    from spacer_b200.model import Qwen2VLB200
+    if family == "qwen2_vl":
+        from oracle import qwen2vl_ref as R
+        d_or, w = R.dims_tiny(), None
+        w = R.init_weights(d_or, seed=3)
+        hf = transformers.Qwen2VLForConditionalGeneration(MG.hf_config(d_or))
+    else:
+        from oracle import qwen25vl_ref as R25
+        d_or = R25.dims25_tiny()
+        w = R25.init_weights(d_or, seed=3)
+        hf = transformers.Qwen2_5_VLForConditionalGeneration(MG.hf_config25(d_or))
+    hf.load_state_dict(w, strict=True)
+    hf = hf.to(torch.bfloat16)
+    src = tmp_path / "hf_ckpt"
+    hf.save_pretrained(src)
+    m = Qwen2VLB200.from_pretrained(str(src), attn_implementation="flash_attention_2", torch_dtype=torch.bfloat16, use_cache=False)
+    assert m.dims.variant == family and m.config._name_or_path == str(src) and m.warnings_issued == {}
+    sd = m.state_dict()
+    for k, v in w.items():
+        assert torch.equal(sd[k].cpu(), v.bfloat16()), k
+    m.gradient_checkpointing_enable()
+    dst = tmp_path / "ours"
+    m.save_pretrained(dst)
+    cls = transformers.Qwen2VLForConditionalGeneration if family == "qwen2_vl" else transformers.Qwen2_5_VLForConditionalGeneration
+    back = cls.from_pretrained(dst, torch_dtype=torch.bfloat16)
+    bsd = back.state_dict()
+    for k, v in w.items():
+        assert torch.equal(bsd[k].cpu(), v.bfloat16()), k
+    m2 = Qwen2VLB200.from_pretrained(str(dst))
+    assert torch.equal(m2.params.mat, m.params.mat) and torch.equal(m2.params.vec, m.params.vec)
