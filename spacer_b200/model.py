@@ -639,6 +639,48 @@ class Qwen2VLB200:
         ops.call("sb_logprob_from_partials", part, nt, tl, lp, R)
         return lp.view(batch.G, batch.C)
 
+    @torch.no_grad()
+    def get_per_token_logps(self, input_ids, pixel_values_videos=None, video_grid_thw=None, pixel_values=None,
+                            image_grid_thw=None, **unused):
+        """Drop-in for `SGRLVRTrainer._get_per_token_logps(model, input_ids, **kwargs)` (SG_RLVR_trainer.py:353-366) on the
+        no-grad path (the reference-policy scoring, TRN:534-547): takes the reference's arguments -- `input_ids [B, L]`
+        whose rows share the prompt, the xB-repeated pixel values and grid (TRN:507-521) -- and returns `[B, L-1]`
+        log-probs of tokens 1..L-1.  The rows are packed behind their longest common prefix (exact for any common
+        prefix); the prefix positions are scored once and broadcast."""
+        d = self.dims
+        ids = input_ids.cpu().long()
+        if ids.dim() != 2:
+            raise SpacerError("get_per_token_logps: input_ids must be [B, L]")
+        B, L = ids.shape
+        if pixel_values is not None:
+            pixel_values_videos, video_grid_thw = pixel_values, image_grid_thw
+        grid = video_grid_thw
+        pix = pixel_values_videos
+        if grid is not None:
+            grid = torch.as_tensor(grid).reshape(-1, 3)
+            if grid.shape[0] == B and B > 1:       # the reference repeats the visual inputs once per row
+                if not bool((grid == grid[:1]).all()):
+                    raise SpacerError("get_per_token_logps: rows must share one visual input")
+                n_p = int(grid[0, 0] * grid[0, 1] * grid[0, 2])
+                pix, grid = pix[:n_p], grid[:1]
+        same = (ids == ids[:1]).all(0)
+        P = int(L if bool(same.all()) else torch.nonzero(~same)[0, 0])
+        P = max(1, min(P, L - 1))                  # at least one "completion" column, at least one prefix token
+        batch = pack_prompt_completions(ids[0, :P], ids[:, P:], grid, d, self.device, self.rope_convention)
+        vis = self.vit_forward(pix.to(self.device), grid) if pix is not None else None
+        hf = self.llm_forward(batch.ids, vis, batch.pos, batch.meta)
+        # rows that predict the completion tokens, then rows 0..P-2 that predict prefix tokens 1..P-1
+        rows = torch.cat([batch.rows, torch.arange(P - 1, device=self.device, dtype=I32)])
+        targets = torch.cat([batch.targets, ids[0, 1:P].to(I32).to(self.device)])
+        R = rows.numel()
+        hsel = torch.empty((R, d.hidden), device=self.device, dtype=BF16)
+        ops.call("sb_gather_rows", hf, rows, hsel, R, d.hidden)
+        part, tl, nt = self._lmhead_partials(hsel, targets)
+        lp = torch.empty(R, device=self.device, dtype=F32)
+        ops.call("sb_logprob_from_partials", part, nt, tl, lp, R)
+        n_c = B * (L - P)
+        return torch.cat([lp[n_c:].view(1, P - 1).expand(B, -1), lp[:n_c].view(B, L - P)], dim=1)
+
     def grpo_forward_backward(self, batch: PackedBatch, pixel_values, grid_thw, ref_logps, advantages, beta,
                               grads: GradStore, lm_chunk: int = 4096):
         """One GRPO forward/backward (TRN:526-528, 551-552, 640-643 + autograd's backward).

@@ -451,3 +451,25 @@ def test_from_pretrained_reads_hf_checkpoints_and_roundtrips(family, tmp_path):
         assert torch.equal(bsd[k].cpu(), v.bfloat16()), k
     m2 = Qwen2VLB200.from_pretrained(str(dst))
     assert torch.equal(m2.params.mat, m.params.mat) and torch.equal(m2.params.vec, m.params.vec)
+
+
+def test_get_per_token_logps_dropin_signature():
+    """The reference's override point `_get_per_token_logps(model, input_ids, pixel_values_videos=(xG), video_grid_thw=(xG))
+    -> [G, L-1]` (SG_RLVR_trainer.py:353-366, 507-528): full-width result vs the oracle, incl. the prompt positions."""
+    R, d_or, d, m, w, wb = _setup()
+    case = _case(d_or)
+    ids = case["input_ids"]
+    G, L = ids.shape
+    grid = case["grid_thw"].repeat(G, 1)
+    pix = case["pixel_values"].repeat(G, 1)
+    got = m.get_per_token_logps(ids, pixel_values_videos=pix.cuda(), video_grid_thw=grid).cpu()
+    assert got.shape == (G, L - 1)
+    pos = R.rope_index_classic(ids, grid, d_or)
+    logits = R.model_logits(wb, ids, pix.bfloat16().float(), grid, pos, d_or)
+    ref = R.per_token_logps(logits.bfloat16().float(), ids)
+    err = (got - ref).abs()
+    assert err.max() < 3e-2 and err.mean() < 3e-3, (err.max().item(), err.mean().item())
+    P = case["prompt_ids"].shape[1]
+    from spacer_b200.model import pack_prompt_completions
+    batch = pack_prompt_completions(case["prompt_ids"], case["completion_ids"], case["grid_thw"], d, m.device)
+    assert torch.equal(got[:, P - 1:], m.per_token_logps(batch, case["pixel_values"].cuda(), case["grid_thw"]).cpu())
