@@ -174,3 +174,54 @@ def test_cfg2_2b_bringup():
     assert torch.isfinite(grads.mat.float().sum()) and float(grads.mat.float().abs().sum()) > 0
     del m, grads
     torch.cuda.empty_cache()
+
+
+def test_cfg1_2b_logprobs_and_loss_vs_oracle():
+    """BASELINE configs[0]: Qwen2-VL-2B dims (real widths, 28 + 32 layers), 2 frames x 224^2 (grid 1x16x16 -> 64 vision
+    tokens), P = 128, C = 16, G = 2: per-token log-probs and the GRPO loss of the CUDA path against the oracle's fp32 CPU
+    forward on the same bf16-rounded weights.  At the real widths and depths (32 + 28 layers) the CUDA path rounds every
+    activation to bf16 like the reference's bf16 model does, the oracle keeps fp32: |d logprob| <= 1e-1, mean <= 2.5e-2
+    at logit std ~1 (the tiny-dims tests hold 2e-2 / 3e-3), and the log-probs must correlate > 0.9995."""
+    from oracle import grpo_ref as GR
+    from oracle import qwen2vl_ref as R
+    from spacer_b200 import config
+    from spacer_b200.model import GradStore, Qwen2VLB200, pack_prompt_completions
+    d_or, d = R.dims_2b(), config.qwen2_vl_2b()
+    w = R.init_weights(d_or, seed=0)
+    m = Qwen2VLB200(d, "cuda").load_state_dict(w)
+    for k in w:
+        w[k] = w[k].bfloat16().float()
+    g = torch.Generator().manual_seed(1)
+    grid = torch.tensor([[1, 16, 16]])
+    pix = torch.randn(256, d_or.patch_dim, generator=g)
+    prompt = R.build_prompt_ids(d_or, 64, 10, 52, seed=1)
+    G, C = 2, 16
+    P = prompt.shape[1]
+    assert P == 128
+    comp = torch.randint(1000, 100000, (G, C), generator=g)
+    comp[1, 11] = d_or.eos_id
+    ids = torch.cat([prompt.repeat(G, 1), comp], 1)
+    with torch.no_grad():
+        pos = R.rope_index_classic(ids, grid.repeat(G, 1), d_or)
+        logits = R.model_logits(w, ids, pix.bfloat16().float().repeat(G, 1), grid.repeat(G, 1), pos, d_or)
+        lp_ref = R.per_token_logps(logits.bfloat16().float(), ids)[:, P - 1:]
+    del logits
+    batch = pack_prompt_completions(prompt, comp, grid, d, m.device)
+    lp = m.per_token_logps(batch, pix.cuda(), grid).cpu()
+    err = (lp - lp_ref).abs()
+    print("cfg1 (2B) |d logprob| max %.4f mean %.4f; lp_ref[0,:4] = %s" % (err.max().item(), err.mean().item(), lp_ref[0, :4].tolist()))
+    assert err.max().item() < 1e-1 and err.mean().item() < 2.5e-2, (err.max().item(), err.mean().item())
+    corr = torch.corrcoef(torch.stack([lp.flatten(), lp_ref.flatten()]))[0, 1].item()
+    assert corr > 0.9995, corr
+    rewards = torch.tensor([1.5, 0.0])
+    adv, _ = GR.advantages(rewards, G)
+    mask = GR.completion_mask(comp, d_or.eos_id)
+    ref_lp = lp_ref + 0.1
+    loss_ref, kl_ref = GR.grpo_loss(lp_ref, ref_lp, adv, mask, 0.04)
+    grads = GradStore(m.params)
+    out = m.grpo_forward_backward(batch, pix.cuda(), grid, ref_lp.cuda(), adv.cuda(), 0.04, grads)
+    print("cfg1 loss %.5f vs oracle %.5f; kl %.5f vs %.5f" % (out["loss"].item(), loss_ref.item(), out["mean_kl"].item(), kl_ref.item()))
+    assert abs(out["loss"].item() - loss_ref.item()) < 5e-3 and abs(out["mean_kl"].item() - kl_ref.item()) < 5e-3
+    assert out["lengths"].tolist() == [16, 12]
+    del m, grads, w
+    torch.cuda.empty_cache()
