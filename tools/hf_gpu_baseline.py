@@ -1,0 +1,128 @@
+#!/usr/bin/env python
+"""The comparator of BASELINE's ">= 5x the reference HF/PyTorch GRPO step" target, measured on the same B200: the
+reference trainer's step (SG_RLVR_trainer.py:384-686) restated over the stock Hugging Face `Qwen2VLForConditionalGeneration`
+(transformers 5.5.0, random-init weights of the real config, bf16) -- none of this repo's kernels.  trl / accelerate /
+deepspeed are absent, so the HF Trainer plumbing is replaced by the plain loop below; the model calls are the reference's:
+    generate(num_return_sequences=G, do_sample, top_p .95)  (+ G/2 on the frame-shuffled video)     TRN:463-481
+    reference-policy forward over the G full sequences with xG-repeated pixels, no grad            TRN:534-547
+    policy forward (gradient checkpointing, as run_SpaceR_SG_RLVR.sh:27) -> per-row log_softmax/gather -> GRPO loss
+    -> backward -> clip 5 -> AdamW                                                                  TRN:353-366, 640-643
+    python tools/hf_gpu_baseline.py [--config c3] [--attn sdpa|flash_attention_2|eager] [--steps 1] [--device cuda]
+Prints one JSON line (samples/s, ms per phase)."""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from oracle import grpo_ref as GR  # noqa: E402  (loss math restatement; CPU/GPU agnostic torch code)
+from oracle import qwen2vl_ref as R  # noqa: E402
+from oracle.make_golden import hf_config  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="c3")
+    ap.add_argument("--attn", default="sdpa")
+    ap.add_argument("--steps", type=int, default=1)
+    ap.add_argument("--device", default="cuda")
+    ap.add_argument("--completion", type=int, default=0, help="override C (debug)")
+    a = ap.parse_args()
+    from transformers import Qwen2VLForConditionalGeneration
+    cfg = dict(bench.CONFIGS[a.config])
+    if a.completion:
+        cfg["C"] = a.completion
+    d = {"7b": R.dims_7b, "2b": R.dims_2b, "tiny": R.dims_tiny}[cfg["preset"]]()
+    dev = torch.device(a.device)
+    dt = torch.bfloat16 if dev.type == "cuda" else torch.float32
+    hc = hf_config(d)
+    hc._attn_implementation = a.attn
+    torch.manual_seed(0)
+    with torch.device(dev):
+        model = Qwen2VLForConditionalGeneration(hc).to(dt)
+        ref = Qwen2VLForConditionalGeneration(hc).to(dt)
+    ref.load_state_dict(model.state_dict())
+    ref.eval()
+    model.gradient_checkpointing_enable()
+    model.config.use_cache = True
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-6, weight_decay=0.01, fused=dev.type == "cuda")
+    ex = bench.synth_example(_dims_like(d), cfg, 1234)
+    pix = ex["pixel_values_host"].to(dev, dt)
+    grid = ex["video_grid_thw"].to(dev)
+    ids = ex["input_ids"].to(dev)
+    P = ids.shape[1]
+    G, C = cfg["G"], cfg["C"]
+    mm = ((ids == d.video_token_id).long() * 2 + (ids == d.image_token_id).long())
+    pix2 = pix.flip(0).contiguous()
+
+    def sync():
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
+
+    def step(C_):
+        t = {}
+        sync(); t0 = time.perf_counter()
+        model.eval()
+        with torch.no_grad():
+            kw = dict(max_new_tokens=C_, min_new_tokens=C_, do_sample=True, top_p=0.95, temperature=1.0,
+                      pad_token_id=d.pad_id, use_cache=True)
+            out = model.generate(input_ids=ids, mm_token_type_ids=mm, pixel_values_videos=pix, video_grid_thw=grid,
+                                 num_return_sequences=G, **kw)
+            model.generate(input_ids=ids, mm_token_type_ids=mm, pixel_values_videos=pix2, video_grid_thw=grid,
+                           num_return_sequences=G // 2, **kw)
+        sync(); t["rollout"] = time.perf_counter() - t0
+        full = out                                            # [G, P + C]
+        mmf = ((full == d.video_token_id).long() * 2 + (full == d.image_token_id).long())
+        pos = R.rope_index_classic(full.cpu(), grid.cpu().repeat(G, 1), d).to(dev)
+        pixG, gridG = pix.repeat(G, 1), grid.repeat(G, 1)
+        t0 = time.perf_counter()
+        with torch.inference_mode():
+            rl = ref(input_ids=full, pixel_values_videos=pixG, video_grid_thw=gridG, position_ids=pos, mm_token_type_ids=mmf,
+                     use_cache=False).logits
+            ref_lp = R.per_token_logps(rl, full)[:, P - 1:]
+            del rl
+        sync(); t["ref_scoring"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        model.train()
+        logits = model(input_ids=full, pixel_values_videos=pixG, video_grid_thw=gridG, position_ids=pos, mm_token_type_ids=mmf,
+                       use_cache=False).logits
+        lp = R.per_token_logps(logits, full)[:, P - 1:]
+        del logits
+        comp = full[:, P:]
+        mask = GR.completion_mask(comp.cpu(), d.eos_id).to(dev)
+        adv, _ = GR.advantages(torch.linspace(0.0, 2.0, G), G)
+        loss, _ = GR.grpo_loss(lp.float(), ref_lp.float().clone(), adv.to(dev), mask, 0.04)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        sync(); t["policy_fwd_bwd_adamw"] = time.perf_counter() - t0
+        return t
+
+    step(min(C, 4))                                           # warm-up (allocator, kernels, autotune)
+    tot = {}
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        for k, v in step(C).items():
+            tot[k] = tot.get(k, 0.0) + v
+    sync()
+    wall = (time.perf_counter() - t0) / a.steps
+    print(json.dumps({"impl": "hf_gpu_restatement", "config": cfg["workload"], "attn_implementation": a.attn, "device": str(dev),
+                      "transformers": __import__("transformers").__version__, "dtype": str(dt), "steps": a.steps,
+                      "s_per_step": round(wall, 3), "samples_per_s": round(G / wall, 4),
+                      "rollout_tok_per_s": round((G + G // 2) * C / (tot["rollout"] / a.steps), 1),
+                      "phase_s": {k: round(v / a.steps, 3) for k, v in tot.items()}}))
+
+
+def _dims_like(d):
+    """bench.synth_example reads spacer_b200.config.ModelDims-style attributes; the oracle Dims has the same names."""
+    return d
+
+
+if __name__ == "__main__":
+    main()
