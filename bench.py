@@ -13,7 +13,6 @@ from __future__ import annotations
 
 import argparse
 import json
-import math
 import os
 import subprocess
 import sys
@@ -295,7 +294,6 @@ def main():
     import torch.distributed as dist
     from spacer_b200 import config as mcfg, ops, rewards as RW
     from spacer_b200.model import Qwen2VLB200
-    from spacer_b200.params import ParamStore
     from spacer_b200.trainer import GRPOConfig, SGRLVRTrainerB200
 
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -11,8 +11,6 @@ import json
 import os
 from types import SimpleNamespace
 
-import torch
-
 from .config import ModelDims
 from .ops import SpacerError
 

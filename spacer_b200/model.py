@@ -18,16 +18,14 @@ Algorithmic differences from the reference's executed path (same mathematics, SU
 """
 from __future__ import annotations
 
-import math
 import os
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 
 import torch
 
 from . import ops
 from .config import ModelDims
-from .ops import (EPI_DLOGITS, EPI_F32T, EPI_GELU, EPI_LMHEAD, EPI_QUICKGELU, EPI_STORE, EPI_SWIGLU,
-                  SpacerError)
+from .ops import EPI_DLOGITS, EPI_F32T, EPI_GELU, EPI_LMHEAD, EPI_QUICKGELU, EPI_SWIGLU, SpacerError
 from .params import ParamStore
 
 I32 = torch.int32
