@@ -27,6 +27,7 @@ MAX_PIXELS = 256 * 28 * 28
 MAX_RATIO = 200
 VIDEO_MIN_PIXELS = 128 * 28 * 28        # QVU:32-33 (the SpaceR fork pins min == max == 128*28*28)
 VIDEO_MAX_PIXELS = 128 * 28 * 28
+VIDEO_TOTAL_PIXELS = int(128000 * 28 * 28 * 0.9)   # QVU:42 (default of the VIDEO_MAX_PIXELS environment variable)
 FRAME_FACTOR = 2
 FPS = 2.0
 FPS_MIN_FRAMES = 4
@@ -182,3 +183,31 @@ def resize_frames(frames: torch.Tensor, height: int, width: int, *, out_u8: bool
     ops.call("sb_resize_bicubic_aa", frames, int(frames.dtype == torch.uint8), F_ * Cc, H, W, tmp, out, int(out_u8), height,
              width, wh, xh, nh, th, wv, xv, nv, tv, round_u8, int(use_fma))
     return out
+
+
+def video_target_size(nframes: int, height: int, width: int, ele: dict | None = None, image_factor: int = IMAGE_FACTOR):
+    """(resized_height, resized_width) exactly as fetch_video computes them (QVU:288-309): max_pixels from the per-video
+    pixel budget, then smart_resize; explicit `resized_height` / `resized_width` in `ele` win."""
+    ele = ele or {}
+    min_pixels = ele.get("min_pixels", VIDEO_MIN_PIXELS)
+    total_pixels = ele.get("total_pixels", VIDEO_TOTAL_PIXELS)
+    max_pixels = max(min(VIDEO_MAX_PIXELS, total_pixels / nframes * FRAME_FACTOR), int(min_pixels * 1.05))
+    max_pixels = min(ele.get("max_pixels", max_pixels), max_pixels)
+    if "resized_height" in ele and "resized_width" in ele:
+        return smart_resize(ele["resized_height"], ele["resized_width"], factor=image_factor)
+    return smart_resize(height, width, factor=image_factor, min_pixels=min_pixels, max_pixels=max_pixels)
+
+
+def fetch_video_frames(video: torch.Tensor, video_fps: float, ele: dict | None = None):
+    """The part of qwen-vl-utils' fetch_video after the container is open (QVU:228-256, 279-318), on the GPU: pick
+    `smart_nframes` frames at linspace indices out of the decoded clip `video` (CUDA uint8 [total_frames, C, H, W]),
+    resize them (bicubic, antialias) to the `smart_resize` target and return (float32 frames [nframes, C, h, w] holding
+    0..255 like the reference, sample_fps).  Decoding the container itself (decord / NVDEC) is not part of this."""
+    ele = ele or {}
+    total = video.shape[0]
+    n = smart_nframes(ele, total_frames=total, video_fps=video_fps)
+    idx = torch.tensor(frame_indices(total, n), device=video.device)
+    frames = video.index_select(0, idx)
+    h, w = video_target_size(n, video.shape[2], video.shape[3], ele)
+    sample_fps = n / max(total, 1e-6) * video_fps
+    return resize_frames(frames, h, w), sample_fps

@@ -70,3 +70,23 @@ def test_resize_frames_matches_torchvision(H, W, oh, ow):
     if oh % 28 == 0 and ow % 28 == 0:
         pv, _, grid = vision.patchify(vision.resize_frames(x.cuda(), oh, ow))
         assert grid.tolist() == [[2, oh // 14, ow // 14]] and pv.shape == (2 * (oh // 14) * (ow // 14), 1176)
+
+
+def test_fetch_video_frames_equals_reference_pipeline():
+    """Frame sampling + target size + resize of fetch_video (QVU:228-256, 279-318) against the same steps done with the
+    reference's own ingredients on the CPU (torch.linspace indices, smart_resize, torchvision resize)."""
+    import torchvision.transforms.functional as TF
+    from torchvision.transforms import InterpolationMode
+    from spacer_b200 import vision
+    g = torch.Generator().manual_seed(7)
+    total, fps = 90, 29.97
+    clip = torch.randint(0, 256, (total, 3, 120, 214), generator=g, dtype=torch.uint8)
+    frames, sample_fps = vision.fetch_video_frames(clip.cuda(), fps)
+    n = vision.smart_nframes({}, total, fps)
+    assert n == 6 and frames.shape[0] == n and abs(sample_fps - n / total * fps) < 1e-9
+    idx = torch.linspace(0, total - 1, n).round().long()
+    h, w = vision.video_target_size(n, 120, 214)
+    ref = TF.resize(clip[idx], [h, w], interpolation=InterpolationMode.BICUBIC, antialias=True).float()
+    assert frames.shape == ref.shape
+    d = (frames.cpu() - ref).abs()
+    assert d.max().item() <= 1.0 and (d > 0).float().mean().item() < 1e-3
