@@ -188,3 +188,46 @@ def test_hf_config_roundtrip_and_name_normalisation():
                                         "model.language_model.layers.3.mlp.up_proj.weight": 2,
                                         "model.language_model.embed_tokens.weight": 3, "model.language_model.norm.weight": 4,
                                         "lm_head.weight": 5, "model.visual.merger.ln_q.weight": 6}
+
+
+def test_qwen25_rope_index_matches_oracle_cpu():
+    """Temporal M-RoPE spacing of Qwen2.5-VL (host integer logic): both conventions, with and without
+    second_per_grid_ts, against oracle/qwen25vl_ref.py (itself pinned to HF 5.5.0 by tests/golden/tiny_model25.pt)."""
+    from oracle import qwen25vl_ref as R25
+    from oracle import qwen2vl_ref as R
+    from spacer_b200 import config
+    from spacer_b200.model import rope_index
+    d_or, d = R25.dims25_tiny(), config.tiny25()
+    for grid in ([[2, 12, 8]], [[3, 4, 6]], [[1, 8, 8]]):
+        g = torch.tensor(grid)
+        n_v = int(g.prod()) // 4
+        ids = R.build_prompt_ids(d_or, n_v, 5, 9, seed=3)
+        for sec in (None, [1.0], [1.5], [2.0], [0.5]):
+            for conv, ref in (("classic", R25.rope_index_classic), ("hf55", R25.rope_index_hf55)):
+                pos, nxt = rope_index(ids, g, d, conv, sec)
+                want = ref(ids, g, d_or, sec)[:, 0]
+                assert torch.equal(pos, want), (grid, sec, conv)
+                assert nxt == int(want.max()) + 1 or conv == "hf55"
+
+
+def test_segment_and_embed_plans():
+    """Host side of the deterministic scatter (sb_segment_sum_rows): the plans reproduce index_add / the embedding
+    backward on CPU tensors."""
+    from spacer_b200 import config
+    from spacer_b200.model import embed_plan, segment_plan
+    g = torch.Generator().manual_seed(0)
+    keys = torch.randint(0, 7, (40,), generator=g)
+    src = torch.randn(40, 5, generator=g)
+    order, off, dst, n = segment_plan(keys, "cpu")
+    out = torch.zeros(7, 5)
+    for s in range(n):
+        rows = order[off[s]:off[s + 1]].long()
+        assert torch.equal(rows, rows.sort().values)              # original order inside a segment (stable)
+        out[dst[s]] = src[rows].sum(0)
+    assert torch.allclose(out, torch.zeros(7, 5).index_add_(0, keys, src), atol=1e-6)
+    d = config.tiny()
+    ids = torch.tensor([5, 9, d.vision_start_id, d.video_token_id, d.video_token_id, d.vision_end_id, 9, 5, 5])
+    order_pos, off, dst, n, vis_pos = embed_plan(ids, d, "cpu")
+    assert vis_pos.tolist() == [3, 4]
+    got = {int(dst[s]): order_pos[off[s]:off[s + 1]].tolist() for s in range(n)}
+    assert got == {5: [0, 7, 8], 9: [1, 6], d.vision_start_id: [2], d.vision_end_id: [5]}
