@@ -274,6 +274,7 @@ class Qwen2VLB200:
         self.rope_convention = rope_convention
         self.training = False
         self._dec = None
+        self.vit_cache = None
         self.phase_marks = None
         # the attributes of an HF module the reference trainer touches (SG_RLVR_trainer.py:156, 193, 234, 312)
         from . import hub
@@ -318,6 +319,10 @@ class Qwen2VLB200:
     def parameters(self):
         return [self.params.mat, self.params.vec]
 
+    # N = 1280 outputs with 256-wide tiles are 320 tiles = 2.16 waves of 148 CTAs (3 waves, 28 % idle); 128-wide tiles
+    # make 4.3 half-size waves (5): the ViT proj / fc2 GEMMs use them
+    VIT_NARROW_BN = 128
+
     # ---- vision tower ----------------------------------------------------------------------------
     def vit_forward(self, pixel_values, grid_thw, tape: dict | None = None):
         """Qwen2VisionTransformerPretrainedModel.forward (MQ2:757-795).  pixel_values [N_p, 1176] fp32/bf16."""
@@ -344,11 +349,11 @@ class Qwen2VLB200:
             ops.rope_vit(qkv, nh, hd, grids_dev, d.merge)
             r2 = ops.attn_fwd(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], meta, nh, nh, hd, save_lse=save)
             a = r2[0] if save else r2
-            x2 = ops.gemm(a, W[p + "proj_w"], bias=W[p + "proj_b"], residual=x)
+            x2 = ops.gemm(a, W[p + "proj_w"], bias=W[p + "proj_b"], residual=x, bn=self.VIT_NARROW_BN)
             r3 = ops.layernorm_fwd(x2, W[p + "ln2_w"], W[p + "ln2_b"], save_stats=save, out=h)
             z = torch.empty((T, d.v_mlp), device=self.device, dtype=BF16) if save else None
             f = ops.gemm(r3[0] if save else r3, W[p + "fc1_w"], bias=W[p + "fc1_b"], epilogue=EPI_QUICKGELU, aux=z)
-            x3 = ops.gemm(f, W[p + "fc2_w"], bias=W[p + "fc2_b"], residual=x2)
+            x3 = ops.gemm(f, W[p + "fc2_w"], bias=W[p + "fc2_b"], residual=x2, bn=self.VIT_NARROW_BN)
             if save:
                 tape["blocks"].append(dict(x=x, m1=r1[1], s1=r1[2], qkv=qkv, a=a, lse=r2[1], x2=x2, m2=r3[1], s2=r3[2], z=z))
             x = x3
@@ -390,11 +395,11 @@ class Qwen2VLB200:
             ops.call("sb_rope_vit_pos", qkv, T, nh, hd, plan["pos_hw"], 0)
             r2 = ops.attn_fwd(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], meta, nh, nh, hd, save_lse=save)
             a = r2[0] if save else r2
-            x2 = ops.gemm(a, W[p + "proj_w"], bias=W[p + "proj_b"], residual=x)
+            x2 = ops.gemm(a, W[p + "proj_w"], bias=W[p + "proj_b"], residual=x, bn=self.VIT_NARROW_BN)
             r3 = ops.rmsnorm_fwd(x2, W[p + "ln2_w"], 1e-6, save_stats=save, out=h)
             gu = torch.empty((T, 2 * Mp), device=self.device, dtype=BF16) if save else None
             act = ops.gemm(r3[0] if save else r3, W[p + "gu_w"], bias=W[p + "gu_b"], epilogue=EPI_SWIGLU, aux=gu)
-            x3 = ops.gemm(act, W[p + "down_w"], bias=W[p + "down_b"], residual=x2)
+            x3 = ops.gemm(act, W[p + "down_w"], bias=W[p + "down_b"], residual=x2, bn=self.VIT_NARROW_BN)
             if save:
                 tape["blocks"].append(dict(x=x, s1=r1[1], qkv=qkv, a=a, lse=r2[1], x2=x2, s2=r3[1], gu=gu))
             x = x3
@@ -680,7 +685,7 @@ class Qwen2VLB200:
         return torch.cat([lp[n_c:].view(1, P - 1).expand(B, -1), lp[:n_c].view(B, L - P)], dim=1)
 
     def grpo_forward_backward(self, batch: PackedBatch, pixel_values, grid_thw, ref_logps, advantages, beta,
-                              grads: GradStore, lm_chunk: int = 4096):
+                              grads: GradStore, lm_chunk: int = 4096, vit_cache: dict | None = None):
         """One GRPO forward/backward (TRN:526-528, 551-552, 640-643 + autograd's backward).
         Returns dict(loss, mean_kl, logps [G,C], mask [G,C], lengths [G]); gradients land in `grads`."""
         d = self.dims
@@ -697,7 +702,10 @@ class Qwen2VLB200:
                 marks.append((name, e))
 
         mark("start")
-        vis = self.vit_forward(pixel_values, grid_thw, vtape) if pixel_values is not None else None
+        if vit_cache is not None and pixel_values is not None and vit_cache["pixels"] is pixel_values:
+            vis, vtape = vit_cache["vis"], vit_cache["tape"]     # forward already done by the rollout (generate)
+        else:
+            vis = self.vit_forward(pixel_values, grid_thw, vtape) if pixel_values is not None else None
         mark("vit_fwd")
         hf = self.llm_forward(batch.ids, vis, batch.pos, batch.meta, ltape)
         mark("llm_fwd")
@@ -1083,7 +1091,8 @@ class Qwen2VLB200:
     def generate(self, input_ids, pixel_values_videos=None, video_grid_thw=None, *, max_new_tokens=1024,
                  num_return_sequences=1, top_p=0.95, temperature=1.0, do_sample=True, seed=0, min_new_tokens=0,
                  pixel_values_videos_2=None, num_return_sequences_2=0, use_graph=True, attention_mask=None,
-                 return_stats=False, second_per_grid_ts=None, pixel_values=None, image_grid_thw=None, **unused):
+                 return_stats=False, second_per_grid_ts=None, pixel_values=None, image_grid_thw=None,
+                 keep_vit_tape=False, **unused):
         """Sampled rollout: `num_return_sequences` completions of ONE prompt (TRN:463-467; generate() with
         do_sample, top_p, temperature 1).  Returns LongTensor [G, P + C'] (prompt echoed, finished rows padded).
 
@@ -1121,8 +1130,16 @@ class Qwen2VLB200:
         pixel_sets = [pixel_values_videos] + ([pixel_values_videos_2] if G2 > 0 else [])
         st = self._decode_state(R, P, max_new_tokens, len(pixel_sets))
         st["seed"].fill_(int(seed))
+        self.vit_cache = None
         for k, pix in enumerate(pixel_sets):
-            vis = self.vit_forward(pix, video_grid_thw) if pix is not None else None
+            if keep_vit_tape and k == 0 and pix is not None:
+                # the update that follows a rollout runs the SAME vision tower on the SAME pixels (one update per
+                # rollout, TRN:526-528): keep its output and saved activations instead of recomputing the forward
+                vtape = {}
+                vis = self.vit_forward(pix, video_grid_thw, vtape)
+                self.vit_cache = dict(pixels=pix, vis=vis, tape=vtape)
+            else:
+                vis = self.vit_forward(pix, video_grid_thw) if pix is not None else None
             kv = [(st["kp"][k][i], st["vp"][k][i]) for i in range(d.layers)]
             hf = self.llm_forward(ids_dev, vis, pos_dev, meta, kv_out=kv)
             # first token: same distribution for every row of a group, independent draws

@@ -155,7 +155,7 @@ class SGRLVRTrainerB200:
             ids = ids[..., -c.max_prompt_length:]                    # TRN:432-440
         # Qwen2.5-VL: the rollout sees the processor's second_per_grid_ts; the scoring forwards do not (TRN:519-520)
         kw = dict(max_new_tokens=c.max_completion_length, top_p=TOP_P, seed=seed, min_new_tokens=c.min_new_tokens,
-                  second_per_grid_ts=example.get("second_per_grid_ts"))
+                  second_per_grid_ts=example.get("second_per_grid_ts"), keep_vit_tape=True)
         if c.temporal and pix is not None:
             if frames is not None:
                 g = torch.Generator(device="cpu").manual_seed(int(seed) + 7919)
@@ -255,7 +255,8 @@ class SGRLVRTrainerB200:
         mark("rewards")
         if self.reducer is not None:
             self.reducer.begin_step()
-        out = m.grpo_forward_backward(batch, pix, grid, ref_lp, adv, c.beta, self.grads)
+        out = m.grpo_forward_backward(batch, pix, grid, ref_lp, adv, c.beta, self.grads, vit_cache=m.vit_cache)
+        m.vit_cache = None
         mark("policy_fwd_bwd")
         # data parallel: sum gradients over ranks, average inside the optimizer
         self._allreduce_grads()

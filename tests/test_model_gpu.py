@@ -473,3 +473,25 @@ def test_get_per_token_logps_dropin_signature():
     from spacer_b200.model import pack_prompt_completions
     batch = pack_prompt_completions(case["prompt_ids"], case["completion_ids"], case["grid_thw"], d, m.device)
     assert torch.equal(got[:, P - 1:], m.per_token_logps(batch, case["pixel_values"].cuda(), case["grid_thw"]).cpu())
+
+
+def test_update_reuses_the_rollout_vit_forward():
+    """generate(keep_vit_tape=True) hands its vision-tower output and saved activations to the update that follows:
+    gradients are bit-identical to recomputing the forward."""
+    from oracle import grpo_ref as GR
+    from spacer_b200.model import GradStore, pack_prompt_completions
+    R, d_or, d, m, w, wb = _setup()
+    case = _case(d_or)
+    grid, pix = case["grid_thw"], case["pixel_values"].cuda()
+    out = m.generate(case["prompt_ids"], pix, grid, max_new_tokens=6, num_return_sequences=4, seed=3, min_new_tokens=6,
+                     keep_vit_tape=True)
+    cache = m.vit_cache
+    assert cache is not None and cache["pixels"] is pix
+    P = case["prompt_ids"].shape[1]
+    batch = pack_prompt_completions(case["prompt_ids"], out[:, P:].cpu(), grid, d, m.device)
+    adv, _ = GR.advantages(torch.tensor([1.0, 0.0, 2.0, 0.5]), 4)
+    g1, g2 = GradStore(m.params), GradStore(m.params)
+    o1 = m.grpo_forward_backward(batch, pix, grid, None, adv.cuda(), 0.0, g1, vit_cache=cache)
+    o2 = m.grpo_forward_backward(batch, pix, grid, None, adv.cuda(), 0.0, g2)
+    assert torch.equal(o1["logps"], o2["logps"])
+    assert torch.equal(g1.mat, g2.mat) and torch.equal(g1.vec, g2.vec)
