@@ -194,6 +194,8 @@ class PackedBatch:
     P: int
     G: int
     C: int
+    prompt_ids_host: torch.Tensor = None   # int64 [P] / [3, P] on the host: lets the update recognise a rollout prefill
+    prompt_pos_host: torch.Tensor = None   # of the same prompt at the same positions (prefix reuse)
     rows_plan: tuple = None    # segment_plan(rows): deterministic d_hidden scatter of the lm_head rows
     embed_plan: tuple = None   # (text positions, segment_plan(token id of the text positions), vision positions)
 
@@ -217,6 +219,7 @@ def pack_prompt_completions(prompt_ids, completion_ids, grid_thw, dims: ModelDim
     return PackedBatch(ids=ids.to(I32).to(device), pos=pos.to(I32).contiguous().to(device), meta=meta,
                        rows=rows.to(I32).to(device), targets=comp.reshape(-1).to(I32).to(device),
                        comp_ids=comp.to(I32).contiguous().to(device), P=P, G=G, C=C,
+                       prompt_ids_host=prompt_ids, prompt_pos_host=ppos,
                        rows_plan=segment_plan(rows, device), embed_plan=embed_plan(ids, dims, device))
 
 
@@ -566,6 +569,62 @@ class Qwen2VLB200:
             return rf[0]
         return rf
 
+    def llm_forward_from_prefix(self, ids, vis, pos, meta, ptape: dict, tape: dict):
+        """llm_forward(ids, vis, pos, meta, tape) when the first P rows were already run with the same weights and saved
+        in `ptape` (the rollout's prompt prefill): only the remaining rows go through the GEMMs; their attention reads the
+        prefix keys/values from the saved projections.  Every per-row result is independent of how many rows a launch
+        covers, so the returned hidden states and the assembled `tape` are bit-identical to the full forward."""
+        d, W = self.dims, self.params
+        T, H = ids.shape[0], d.hidden
+        P = ptape["ids"].shape[0]
+        Tc = T - P
+        nh, nkv, hd = d.heads, d.kv_heads, d.head_dim
+        nq, nk = nh * hd, nkv * hd
+        vis_idx, n_vis = None, 0
+        if vis is not None:
+            vis_idx = torch.empty(T, dtype=I32, device=self.device)
+            cnt = torch.zeros(1, dtype=I32, device=self.device)
+            ops.call("sb_vision_index", ids, vis_idx, T, d.video_token_id, d.image_token_id, cnt)
+            n_vis = vis.shape[0]
+        pl = ptape["layers"]
+        x = torch.empty((T, H), device=self.device, dtype=BF16)
+        x[:P].copy_(pl[0]["x"])
+        ops.call("sb_embed_merge", ids[P:], None if vis_idx is None else vis_idx[P:], W["embed"], vis, x[P:], Tc, H, n_vis)
+        tape.update(ids=ids, vis_idx=vis_idx, n_vis=n_vis, pos=pos, meta=meta, layers=[])
+        pos_c = pos[:, P:].contiguous()
+        meta_c = meta[P:]
+        h = torch.empty((Tc, H), device=self.device, dtype=BF16)
+        for i in range(d.layers):
+            p, pt = f"l.{i}.", pl[i]
+            r1 = ops.rmsnorm_fwd(x[P:], W[p + "ln1_w"], d.rms_eps, save_stats=True, out=h)
+            qkv = torch.empty((T, d.qkv_dim), device=self.device, dtype=BF16)
+            qkv[:P].copy_(pt["qkv"])
+            ops.gemm(h, W[p + "qkv_w"], bias=W[p + "qkv_b"], out=qkv[P:])
+            ops.mrope(qkv[P:], pos_c, nh, nkv, hd, d.rope_theta, d.mrope_section)
+            a = torch.empty((T, nq), device=self.device, dtype=BF16)
+            a[:P].copy_(pt["a"])
+            _, lse_c = ops.attn_fwd(qkv[P:, :nq], qkv[:, nq:nq + nk], qkv[:, nq + nk:], meta_c, nh, nkv, hd, out=a[P:],
+                                    save_lse=True, Tk=T)
+            x2 = torch.empty((T, H), device=self.device, dtype=BF16)
+            x2[:P].copy_(pt["x2"])
+            ops.gemm(a[P:], W[p + "o_w"], residual=x[P:], out=x2[P:])
+            r3 = ops.rmsnorm_fwd(x2[P:], W[p + "ln2_w"], d.rms_eps, save_stats=True, out=h)
+            gu = torch.empty((T, 2 * d.inter), device=self.device, dtype=BF16)
+            gu[:P].copy_(pt["gu"])
+            act = ops.gemm(h, W[p + "gu_w"], epilogue=EPI_SWIGLU, aux=gu[P:])
+            x3 = torch.empty((T, H), device=self.device, dtype=BF16)
+            x3[:P].copy_(pl[i + 1]["x"] if i + 1 < d.layers else ptape["x_last"])
+            ops.gemm(act, W[p + "down_w"], residual=x2[P:], out=x3[P:])
+            tape["layers"].append(dict(x=x, s1=torch.cat([pt["s1"], r1[1]]), qkv=qkv, a=a,
+                                       lse=torch.cat([pt["lse"], lse_c], dim=1), x2=x2, s2=torch.cat([pt["s2"], r3[1]]),
+                                       gu=gu))
+            pl[i] = None          # the prefix copy of this layer is no longer needed
+            x = x3
+            del act
+        rf = ops.rmsnorm_fwd(x, W["norm_w"], d.rms_eps, save_stats=True)
+        tape.update(x_last=x, sf=rf[1])
+        return rf[0]
+
     def llm_backward(self, tape: dict, d_hf, grads: GradStore, want_d_vis=True):
         d, W, G = self.dims, self.params, grads
         T, H, I = tape["ids"].shape[0], d.hidden, d.inter
@@ -707,7 +766,18 @@ class Qwen2VLB200:
         else:
             vis = self.vit_forward(pixel_values, grid_thw, vtape) if pixel_values is not None else None
         mark("vit_fwd")
-        hf = self.llm_forward(batch.ids, vis, batch.pos, batch.meta, ltape)
+        ptape = None
+        if vit_cache is not None and vit_cache.get("llm_tape") is not None and batch.prompt_ids_host is not None:
+            # the rollout's prefill ran these prompt rows with the same weights: reuse them if prompt and positions agree
+            # (they differ e.g. when Qwen2.5-VL's rollout saw second_per_grid_ts and the scoring does not, TRN:519-520)
+            if (vit_cache["pixels"] is pixel_values and torch.equal(vit_cache["prompt_ids"], batch.prompt_ids_host)
+                    and torch.equal(vit_cache["prompt_pos"], batch.prompt_pos_host)):
+                ptape = vit_cache["llm_tape"]
+        if ptape is not None:
+            hf = self.llm_forward_from_prefix(batch.ids, vis, batch.pos, batch.meta, ptape, ltape)
+            vit_cache["llm_tape"] = None
+        else:
+            hf = self.llm_forward(batch.ids, vis, batch.pos, batch.meta, ltape)
         mark("llm_fwd")
         hsel = torch.empty((R, H), device=self.device, dtype=BF16)
         ops.call("sb_gather_rows", hf, batch.rows, hsel, R, H)
@@ -1135,13 +1205,15 @@ class Qwen2VLB200:
             if keep_vit_tape and k == 0 and pix is not None:
                 # the update that follows a rollout runs the SAME vision tower on the SAME pixels (one update per
                 # rollout, TRN:526-528): keep its output and saved activations instead of recomputing the forward
-                vtape = {}
+                vtape, ptape = {}, {}
                 vis = self.vit_forward(pix, video_grid_thw, vtape)
-                self.vit_cache = dict(pixels=pix, vis=vis, tape=vtape)
+                self.vit_cache = dict(pixels=pix, vis=vis, tape=vtape, llm_tape=ptape, prompt_ids=ids.cpu().long(),
+                                      prompt_pos=pos)
             else:
+                ptape = None
                 vis = self.vit_forward(pix, video_grid_thw) if pix is not None else None
             kv = [(st["kp"][k][i], st["vp"][k][i]) for i in range(d.layers)]
-            hf = self.llm_forward(ids_dev, vis, pos_dev, meta, kv_out=kv)
+            hf = self.llm_forward(ids_dev, vis, pos_dev, meta, tape=ptape, kv_out=kv)
             # first token: same distribution for every row of a group, independent draws
             r0, r1 = (0, G1) if k == 0 else (G1, R)
             st["xn"][r0:r1].copy_(hf[P - 1][None].expand(r1 - r0, -1))

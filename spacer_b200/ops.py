@@ -193,14 +193,15 @@ def attn_args(q, k, v, o, meta, n_heads, n_kv_heads, head_dim, scale, lse=None, 
     return a
 
 
-def attn_fwd(q, k, v, meta, n_heads, n_kv_heads, head_dim, scale=None, out=None, save_lse=False):
-    """q/k/v are column views into a fused projection buffer (row stride = buffer width)."""
+def attn_fwd(q, k, v, meta, n_heads, n_kv_heads, head_dim, scale=None, out=None, save_lse=False, Tk=0):
+    """q/k/v are column views into a fused projection buffer (row stride = buffer width).  Tk > 0: the key/value views
+    hold Tk rows while q (and meta, whose key indices are absolute) cover only the last q.shape[0] of them."""
     T = q.shape[0]
     _req(meta, torch.int32, "meta")
     scale = head_dim ** -0.5 if scale is None else scale
     o = out if out is not None else torch.empty((T, n_heads * head_dim), device=q.device, dtype=torch.bfloat16)
     lse = torch.empty((n_heads, T), device=q.device, dtype=torch.float32) if save_lse else None
-    a = attn_args(q, k, v, o, meta, n_heads, n_kv_heads, head_dim, scale, lse)
+    a = attn_args(q, k, v, o, meta, n_heads, n_kv_heads, head_dim, scale, lse, Tk=Tk)
     check(_lib.load().sb_attn_fwd(C.byref(a), _stream()), "sb_attn_fwd")
     return (o, lse) if save_lse else o
 
