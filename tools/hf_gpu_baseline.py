@@ -20,9 +20,44 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 import bench  # noqa: E402
-from oracle import grpo_ref as GR  # noqa: E402  (loss math restatement; CPU/GPU agnostic torch code)
-from oracle import qwen2vl_ref as R  # noqa: E402
-from oracle.make_golden import hf_config  # noqa: E402
+from spacer_b200 import config as mcfg  # noqa: E402  (dimensions and host-side position ids only; no kernels)
+from spacer_b200.model import rope_index  # noqa: E402
+
+
+def hf_config(d):
+    from transformers import Qwen2VLConfig
+    return Qwen2VLConfig(
+        text_config=dict(hidden_size=d.hidden, num_hidden_layers=d.layers, num_attention_heads=d.heads,
+                         num_key_value_heads=d.kv_heads, intermediate_size=d.inter, vocab_size=d.vocab,
+                         rms_norm_eps=d.rms_eps,
+                         rope_parameters={"rope_type": "default", "rope_theta": d.rope_theta,
+                                          "mrope_section": list(d.mrope_section)},
+                         tie_word_embeddings=d.tie, max_position_embeddings=32768, use_sliding_window=False,
+                         bos_token_id=d.pad_id, eos_token_id=d.eos_id, pad_token_id=d.pad_id),
+        vision_config=dict(depth=d.v_depth, embed_dim=d.v_embed, hidden_size=d.hidden, num_heads=d.v_heads,
+                           mlp_ratio=d.v_mlp // d.v_embed, patch_size=d.patch, temporal_patch_size=d.t_patch,
+                           spatial_merge_size=d.merge, in_channels=d.in_ch, hidden_act="quick_gelu"),
+        image_token_id=d.image_token_id, video_token_id=d.video_token_id,
+        vision_start_token_id=d.vision_start_id, vision_end_token_id=d.vision_end_id, tie_word_embeddings=d.tie)
+
+
+def per_token_logps(logits, input_ids):
+    """SGRLVRTrainer._get_per_token_logps (SG_RLVR_trainer.py:353-366), verbatim structure: per-row log_softmax + gather."""
+    logits = logits[:, :-1, :]
+    ids = input_ids[:, 1:]
+    out = []
+    for lr, ir in zip(logits, ids):
+        lp = lr.log_softmax(dim=-1)
+        out.append(torch.gather(lp, dim=1, index=ir.unsqueeze(1)).squeeze(1))
+    return torch.stack(out)
+
+
+def grpo_loss(lp, ref_lp, adv, mask, beta):
+    """SG_RLVR_trainer.py:551-552, 640-643."""
+    x = torch.clamp(ref_lp - lp, -10, 10)
+    kl = torch.exp(x) - x - 1
+    per_tok = -(torch.exp(lp - lp.detach()) * adv.unsqueeze(1) - beta * kl)
+    return ((per_tok * mask).sum(1) / mask.sum(1)).mean()
 
 
 def main():
@@ -37,7 +72,7 @@ def main():
     cfg = dict(bench.CONFIGS[a.config])
     if a.completion:
         cfg["C"] = a.completion
-    d = {"7b": R.dims_7b, "2b": R.dims_2b, "tiny": R.dims_tiny}[cfg["preset"]]()
+    d = mcfg.PRESETS[cfg["preset"]]()
     dev = torch.device(a.device)
     dt = torch.bfloat16 if dev.type == "cuda" else torch.float32
     hc = hf_config(d)
@@ -51,7 +86,7 @@ def main():
     model.gradient_checkpointing_enable()
     model.config.use_cache = True
     opt = torch.optim.AdamW(model.parameters(), lr=1e-6, weight_decay=0.01, fused=dev.type == "cuda")
-    ex = bench.synth_example(_dims_like(d), cfg, 1234)
+    ex = bench.synth_example(d, cfg, 1234)
     pix = ex["pixel_values_host"].to(dev, dt)
     grid = ex["video_grid_thw"].to(dev)
     ids = ex["input_ids"].to(dev)
@@ -78,25 +113,29 @@ def main():
         sync(); t["rollout"] = time.perf_counter() - t0
         full = out                                            # [G, P + C]
         mmf = ((full == d.video_token_id).long() * 2 + (full == d.image_token_id).long())
-        pos = R.rope_index_classic(full.cpu(), grid.cpu().repeat(G, 1), d).to(dev)
+        pos = torch.stack([rope_index(row, grid.cpu(), d, "classic")[0] for row in full.cpu()], dim=1).to(dev)
         pixG, gridG = pix.repeat(G, 1), grid.repeat(G, 1)
         t0 = time.perf_counter()
         with torch.inference_mode():
             rl = ref(input_ids=full, pixel_values_videos=pixG, video_grid_thw=gridG, position_ids=pos, mm_token_type_ids=mmf,
                      use_cache=False).logits
-            ref_lp = R.per_token_logps(rl, full)[:, P - 1:]
+            ref_lp = per_token_logps(rl, full)[:, P - 1:]
             del rl
         sync(); t["ref_scoring"] = time.perf_counter() - t0
         t0 = time.perf_counter()
         model.train()
         logits = model(input_ids=full, pixel_values_videos=pixG, video_grid_thw=gridG, position_ids=pos, mm_token_type_ids=mmf,
                        use_cache=False).logits
-        lp = R.per_token_logps(logits, full)[:, P - 1:]
+        lp = per_token_logps(logits, full)[:, P - 1:]
         del logits
         comp = full[:, P:]
-        mask = GR.completion_mask(comp.cpu(), d.eos_id).to(dev)
-        adv, _ = GR.advantages(torch.linspace(0.0, 2.0, G), G)
-        loss, _ = GR.grpo_loss(lp.float(), ref_lp.float().clone(), adv.to(dev), mask, 0.04)
+        is_eos = comp == d.eos_id                                             # TRN:493-498
+        eos_idx = torch.full((G,), comp.shape[1], dtype=torch.long, device=dev)
+        eos_idx[is_eos.any(1)] = is_eos.int().argmax(1)[is_eos.any(1)]
+        mask = (torch.arange(comp.shape[1], device=dev)[None] <= eos_idx[:, None]).int()
+        rewards = torch.linspace(0.0, 2.0, G, device=dev)
+        adv = (rewards - rewards.mean()) / (rewards.std() + 1e-4)             # TRN:632-638
+        loss = grpo_loss(lp.float(), ref_lp.float().clone(), adv, mask, 0.04)
         loss.backward()
         torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0)
         opt.step()
@@ -117,11 +156,6 @@ def main():
                       "s_per_step": round(wall, 3), "samples_per_s": round(G / wall, 4),
                       "rollout_tok_per_s": round((G + G // 2) * C / (tot["rollout"] / a.steps), 1),
                       "phase_s": {k: round(v / a.steps, 3) for k, v in tot.items()}}))
-
-
-def _dims_like(d):
-    """bench.synth_example reads spacer_b200.config.ModelDims-style attributes; the oracle Dims has the same names."""
-    return d
 
 
 if __name__ == "__main__":
