@@ -3,6 +3,8 @@
 //           B = the 16 activation rows [16 x 64] (2 KB), 4 x tcgen05.mma M=128 N=16 K=16 per stage
 //   mode 1: activations as A: A = [64 rows (16 valid) x 64 k], B = weight tile [128 x 64], 4 x tcgen05.mma M=64 N=128 K=16
 //   mode 2: no MMA (the consumer frees the stage at once) -- the load path alone
+//   mode 3: swap-AB MMAs as in mode 0, but the activation tile is resident (loaded once): ONE TMA per stage
+//   mode 4: activations-as-A MMAs as in mode 1 with the resident activation tile
 // Same TMA boxes and 8-stage ring in all modes; the weights are streamed from a 1.09 GB buffer (> L2).
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I spacer_b200/csrc -I include \
 //        -o tools/labs/ingest_mma_lab tools/labs/ingest_mma_lab.cu -lcuda
@@ -43,9 +45,10 @@ lab_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       const int mt = t / k_tiles, kt = t % k_tiles;
       mbar_wait(empty0 + 8 * stage, phase ^ 1);
-      mbar_expect_tx(full0 + 8 * stage, W_BYTES + 2048);
+      const bool load_x = mode < 3 || t == (int)blockIdx.x;      // modes 3/4: the activation tile is loaded once
+      mbar_expect_tx(full0 + 8 * stage, W_BYTES + (load_x ? 2048 : 0));
       tma_load_2d(sbase + stage * STAGE, &tmW, full0 + 8 * stage, kt * 64, mt * 128);
-      tma_load_2d(sbase + stage * STAGE + W_BYTES, &tmX, full0 + 8 * stage, kt * 64, 0);
+      if (load_x) tma_load_2d(sbase + stage * STAGE + W_BYTES, &tmX, full0 + 8 * stage, kt * 64, 0);
       if (++stage == NST) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1 && lane == 0) {   // consumer
@@ -55,14 +58,14 @@ lab_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUte
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       mbar_wait(full0 + 8 * stage, phase);
       tc_fence_after();
-      const uint32_t sw = sbase + stage * STAGE, sx = sw + W_BYTES;
+      const uint32_t sw = sbase + stage * STAGE, sx = (mode >= 3 ? sbase : sw) + W_BYTES;   // resident tile: stage 0's
       if (mode == 2) {
         mbar_arrive(empty0 + 8 * stage);
       } else {
         const uint64_t wdesc = umma_desc_sw128(sw, 0, 1024), xdesc = umma_desc_sw128(sx, 0, 1024);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          if (mode == 0) tc_mma_bf16(tmem_base, wdesc + (uint64_t)(k * 2), xdesc + (uint64_t)(k * 2), idesc_swap, (first && k == 0) ? 0u : 1u);
+          if (mode == 0 || mode == 3) tc_mma_bf16(tmem_base, wdesc + (uint64_t)(k * 2), xdesc + (uint64_t)(k * 2), idesc_swap, (first && k == 0) ? 0u : 1u);
           else tc_mma_bf16(tmem_base, xdesc + (uint64_t)(k * 2), wdesc + (uint64_t)(k * 2), idesc_actA, (first && k == 0) ? 0u : 1u);
         }
         first = false;
@@ -108,7 +111,7 @@ int main() {
   CK(cudaFuncSetAttribute(lab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   const int grids[] = {148, 112, 74, 37};
-  for (int mode = 0; mode < 3; ++mode)
+  for (int mode = 0; mode < 5; ++mode)
     for (int g : grids) {
       lab_kernel<<<g, 96, smem>>>(tmW, tmX, mode, n_tiles, k_tiles);
       CK(cudaDeviceSynchronize());
