@@ -761,8 +761,10 @@ class Qwen2VLB200:
                 marks.append((name, e))
 
         mark("start")
-        if vit_cache is not None and pixel_values is not None and vit_cache["pixels"] is pixel_values:
+        if (vit_cache is not None and pixel_values is not None and vit_cache["pixels"] is pixel_values
+                and vit_cache.get("tape") is not None):
             vis, vtape = vit_cache["vis"], vit_cache["tape"]     # forward already done by the rollout (generate)
+            vit_cache["tape"] = None                             # single use: the backward frees it block by block
         else:
             vis = self.vit_forward(pixel_values, grid_thw, vtape) if pixel_values is not None else None
         mark("vit_fwd")
