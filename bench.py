@@ -286,6 +286,8 @@ def main():
     ap.add_argument("--moments-bf16", action="store_true")
     ap.add_argument("--no-temporal", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="gradient all-reduce after the backward instead of overlapped")
+    ap.add_argument("--no-zero1", action="store_true", help="N > 1: all-reduce + replicated AdamW instead of the default ZeRO-1 "
+                    "(reduce-scatter, AdamW on the own 1/N of the arena, all-gather of the bf16 weights)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -321,7 +323,7 @@ def main():
     RW.set_map_data(SYN_MAP)
     tcfg = GRPOConfig(num_generations=cfg["G"], max_completion_length=cfg["C"], min_new_tokens=cfg["C"],
                       temporal=not args.no_temporal, moments_bf16=args.moments_bf16, max_steps=1000,
-                      overlap_allreduce=not args.no_overlap)
+                      overlap_allreduce=not args.no_overlap, zero1=not args.no_zero1)
     trainer = SGRLVRTrainerB200(policy, ref, [RW.accuracy_reward, RW.format_reward], tcfg, synth_decode)
     ex = synth_example(dims, cfg, 1234 + rank)
     ex.pop("pixel_values_host")        # (the fp32 patch matrix the HF processor would hand over; not used here)
@@ -434,6 +436,7 @@ def main():
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": cfg["workload"], "parallelism": f"dp{world}", "inputs": "larger than L2 (14 GB of weights streamed per decode step); step input = uint8 video frames",
                        "adam_moments": "bf16" if args.moments_bf16 else "fp32", "temporal": tcfg.temporal,
+                       "grad_sync": ("zero1" if not args.no_zero1 else ("allreduce" if args.no_overlap else "overlapped allreduce")) if world > 1 else None,
                        "rollout_tok_per_s": (world * (toks / K) / (stats["rollout_ms"] / 1000.0)) if stats.get("rollout_ms") else None,
                        "tok_per_s_of_step": world * toks / (ms_res / 1000.0),
                        "rollout_ms_per_step": stats.get("rollout_ms"), "prefill_ms": stats.get("prefill_ms"),

@@ -54,20 +54,36 @@ class GRPOConfig:
     moments_bf16: bool = False      # fp32 moments like DeepSpeed unless memory forces otherwise
     min_new_tokens: int = 0         # = max_completion_length disables EOS (timing runs)
     overlap_allreduce: bool = True  # per-layer gradient buckets all-reduced during the backward (N > 1)
+    zero1: bool = False             # N > 1: shard the optimizer state (fp32 master + moments) over the ranks:
+                                    # reduce-scatter gradients -> AdamW on the own 1/N of the matrix arena -> all-gather
+                                    # the updated bf16 weights (what the reference gets from DeepSpeed, zero3.json)
 
 
 class AdamW:
     """AdamW over the flat arenas with fp32 master weights + global-norm clip (zero3.json:10-12 semantics)."""
 
-    def __init__(self, params: ParamStore, cfg: GRPOConfig):
-        self.p, self.cfg = params, cfg
+    def __init__(self, params: ParamStore, cfg: GRPOConfig, shard: tuple | None = None, group=None):
+        """shard = (rank, world): this rank owns elements [rank * n / world, (rank + 1) * n / world) of the matrix arena
+        (ZeRO-1); master weights and moments exist for that range only.  The small vector arena is replicated."""
+        self.p, self.cfg, self.group = params, cfg, group
         mdt = torch.bfloat16 if cfg.moments_bf16 else torch.float32
         dev = params.device
-        self.master = [torch.empty(params.sizes[k], device=dev, dtype=torch.float32) for k in ("mat", "vec")]
-        ops.call("sb_bf16_to_f32", params.mat, self.master[0], params.mat.numel())
+        n = params.sizes["mat"]
+        self.shard = None
+        self.lo, self.hi = 0, n
+        if shard is not None and shard[1] > 1:
+            rank, world = shard
+            if n % (world * 16) != 0:
+                raise ops.SpacerError(f"zero1: matrix arena of {n} elements does not split into {world} aligned shards")
+            per = n // world
+            self.shard, self.lo, self.hi = (rank, world), rank * per, (rank + 1) * per
+        n_own = self.hi - self.lo
+        sizes = {"mat": n_own, "vec": params.sizes["vec"]}
+        self.master = [torch.empty(sizes[k], device=dev, dtype=torch.float32) for k in ("mat", "vec")]
+        ops.call("sb_bf16_to_f32", params.mat[self.lo:self.hi], self.master[0], n_own)
         ops.call("sb_bf16_to_f32", params.vec, self.master[1], params.vec.numel())
-        self.m = [torch.zeros(params.sizes[k], device=dev, dtype=mdt) for k in ("mat", "vec")]
-        self.v = [torch.zeros(params.sizes[k], device=dev, dtype=mdt) for k in ("mat", "vec")]
+        self.m = [torch.zeros(sizes[k], device=dev, dtype=mdt) for k in ("mat", "vec")]
+        self.v = [torch.zeros(sizes[k], device=dev, dtype=mdt) for k in ("mat", "vec")]
         self.total_sq = torch.zeros(1, device=dev, dtype=torch.float32)
         self.t = 0
 
@@ -81,9 +97,14 @@ class AdamW:
         return c.learning_rate
 
     def grad_sumsq(self, grads: GradStore):
+        """Global sum of squares of the (already reduced) gradients.  Sharded: every rank sums its own slice of the matrix
+        arena (rank 0 adds the replicated vector arena) and one scalar all-reduce makes the total identical everywhere."""
         self.total_sq.zero_()
-        ops.call("sb_grad_sumsq", grads.mat, grads.mat.numel(), 0, self.total_sq)
-        ops.call("sb_grad_sumsq", grads.vec, grads.vec.numel(), 1, self.total_sq)
+        ops.call("sb_grad_sumsq", grads.mat[self.lo:self.hi], self.hi - self.lo, 0, self.total_sq)
+        if self.shard is None or self.shard[0] == 0:
+            ops.call("sb_grad_sumsq", grads.vec, grads.vec.numel(), 1, self.total_sq)
+        if self.shard is not None:
+            torch.distributed.all_reduce(self.total_sq, group=self.group)
         return self.total_sq
 
     def step(self, grads: GradStore, grad_scale: float = 1.0, sumsq_ready: bool = False):
@@ -93,7 +114,8 @@ class AdamW:
         lr = self.lr_at(self.t)
         self.t += 1
         mb = int(c.moments_bf16)
-        ops.call("sb_adamw_step", self.p.mat, self.master[0], self.m[0], self.v[0], grads.mat, self.p.mat.numel(), 0,
+        ops.call("sb_adamw_step", self.p.mat[self.lo:self.hi], self.master[0], self.m[0], self.v[0],
+                 grads.mat[self.lo:self.hi], self.hi - self.lo, 0,
                  mb, self.total_sq, lr, c.adam_beta1, c.adam_beta2, c.adam_eps, c.weight_decay, self.t,
                  c.max_grad_norm, grad_scale)
         ops.call("sb_adamw_step", self.p.vec, self.master[1], self.m[1], self.v[1], grads.vec, self.p.vec.numel(), 1,
@@ -113,10 +135,13 @@ class SGRLVRTrainerB200:
         self.model, self.ref_model, self.reward_funcs, self.cfg = model, ref_model, list(reward_funcs), cfg
         self.decode_completions = decode_completions
         self.grads = GradStore(model.params)
-        self.opt = AdamW(model.params, cfg)
         self.pg = process_group
+        self.zero1 = bool(cfg.zero1) and D.world_size(process_group) > 1
+        self.opt = AdamW(model.params, cfg, shard=(D.rank(process_group), D.world_size(process_group)) if self.zero1 else None,
+                         group=process_group)
         # data parallel: per-layer gradient buckets are all-reduced while the backward is still running
-        self.reducer = D.OverlappedGradReducer(self.grads.mat, self.grads.vec, process_group) if cfg.overlap_allreduce else None
+        self.reducer = (D.OverlappedGradReducer(self.grads.mat, self.grads.vec, process_group)
+                        if cfg.overlap_allreduce and not self.zero1 else None)
         if self.reducer is not None:
             self.grads.on_ready = self.reducer.ready
         self._metrics = defaultdict(list)
@@ -128,7 +153,12 @@ class SGRLVRTrainerB200:
         return D.world_size(self.pg)
 
     def _allreduce_grads(self):
-        if self.reducer is not None:
+        if self.zero1:
+            # every rank receives the sum of ITS slice of the matrix gradients (in place); the vector arena is replicated
+            o = self.opt
+            torch.distributed.reduce_scatter_tensor(self.grads.mat[o.lo:o.hi], self.grads.mat, group=self.pg)
+            torch.distributed.all_reduce(self.grads.vec, group=self.pg)
+        elif self.reducer is not None:
             self.reducer.finish()
         else:
             D.allreduce_sum_([self.grads.mat, self.grads.vec], group=self.pg)
@@ -262,6 +292,9 @@ class SGRLVRTrainerB200:
         self._allreduce_grads()
         mark("grad_allreduce")
         lr = self.opt.step(self.grads, grad_scale=1.0 / self._world())
+        if self.zero1:      # every rank publishes the slice of bf16 weights it owns (in place)
+            o = self.opt
+            torch.distributed.all_gather_into_tensor(m.params.mat, m.params.mat[o.lo:o.hi], group=self.pg)
         mark("adamw")
         self.global_step += 1
         # metrics (TRN:650-683), one gather per quantity like the reference but on a packed struct

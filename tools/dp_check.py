@@ -24,14 +24,14 @@ from spacer_b200.model import Qwen2VLB200  # noqa: E402
 from spacer_b200.trainer import GRPOConfig, SGRLVRTrainerB200  # noqa: E402
 
 
-def run(dims, cfg, overlap, steps, rank, dev):
+def run(dims, cfg, overlap, steps, rank, dev, zero1=False):
     policy = Qwen2VLB200(dims, dev)
     policy.params.init_random(seed=0)
     ref = Qwen2VLB200(dims, dev)
     ref.params.mat.copy_(policy.params.mat)
     ref.params.vec.copy_(policy.params.vec)
     tcfg = GRPOConfig(num_generations=cfg["G"], max_completion_length=cfg["C"], min_new_tokens=cfg["C"], temporal=True,
-                      learning_rate=1e-3, overlap_allreduce=overlap)    # large lr: updates must be visible in bf16
+                      learning_rate=1e-3, overlap_allreduce=overlap, zero1=zero1)    # large lr: updates visible in bf16
     tr = SGRLVRTrainerB200(policy, ref, [RW.accuracy_reward, RW.format_reward], tcfg, bench.synth_decode)
     ex = bench.synth_example(dims, cfg, 1234 + rank)
     ex.pop("pixel_values_host")
@@ -68,7 +68,15 @@ def main():
         dist.all_gather(vo, vec)
         res[overlap] = dict(mat=mat, vec=vec, moved=moved,
                             same_across_ranks=all(torch.equal(others[0], o) for o in others) and all(torch.equal(vo[0], o) for o in vo))
+    zmat, zvec, zmoved = run(dims, cfg, False, a.steps, rank, dev, zero1=True)
+    zo = [torch.empty_like(zmat) for _ in range(world)]
+    dist.all_gather(zo, zmat)
+    zv = [torch.empty_like(zvec) for _ in range(world)]
+    dist.all_gather(zv, zvec)
     out = {"preset": a.preset, "world": world, "steps": a.steps,
+           "zero1_ranks_identical": all(torch.equal(zo[0], o) for o in zo) and all(torch.equal(zv[0], o) for o in zv),
+           "zero1_max_abs_diff_vs_allreduce": float((zmat.float() - res[False]["mat"].float()).abs().max()),
+           "zero1_weights_changed": zmoved,
            "weights_changed": [res[False]["moved"], res[True]["moved"]],
            "ranks_identical_no_overlap": res[False]["same_across_ranks"], "ranks_identical_overlap": res[True]["same_across_ranks"],
            "overlap_equals_no_overlap": bool(torch.equal(res[False]["mat"], res[True]["mat"]) and torch.equal(res[False]["vec"], res[True]["vec"])),
