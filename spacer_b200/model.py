@@ -14,7 +14,12 @@ Algorithmic differences from the reference's executed path (same mathematics, SU
     prompt shared through the attention mask (every completion token sees the whole prompt + its own
     completion causally) -- identical to G independent causal sequences because the prompt rows are
     identical across copies and no padding mask is passed (TRN:357, Appendix B.1-2);
-  * the [.,V] logits are never materialised: lm_head -> online logsumexp -> gather in the GEMM epilogue.
+  * the [.,V] logits are never materialised: lm_head -> online logsumexp -> gather in the GEMM epilogue;
+  * the update that follows a rollout reuses the rollout's vision-tower forward and prompt prefill (same weights, same
+    inputs: `generate(keep_vit_tape=True)` -> `grpo_forward_backward(vit_cache=...)`, bit-identical gradients).
+Also here: the Qwen2.5-VL family (`dims.variant == "qwen2_5_vl"`: windowed RMSNorm/SwiGLU vision tower, temporal M-RoPE
+spacing), greedy decoding for evaluation, the SFT loss on the same kernels (`sft_forward_backward`), the drop-in
+`get_per_token_logps`, and HF checkpoint I/O (`from_pretrained` / `save_pretrained`, hub.py).
 """
 from __future__ import annotations
 
