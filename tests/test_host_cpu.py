@@ -231,3 +231,23 @@ def test_segment_and_embed_plans():
     assert vis_pos.tolist() == [3, 4]
     got = {int(dst[s]): order_pos[off[s]:off[s + 1]].tolist() for s in range(n)}
     assert got == {5: [0, 7, 8], 9: [1, 6], d.vision_start_id: [2], d.vision_end_id: [5]}
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to the GPU arm): one JSON line with the contract's
+    keys, same metric / unit as the GPU arm, e2e == value, zero copy bytes."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--config", "tiny", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["metric"] == "grpo_samples_per_sec" and line["unit"] == "samples/s"
+    assert line["value"] > 0 and line["e2e"]["value"] == line["value"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
