@@ -27,7 +27,7 @@ extern "C" {
 
 typedef struct CUstream_st* sb_stream_t;
 
-#define SB_ABI_VERSION 1
+#define SB_ABI_VERSION 2
 
 const char* sb_last_error(void);
 int sb_abi_version(void);
@@ -261,6 +261,30 @@ int sb_sample_top_p(const float* logits, long long ld, int R, int V, float top_p
 int sb_sample_greedy(const float* logits, long long ld, int R, int V, const int* step_ptr, int* finished,
                      int* out_tokens, int* out_ids, long long out_ld, int eos_id, int pad_id, int suppress_eos,
                      sb_stream_t stream);
+/* One sampler entry for every decoding mode generate() is called with (training rollouts: GenerationConfig(do_sample,
+ * top_p 0.95, temperature 1) -> with HF's default top_k = 50, SG_RLVR_trainer.py:277-302; evaluation: the checkpoint's
+ * generation_config.json (repetition_penalty 1.05, top_k 1) with temperature 0.01, SpaceR-Eval/data_utils/vsibench.py:174).
+ * Order of the transformations = HF's logits-processor list: repetition penalty (logits_process.py
+ * RepetitionPenaltyLogitsProcessor: score < 0 ? score * p : score / p for every token already in prompt + completion),
+ * temperature, top-k (ties at the k-th value are kept), top-p, multinomial.  A row is finished by ANY id of eos_ids.
+ * Values changed by penalty / temperature are rounded to bf16 again before the radix select (HF keeps fp32). */
+typedef struct sb_sample_args {
+  const float* logits; long long ld; int R; int V;
+  int mode;                         /* 0 = sample, 1 = greedy argmax (lowest index on ties)                        */
+  float top_p;                      /* (0, 1]; 1 disables the nucleus cut                                          */
+  int top_k;                        /* 0 disables                                                                  */
+  float temperature;                /* > 0                                                                         */
+  float repetition_penalty;         /* 1 disables; otherwise `seen` is required                                    */
+  unsigned int* seen; long long seen_ld; /* bitmap [R][seen_ld] words (bit t of row r: token t occurred); the
+                                       sampled token is OR-ed in.  NULL = no bookkeeping                           */
+  unsigned long long seed; const long long* seed_dev;
+  const int* step_ptr; int* finished; int* out_tokens; int* out_ids; long long out_ld; float* out_logprob;
+  int eos_ids[4]; int n_eos; int pad_id; int suppress_eos;
+} sb_sample_args;
+int sb_sample(const sb_sample_args* args, sb_stream_t stream);
+/* seen[r][ids[i]] = 1 for all i < n and r < rows (the prompt tokens count for the repetition penalty) */
+int sb_token_bitmap_set(const int* ids, int n, unsigned int* seen, long long seen_ld, int rows, int V,
+                        sb_stream_t stream);
 int sb_step_advance(int* step_ptr, sb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -95,6 +95,20 @@ class AttnArgs(C.Structure):
     ]
 
 
+class SampleArgs(C.Structure):
+    """sb_sample_args (include/spacer_b200.h)."""
+    _fields_ = [
+        ("logits", C.c_void_p), ("ld", C.c_longlong), ("R", C.c_int), ("V", C.c_int),
+        ("mode", C.c_int), ("top_p", C.c_float), ("top_k", C.c_int), ("temperature", C.c_float),
+        ("repetition_penalty", C.c_float),
+        ("seen", C.c_void_p), ("seen_ld", C.c_longlong),
+        ("seed", C.c_ulonglong), ("seed_dev", C.c_void_p),
+        ("step_ptr", C.c_void_p), ("finished", C.c_void_p), ("out_tokens", C.c_void_p), ("out_ids", C.c_void_p),
+        ("out_ld", C.c_longlong), ("out_logprob", C.c_void_p),
+        ("eos_ids", C.c_int * 4), ("n_eos", C.c_int), ("pad_id", C.c_int), ("suppress_eos", C.c_int),
+    ]
+
+
 _HEADER = Path(__file__).resolve().parent.parent / "include" / "spacer_b200.h"
 _CT = {"p": C.c_void_p, "i": C.c_int, "l": C.c_longlong, "f": C.c_float, "u": C.c_ulonglong, "s": C.c_void_p}
 

@@ -33,8 +33,10 @@ class ModelDims:
     video_token_id: int = 151656
     vision_start_id: int = 151652
     vision_end_id: int = 151653
-    eos_id: int = 151645
+    eos_id: int = 151645                  # the tokenizer's eos (<|im_end|>): what the completion mask looks for (TRN:489)
     pad_id: int = 151643
+    eos_ids: tuple = ()                   # every id that ends a rollout row (generation_config.json: [151645, 151643]);
+                                          # empty = (eos_id,)
     name: str = "Qwen2-VL-7B"
     # family: "qwen2_vl" (LayerNorm + QuickGELU ViT, per-frame attention) or "qwen2_5_vl" (RMSNorm + SwiGLU ViT with
     # windowed attention, modeling_qwen2_5_vl.py:345-520).  For qwen2_5_vl `v_mlp` is the ViT intermediate size (3420).

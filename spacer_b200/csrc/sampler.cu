@@ -44,6 +44,12 @@ SB_DEVICE void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
 struct SampleParams {
   const float* logits; long long ld; int V;
   float top_p;
+  int top_k;                // 0 = off (TopKLogitsWarper, logits_process.py: scores < k-th largest removed, ties kept)
+  float inv_temp;           // 1 / temperature (TemperatureLogitsWarper)
+  float rep_pen;            // repetition penalty (RepetitionPenaltyLogitsProcessor); 1 = off
+  const uint32_t* seen_r;   // bitmap [R][seen_ld] of the tokens already in prompt + completion (repetition penalty)
+  uint32_t* seen_w;         // same buffer, updated with the sampled token
+  long long seen_ld;
   unsigned long long seed;
   const long long* seed_dev;  // optional: overrides `seed` (lets one captured CUDA graph serve every rollout)
   const int* step_ptr;
@@ -51,9 +57,44 @@ struct SampleParams {
   int* out_tokens;          // [R]
   int* out_ids; long long out_ld;   // optional [R][out_ld], column = step
   float* out_logprob;       // optional [R]: log-prob of the sampled token under the filtered distribution
-  int eos_id, pad_id, suppress_eos;
+  int eos[4]; int n_eos;    // every id in the model's eos list finishes a row (generation/utils.py stopping criteria)
+  int pad_id, suppress_eos;
   int slice;                // elements per CTA
 };
+
+SB_DEVICE bool is_eos(const SampleParams& p, int tok) {
+  bool e = false;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) e |= (k < p.n_eos && tok == p.eos[k]);
+  return e;
+}
+
+// logit of token gi of `row` as the samplers see it: the model's bf16 logit, then (HF's processor order) repetition
+// penalty and temperature in fp32.  Transformed values are rounded to bf16 again (the radix select works on 16-bit keys;
+// HF keeps fp32 there: a deliberate deviation), untransformed ones are exactly the model's.
+SB_DEVICE float load_logit(const SampleParams& p, const float* lg, int row, int gi) {
+  float v = bf16_round(lg[gi]);
+  bool changed = false;
+  if (p.seen_r != nullptr && p.rep_pen != 1.f && ((p.seen_r[(long long)row * p.seen_ld + (gi >> 5)] >> (gi & 31)) & 1u)) {
+    v = v < 0.f ? v * p.rep_pen : v / p.rep_pen;
+    changed = true;
+  }
+  if (p.inv_temp != 1.f) { v *= p.inv_temp; changed = true; }
+  if (changed) v = bf16_round(v);
+  if (p.suppress_eos && is_eos(p, gi)) v = -INFINITY;
+  return v;
+}
+
+SB_DEVICE void emit_token(const SampleParams& p, int row, int step, int tok) {
+  const int fin = p.finished ? p.finished[row] : 0;
+  if (fin) tok = p.pad_id;
+  else {
+    if (is_eos(p, tok) && p.finished) p.finished[row] = 1;
+    if (p.seen_w) atomicOr(&p.seen_w[(long long)row * p.seen_ld + (tok >> 5)], 1u << (tok & 31));
+  }
+  p.out_tokens[row] = tok;
+  if (p.out_ids) p.out_ids[(long long)row * p.out_ld + step] = tok;
+}
 
 struct Shared {
   float part_f[4];          // [0] max, [1] Z, [2] kept mass
@@ -62,9 +103,11 @@ struct Shared {
   float scan_f[ST];
   int scan_i[ST];
   float g_hist[256];
+  int g_cnt[256];
   float wtot_f[NW + 1];
   int wtot_i[NW + 1];
   int b1, b2, sel, last;
+  int kb, kabove;
   float below;
 };
 
@@ -119,6 +162,21 @@ SB_DEVICE void find_bin(Shared* sh, float start, float thr, int* out_b, float* o
   __syncthreads();
 }
 
+// top-k: highest bin b (of sh->g_cnt) such that count(bins > b) < k <= count(bins >= b); above = count(bins > b).
+// Returns the total count; when total < k nothing is found (*out_b = -1).   (all threads call)
+SB_DEVICE int find_bin_top(Shared* sh, int k, int* out_b, int* out_above) {
+  const int tid = threadIdx.x;
+  const int bin = 255 - tid;
+  const int c = tid < 256 ? sh->g_cnt[bin] : 0;
+  int tot;
+  const int above = excl_scan_i(c, sh->wtot_i, tot);
+  if (tid == 0) { *out_b = -1; *out_above = 0; }
+  __syncthreads();
+  if (tid < 256 && above < k && above + c >= k) { *out_b = bin; *out_above = above; }
+  __syncthreads();
+  return tot;
+}
+
 SB_DEVICE bool kept_token(uint32_t k, uint32_t kstar, int& tie_rank, int n_drop) {
   if (k > kstar) return true;
   if (k < kstar) return false;
@@ -151,8 +209,7 @@ sample_kernel(const SampleParams p) {
   // ---- phase A: load slice (bf16-rounded), cluster max
   float mx = -INFINITY;
   for (int i = tid; i < n; i += ST) {
-    float v = bf16_round(lg[i0 + i]);
-    if (p.suppress_eos && i0 + i == p.eos_id) v = -INFINITY;
+    const float v = load_logit(p, lg, row, i0 + i);
     sl[i] = v;
     mx = fmaxf(mx, v);
   }
@@ -161,6 +218,48 @@ sample_kernel(const SampleParams p) {
   cluster.sync();
   float m = -INFINITY;
   for (int c = 0; c < CL; ++c) m = fmaxf(m, cluster.map_shared_rank(sh, c)->part_f[0]);
+
+  // ---- phase A2 (top_k > 0): two-level radix select of the k-th largest key by COUNT; everything strictly below it
+  // is removed (-inf) before the nucleus cut, ties at the k-th value stay (TopKLogitsWarper)
+  if (p.top_k > 0 && p.top_k < p.V) {
+    uint32_t kth_key = 0;
+    int want = p.top_k, hi_bin = -1;
+    for (int level = 0; level < 2; ++level) {
+      for (int i = tid; i < NW * 256; i += ST) wh_c[i] = 0;
+      __syncthreads();
+      for (int i = tid; i < n; i += ST) {
+        const float v = sl[i];
+        if (v == -INFINITY) continue;
+        const uint32_t k = key16(v);
+        if (level == 0) atomicAdd(&wh_c[warp * 256 + (k >> 8)], 1);
+        else if ((int)(k >> 8) == hi_bin) atomicAdd(&wh_c[warp * 256 + (k & 255)], 1);
+      }
+      __syncthreads();
+      if (tid < 256) {
+        int c = 0;
+        for (int w = 0; w < NW; ++w) c += wh_c[w * 256 + tid];
+        sh->hist_c[tid] = c;
+      }
+      cluster.sync();
+      if (tid < 256) {
+        int c = 0;
+        for (int q = 0; q < CL; ++q) c += cluster.map_shared_rank(sh, q)->hist_c[tid];
+        sh->g_cnt[tid] = c;
+      }
+      __syncthreads();
+      find_bin_top(sh, want, &sh->kb, &sh->kabove);
+      const int b = sh->kb, above = sh->kabove;
+      cluster.sync();   // remote reads of hist_c are done before the next level overwrites it
+      if (b < 0) { kth_key = 0; break; }          // fewer than k candidates: keep all (CTA- and cluster-uniform)
+      if (level == 0) { hi_bin = b; want -= above; }
+      else kth_key = ((uint32_t)hi_bin << 8) | (uint32_t)b;
+    }
+    for (int i = tid; i < n; i += ST) {
+      const float v = sl[i];
+      if (v != -INFINITY && key16(v) < kth_key) sl[i] = -INFINITY;
+    }
+    __syncthreads();
+  }
 
   // ---- phase B: Z and level-1 histogram (high 8 key bits) of probability mass
   for (int i = tid; i < NW * 256; i += ST) { wh_m[i] = 0.f; wh_c[i] = 0; }
@@ -300,12 +399,7 @@ sample_kernel(const SampleParams p) {
         run += e;
       }
       if (chosen < 0) { chosen = last_kept; chosen_e = last_e; }
-      int tok = i0 + chosen;
-      const int fin = p.finished ? p.finished[row] : 0;
-      if (fin) tok = p.pad_id;
-      else if (tok == p.eos_id && p.finished) p.finished[row] = 1;
-      p.out_tokens[row] = tok;
-      if (p.out_ids) p.out_ids[(long long)row * p.out_ld + step] = tok;
+      emit_token(p, row, step, i0 + chosen);
       if (p.out_logprob) p.out_logprob[row] = logf(chosen_e / kept_total);
     }
   }
@@ -317,9 +411,7 @@ sample_kernel(const SampleParams p) {
 // config, data_utils/vsibench.py:174; HF `do_sample=False`): token = argmax of the bf16-rounded logits, lowest index on
 // ties (torch.argmax); EOS / pad bookkeeping identical to sample_kernel.  One CTA per row.
 __global__ void __launch_bounds__(1024)
-greedy_kernel(const float* __restrict__ logits, long long ld, int V, const int* __restrict__ step_ptr,
-              int* __restrict__ finished, int* __restrict__ out_tokens, int* __restrict__ out_ids, long long out_ld,
-              int eos_id, int pad_id, int suppress_eos) {
+greedy_kernel(const SampleParams p) {
   pdl_launch_dependents();
   const int tr = (blockIdx.x == 0 && threadIdx.x == 0) ? sb_trace_begin(SB_TR_SAMPLE) : -1;
   pdl_wait();
@@ -327,12 +419,11 @@ greedy_kernel(const float* __restrict__ logits, long long ld, int V, const int* 
   __shared__ float s_v[32];
   __shared__ int s_i[32];
   const int row = blockIdx.x;
-  const float* lg = logits + (long long)row * ld;
+  const float* lg = p.logits + (long long)row * p.ld;
   float best = -INFINITY;
   int best_i = 0x7fffffff;
-  for (int i = threadIdx.x; i < V; i += blockDim.x) {
-    float v = bf16_round(lg[i]);
-    if (suppress_eos && i == eos_id) v = -INFINITY;
+  for (int i = threadIdx.x; i < p.V; i += blockDim.x) {
+    const float v = load_logit(p, lg, row, i);
     if (v > best) { best = v; best_i = i; }       // ascending i per thread: the first maximum is kept
   }
 #pragma unroll
@@ -354,17 +445,19 @@ greedy_kernel(const float* __restrict__ logits, long long ld, int V, const int* 
       const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
       if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
     }
-    if (lane == 0) {
-      const int step = *step_ptr;
-      int tok = best_i;
-      const int fin = finished ? finished[row] : 0;
-      if (fin) tok = pad_id;
-      else if (tok == eos_id && finished) finished[row] = 1;
-      out_tokens[row] = tok;
-      if (out_ids) out_ids[(long long)row * out_ld + step] = tok;
-    }
+    if (lane == 0) emit_token(p, row, *p.step_ptr, best_i);
   }
   sb_trace_mark(tr, 2);
+}
+
+// bitmap[row][tok] = 1 for every token of ids[0..n) and every row (the prompt is shared by the rows of a rollout)
+__global__ void bitmap_set_kernel(const int* __restrict__ ids, int n, uint32_t* __restrict__ seen, long long seen_ld,
+                                  int rows, int V) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int tok = ids[i];
+  if (tok < 0 || tok >= V) return;
+  for (int r = 0; r < rows; ++r) atomicOr(&seen[(long long)r * seen_ld + (tok >> 5)], 1u << (tok & 31));
 }
 
 __global__ void step_advance_kernel(int* step_ptr) {
@@ -380,35 +473,78 @@ __global__ void step_advance_kernel(int* step_ptr) {
 
 SB_DEFINE_TRACE_SETTER(sb_trace_set_sampler)
 
+static int fill_params(const sb_sample_args* a, SampleParams& p, const char* who) {
+  SB_REQUIRE(a && a->logits && a->step_ptr && a->out_tokens && a->R > 0 && a->V > 0, "%s: bad arguments", who);
+  SB_REQUIRE(a->n_eos >= 0 && a->n_eos <= 4, "%s: at most 4 eos ids, got %d", who, a->n_eos);
+  SB_REQUIRE(a->temperature > 0.f, "%s: temperature must be > 0, got %f", who, a->temperature);
+  SB_REQUIRE(a->repetition_penalty > 0.f, "%s: repetition_penalty must be > 0, got %f", who, a->repetition_penalty);
+  SB_REQUIRE(a->repetition_penalty == 1.f || a->seen != nullptr, "%s: repetition_penalty needs the token bitmap", who);
+  SB_REQUIRE(a->seen == nullptr || a->seen_ld * 32 >= a->V, "%s: token bitmap narrower than the vocabulary", who);
+  p.logits = a->logits; p.ld = a->ld; p.V = a->V; p.top_p = a->top_p; p.top_k = a->top_k;
+  p.inv_temp = 1.f / a->temperature; p.rep_pen = a->repetition_penalty;
+  p.seen_r = a->seen; p.seen_w = a->seen; p.seen_ld = a->seen_ld;
+  p.seed = a->seed; p.seed_dev = a->seed_dev; p.step_ptr = a->step_ptr;
+  p.finished = a->finished; p.out_tokens = a->out_tokens; p.out_ids = a->out_ids; p.out_ld = a->out_ld;
+  p.out_logprob = a->out_logprob;
+  for (int k = 0; k < 4; ++k) p.eos[k] = k < a->n_eos ? a->eos_ids[k] : -1;
+  p.n_eos = a->n_eos; p.pad_id = a->pad_id; p.suppress_eos = a->suppress_eos;
+  p.slice = ((a->V + CL - 1) / CL + 3) & ~3;
+  return 0;
+}
+
+extern "C" int sb_sample(const sb_sample_args* a, sb_stream_t stream) {
+  SampleParams p;
+  if (fill_params(a, p, "sb_sample")) return 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (a->mode == 1) {
+    SB_CUDA(sb_launch(greedy_kernel, dim3(a->R), dim3(1024), 0, st, sb_pdl_enabled(), p));
+    return sb_check_launch("sb_sample(greedy)");
+  }
+  SB_REQUIRE(a->mode == 0, "sb_sample: mode must be 0 (sample) or 1 (greedy)");
+  SB_REQUIRE(a->top_p > 0.f && a->top_p <= 1.f, "sb_sample: top_p must be in (0,1], got %f", a->top_p);
+  SB_REQUIRE(a->top_k >= 0, "sb_sample: top_k must be >= 0");
+  const size_t smem = ((sizeof(Shared) + 15) & ~(size_t)15) + (size_t)NW * 256 * 8 + (size_t)p.slice * 4;
+  SB_REQUIRE(smem <= 220 * 1024, "sb_sample: vocabulary %d too large for the 8-CTA cluster sampler", a->V);
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    SB_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  SB_CUDA(sb_launch(sample_kernel, dim3(a->R * CL), dim3(ST), smem, st, sb_pdl_enabled(), p));
+  return sb_check_launch("sb_sample");
+}
+
+extern "C" int sb_token_bitmap_set(const int* ids, int n, unsigned int* seen, long long seen_ld, int rows, int V,
+                                   sb_stream_t stream) {
+  SB_REQUIRE(ids && seen && n >= 0 && rows > 0 && seen_ld * 32 >= V, "sb_token_bitmap_set: bad arguments");
+  if (n == 0) return 0;
+  SB_CUDA(sb_launch(bitmap_set_kernel, dim3((n + 255) / 256), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), false,
+                    ids, n, seen, seen_ld, rows, V));
+  return sb_check_launch("sb_token_bitmap_set");
+}
+
+// the round-1 entry points: one eos id, no top-k / temperature / repetition penalty
 extern "C" int sb_sample_greedy(const float* logits, long long ld, int R, int V, const int* step_ptr, int* finished,
                                 int* out_tokens, int* out_ids, long long out_ld, int eos_id, int pad_id, int suppress_eos,
                                 sb_stream_t stream) {
-  SB_REQUIRE(logits && step_ptr && out_tokens && R > 0 && V > 0, "sb_sample_greedy: bad arguments");
-  SB_CUDA(sb_launch(greedy_kernel, dim3(R), dim3(1024), 0, reinterpret_cast<cudaStream_t>(stream), sb_pdl_enabled(), logits,
-                    ld, V, step_ptr, finished, out_tokens, out_ids, out_ld, eos_id, pad_id, suppress_eos));
-  return sb_check_launch("sb_sample_greedy");
+  sb_sample_args a = {};
+  a.logits = logits; a.ld = ld; a.R = R; a.V = V; a.mode = 1; a.top_p = 1.f; a.temperature = 1.f;
+  a.repetition_penalty = 1.f; a.step_ptr = step_ptr; a.finished = finished; a.out_tokens = out_tokens;
+  a.out_ids = out_ids; a.out_ld = out_ld; a.eos_ids[0] = eos_id; a.n_eos = 1; a.pad_id = pad_id;
+  a.suppress_eos = suppress_eos;
+  return sb_sample(&a, stream);
 }
 
 extern "C" int sb_sample_top_p(const float* logits, long long ld, int R, int V, float top_p, unsigned long long seed,
                                const int* step_ptr, int* finished, int* out_tokens, int* out_ids, long long out_ld,
                                float* out_logprob, int eos_id, int pad_id, int suppress_eos, const long long* seed_dev,
                                sb_stream_t stream) {
-  SB_REQUIRE(logits && step_ptr && out_tokens && R > 0 && V > 0, "sb_sample_top_p: bad arguments");
-  SB_REQUIRE(top_p > 0.f && top_p <= 1.f, "sb_sample_top_p: top_p must be in (0,1], got %f", top_p);
-  SampleParams p;
-  p.logits = logits; p.ld = ld; p.V = V; p.top_p = top_p; p.seed = seed; p.seed_dev = seed_dev; p.step_ptr = step_ptr;
-  p.finished = finished; p.out_tokens = out_tokens; p.out_ids = out_ids; p.out_ld = out_ld;
-  p.out_logprob = out_logprob; p.eos_id = eos_id; p.pad_id = pad_id; p.suppress_eos = suppress_eos;
-  p.slice = ((V + CL - 1) / CL + 3) & ~3;
-  const size_t smem = ((sizeof(Shared) + 15) & ~(size_t)15) + (size_t)NW * 256 * 8 + (size_t)p.slice * 4;
-  SB_REQUIRE(smem <= 220 * 1024, "sb_sample_top_p: vocabulary %d too large for the 8-CTA cluster sampler", V);
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    SB_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
-  }
-  SB_CUDA(sb_launch(sample_kernel, dim3(R * CL), dim3(ST), smem, reinterpret_cast<cudaStream_t>(stream), sb_pdl_enabled(), p));
-  return sb_check_launch("sb_sample_top_p");
+  sb_sample_args a = {};
+  a.logits = logits; a.ld = ld; a.R = R; a.V = V; a.mode = 0; a.top_p = top_p; a.temperature = 1.f;
+  a.repetition_penalty = 1.f; a.seed = seed; a.seed_dev = seed_dev; a.step_ptr = step_ptr; a.finished = finished;
+  a.out_tokens = out_tokens; a.out_ids = out_ids; a.out_ld = out_ld; a.out_logprob = out_logprob;
+  a.eos_ids[0] = eos_id; a.n_eos = 1; a.pad_id = pad_id; a.suppress_eos = suppress_eos;
+  return sb_sample(&a, stream);
 }
 
 extern "C" int sb_step_advance(int* step_ptr, sb_stream_t stream) {

@@ -112,7 +112,17 @@ def from_pretrained(cls, path: str, device="cuda", rope_convention: str = "class
     with open(os.path.join(path, "config.json")) as f:
         cfg = json.load(f)
     dims = dims_from_hf_config(cfg, name_hint=path)
+    gen = {}
+    gpath = os.path.join(path, "generation_config.json")
+    if os.path.exists(gpath):       # the defaults model.generate() merges under the caller's options (utils.py:1693-1701)
+        with open(gpath) as f:
+            gen = {k: v for k, v in json.load(f).items() if not k.startswith("_") and k != "transformers_version"}
+        eos = gen.get("eos_token_id")
+        if isinstance(eos, (list, tuple)) and eos:
+            from dataclasses import replace
+            dims = replace(dims, eos_ids=tuple(int(e) for e in eos))
     m = cls(dims, device, rope_convention=rope_convention)
+    m.generation_config = gen
     sd = load_checkpoint_tensors(path)
     if dims.tie and "lm_head.weight" not in sd:
         sd["lm_head.weight"] = sd["model.language_model.embed_tokens.weight"]
@@ -127,6 +137,12 @@ def save_pretrained(model, path: str, max_shard_bytes: int = 5 << 30):
     os.makedirs(path, exist_ok=True)
     with open(os.path.join(path, "config.json"), "w") as f:
         json.dump(hf_config_from_dims(model.dims), f, indent=2)
+    gen = dict(getattr(model, "generation_config", None) or {})
+    if model.dims.eos_ids and "eos_token_id" not in gen:
+        gen["eos_token_id"] = list(model.dims.eos_ids)
+    if gen:
+        with open(os.path.join(path, "generation_config.json"), "w") as f:
+            json.dump(gen, f, indent=2)
     shards, cur, size = [], {}, 0
     for k, v in model.params.hf_items():
         if model.dims.tie and k == "lm_head.weight":

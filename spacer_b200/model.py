@@ -205,6 +205,21 @@ class PackedBatch:
     embed_plan: tuple = None   # (text positions, segment_plan(token id of the text positions), vision positions)
 
 
+@dataclass(frozen=True)
+class SamplingParams:
+    """What one sampler launch needs (sb_sample_args): the resolved generation options of a rollout."""
+    greedy: bool = False
+    top_p: float = 0.95
+    top_k: int = 0
+    temperature: float = 1.0
+    repetition_penalty: float = 1.0
+    eos_ids: tuple = (151645,)
+    pad_id: int = 151643
+
+    def key(self):
+        return (self.greedy, self.top_p, self.top_k, self.temperature, self.repetition_penalty, self.eos_ids, self.pad_id)
+
+
 def pack_prompt_completions(prompt_ids, completion_ids, grid_thw, dims: ModelDims, device, convention="classic",
                             second_per_grid_ts=None):
     prompt_ids = prompt_ids.reshape(-1).cpu().long()
@@ -263,6 +278,13 @@ class GradStore:
                 hi = off + n if hi is None else max(hi, off + n)
         return lo, hi
 
+    def zero_range(self, prefix: str):
+        """Zero the matrix gradients of every tensor under `prefix` (a sub-network that took no part in this step, e.g.
+        the vision tower on a text-only prompt: its GEMM epilogues did not overwrite last step's values)."""
+        lo, hi = self.mat_range(prefix)
+        if lo is not None:
+            self.mat[lo:hi].zero_()
+
     def ready(self, prefix: str):
         if self.on_ready is not None:
             lo, hi = self.mat_range(prefix)
@@ -287,6 +309,7 @@ class Qwen2VLB200:
         # the attributes of an HF module the reference trainer touches (SG_RLVR_trainer.py:156, 193, 234, 312)
         from . import hub
         self.config = hub.make_config_namespace(dims)
+        self.generation_config = {}      # the checkpoint's generation_config.json (hub.from_pretrained fills it)
         self.warnings_issued = {}
 
     # ---- HF-like surface -------------------------------------------------------------------------
@@ -832,6 +855,8 @@ class Qwen2VLB200:
         del ltape, d_hf
         if vis is not None:
             self.vit_backward(vtape, d_vis, grads)
+        else:
+            grads.zero_range("v.")
         mark("vit_bwd")
         grads.ready("v.")         # the whole vision tower as one bucket (1.3 GB of bf16 at 7B)
         return dict(loss=out2[0], mean_kl=out2[1], logps=lp.view(G_, C), mask=mask.view(G_, C), lengths=row_len)
@@ -893,6 +918,8 @@ class Qwen2VLB200:
         d_vis = self.llm_backward(ltape, d_hf, grads)
         if vis is not None:
             self.vit_backward(vtape, d_vis, grads)
+        else:
+            grads.zero_range("v.")
         grads.ready("v.")
         return dict(loss=loss, n_tokens=R, logps=lp)
 
@@ -997,6 +1024,7 @@ class Qwen2VLB200:
             finished=torch.zeros(RP, device=dev, dtype=I32),
             out_ids=torch.zeros((R, c_max), device=dev, dtype=I32),
             seed=torch.zeros(1, device=dev, dtype=torch.int64),
+            seen=torch.zeros((RP, (d.vocab + 31) // 32), device=dev, dtype=I32),   # token bitmap (repetition penalty)
             # fused-epilogue chain (sb_dec_fuse): x * w_norm and per-128-column-tile sums of squares
             xw=torch.zeros((RP, H), device=dev, dtype=BF16),
             ssq=torch.zeros(((H + 127) // 128, RP), device=dev, dtype=F32),
@@ -1033,21 +1061,31 @@ class Qwen2VLB200:
     # tops out at ~48 GB/s -- the step gets slower (3.30 vs 3.16 ms, profiles/r01_decode_fused_epilogues.md).
     decode_fused = os.environ.get("SB_DECODE_FUSED") is not None
 
-    def _sample(self, st, top_p, suppress_eos):
-        """Next token per row from st["logits"]: top-p sampling (TRN:277-302 generation configs) or, for top_p <= 0,
-        greedy argmax (evaluation, SpaceR-Eval/data_utils/vsibench.py:174)."""
+    def _sample(self, st, sp, suppress_eos):
+        """Next token per row from st["logits"] under the sampling parameters `sp` (SamplingParams): HF's processor chain
+        repetition penalty -> temperature -> top-k -> top-p -> multinomial (TRN:277-302 generation configs), or greedy
+        argmax (evaluation, SpaceR-Eval/data_utils/vsibench.py:174)."""
+        import ctypes
         d, R = self.dims, st["R"]
-        if top_p <= 0.0:
-            ops.call("sb_sample_greedy", st["logits"], d.vocab, R, d.vocab, st["step"], st["finished"], st["tokens"],
-                     st["out_ids"], st["c_max"], d.eos_id, d.pad_id, int(suppress_eos))
-        else:
-            ops.call("sb_sample_top_p", st["logits"], d.vocab, R, d.vocab, float(top_p), 0, st["step"], st["finished"],
-                     st["tokens"], st["out_ids"], st["c_max"], None, d.eos_id, d.pad_id, int(suppress_eos), st["seed"])
+        a = ops.SampleArgs()
+        a.logits, a.ld, a.R, a.V = st["logits"].data_ptr(), d.vocab, R, d.vocab
+        a.mode = 1 if sp.greedy else 0
+        a.top_p, a.top_k, a.temperature = float(sp.top_p), int(sp.top_k), float(sp.temperature)
+        a.repetition_penalty = float(sp.repetition_penalty)
+        if sp.repetition_penalty != 1.0:
+            a.seen, a.seen_ld = st["seen"].data_ptr(), st["seen"].shape[1]
+        a.seed, a.seed_dev = 0, st["seed"].data_ptr()
+        a.step_ptr, a.finished, a.out_tokens = st["step"].data_ptr(), st["finished"].data_ptr(), st["tokens"].data_ptr()
+        a.out_ids, a.out_ld = st["out_ids"].data_ptr(), st["c_max"]
+        for k, e in enumerate(sp.eos_ids):
+            a.eos_ids[k] = int(e)
+        a.n_eos, a.pad_id, a.suppress_eos = len(sp.eos_ids), int(sp.pad_id), int(suppress_eos)
+        ops.check(ops._lib.load().sb_sample(ctypes.byref(a), ops._stream()), "sb_sample")
 
-    def _decode_step(self, st, rope_base, rows_group0, top_p, suppress_eos):
+    def _decode_step(self, st, rope_base, rows_group0, sp, suppress_eos):
         """Enqueue one decode step (feeds tokens at slot *step, samples the next token into slot *step + 1)."""
         if self.decode_fused:
-            return self._decode_step_fused(st, rope_base, rows_group0, top_p, suppress_eos)
+            return self._decode_step_fused(st, rope_base, rows_group0, sp, suppress_eos)
         d, W = self.dims, self.params
         R, RP, P, S = st["R"], st["RP"], st["P"], st["S"]
         H, I = d.hidden, d.inter
@@ -1082,9 +1120,9 @@ class Qwen2VLB200:
         ops.call("sb_dec_residual_rmsnorm", st["x"], parts, sp, RP * H, H, W["norm_w"], st["xn"], R, H, d.rms_eps)
         self._gemv(W["lm_head"], st["xn"], st["logits"], 1, next_w=W["l.0.qkv_w"])   # warms L2 for the next step
         ops.call("sb_step_advance", st["step"])
-        self._sample(st, top_p, suppress_eos)
+        self._sample(st, sp, suppress_eos)
 
-    def _decode_step_fused(self, st, rope_base, rows_group0, top_p, suppress_eos):
+    def _decode_step_fused(self, st, rope_base, rows_group0, sp, suppress_eos):
         """One decode step with the fused GEMV epilogues: per layer qkv GEMV (+ bias, M-RoPE, KV append) -> attention ->
         combine -> o GEMV (+ residual, x * ln2_w, sums of squares) -> gate|up GEMV (rstd scale + SwiGLU) -> down GEMV
         (+ residual, x * next ln1_w, sums of squares)."""
@@ -1135,18 +1173,18 @@ class Qwen2VLB200:
                        epilogue=ops.EPI_DEC_RESID)
         self._gemv(W["lm_head"], st["xw"], st["logits"], 1, next_w=W["l.0.qkv_w"], dec=scaled())
         ops.call("sb_step_advance", st["step"])
-        self._sample(st, top_p, suppress_eos)
+        self._sample(st, sp, suppress_eos)
 
-    def _decode_graph(self, st, rope_base, rows_group0, top_p, suppress_eos):
+    def _decode_graph(self, st, rope_base, rows_group0, sp, suppress_eos):
         """Capture one decode step into a CUDA graph (cached per decode state and step arguments).  Captured with the
         raw CUDAGraph API: the `torch.cuda.graph` context manager would empty the caching allocator, which makes
         every later phase of the training step re-map its memory."""
-        key = (int(rope_base), int(rows_group0), float(top_p), bool(suppress_eos), bool(self.decode_fused))
+        key = (int(rope_base), int(rows_group0), sp.key(), bool(suppress_eos), bool(self.decode_fused))
         hit = st["graphs"].get(key)
         if hit is not None:
             return hit
         snap = (st["step"].clone(), st["tokens"].clone(), st["finished"].clone(), st["out_ids"].clone())
-        self._decode_step(st, rope_base, rows_group0, top_p, suppress_eos)   # warm-up outside capture (func attributes)
+        self._decode_step(st, rope_base, rows_group0, sp, suppress_eos)   # warm-up outside capture (func attributes)
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(cur)
@@ -1155,7 +1193,7 @@ class Qwen2VLB200:
         with torch.cuda.stream(side):
             graph.capture_begin()
             try:
-                self._decode_step(st, rope_base, rows_group0, top_p, suppress_eos)
+                self._decode_step(st, rope_base, rows_group0, sp, suppress_eos)
             finally:
                 graph.capture_end()
         nodes = ops.direct_launch_count() - n0
@@ -1164,37 +1202,107 @@ class Qwen2VLB200:
         st["graphs"][key] = (graph, nodes)
         return graph, nodes
 
+    # ---- generation parameters ------------------------------------------------------------------------------------
+    # What `generate()` falls back to when NO generation_config is passed (the engine-level call of trainer.rollout and
+    # of the kernel tests): the reference's rollout configuration (TRN:277-284) without HF's implicit top_k.
+    ENGINE_DEFAULTS = dict(do_sample=True, temperature=1.0, top_k=0, top_p=0.95, repetition_penalty=1.0,
+                           num_return_sequences=1, max_new_tokens=1024, min_new_tokens=0)
+    # GenerationConfig._get_default_generation_params() (generation/configuration_utils.py:551-581): what HF fills in
+    # for every field the caller's config and the checkpoint's generation_config.json leave at None
+    HF_DEFAULTS = dict(do_sample=False, temperature=1.0, top_k=50, top_p=1.0, repetition_penalty=1.0,
+                       num_return_sequences=1, max_new_tokens=None, min_new_tokens=0)
+    _GEN_UNSUPPORTED = dict(num_beams=1, num_beam_groups=1, penalty_alpha=None, typical_p=1.0, epsilon_cutoff=0.0,
+                            eta_cutoff=0.0, no_repeat_ngram_size=0, encoder_no_repeat_ngram_size=0, bad_words_ids=None,
+                            min_p=None, length_penalty=1.0, diversity_penalty=0.0, encoder_repetition_penalty=1.0,
+                            suppress_tokens=None, begin_suppress_tokens=None, forced_bos_token_id=None,
+                            forced_eos_token_id=None, stop_strings=None, guidance_scale=None, sequence_bias=None,
+                            exponential_decay_length_penalty=None, output_scores=False, output_logits=None,
+                            return_dict_in_generate=False, max_time=None, assistant_model=None)
+
+    def resolve_generation(self, generation_config=None, **explicit):
+        """SamplingParams + (max_new_tokens, min_new_tokens, num_return_sequences) from, in priority order, the explicit
+        keyword arguments that are not None, `generation_config` (a transformers.GenerationConfig or any object / dict
+        with those attributes: TRN:277-302, 463), the checkpoint's generation_config.json (`self.generation_config`) and
+        the defaults (HF's when a generation_config is involved, the engine's otherwise; generation/utils.py:1664-1729).
+        Options this engine does not implement raise instead of being ignored."""
+        d = self.dims
+        layers = [{k: v for k, v in explicit.items() if v is not None}]
+        hf_mode = generation_config is not None
+        if hf_mode:
+            gc = generation_config if isinstance(generation_config, dict) else {
+                k: getattr(generation_config, k) for k in dir(generation_config)
+                if not k.startswith("_") and not callable(getattr(generation_config, k, None))}
+            layers.append({k: v for k, v in gc.items() if v is not None})
+            layers.append({k: v for k, v in (self.generation_config or {}).items() if v is not None})
+        merged = {}
+        for lay in reversed(layers):
+            merged.update(lay)
+        for k, dflt in self._GEN_UNSUPPORTED.items():
+            v = merged.get(k, dflt)
+            if v is not None and v != dflt and not (dflt in (False, None) and not v):
+                raise SpacerError(f"generate: {k}={v!r} is not supported by the B200 rollout engine")
+        base = self.HF_DEFAULTS if hf_mode else self.ENGINE_DEFAULTS
+        g = {k: merged.get(k, base[k]) for k in base}
+        if g["max_new_tokens"] is None:
+            raise SpacerError("generate: max_new_tokens is required (HF's max_length = 20 default is shorter than any prompt)")
+        eos = merged.get("eos_token_id")
+        if eos is None:
+            eos = list(d.eos_ids) if d.eos_ids else [d.eos_id]
+        eos = [int(e) for e in (eos if isinstance(eos, (list, tuple)) else [eos])]
+        if not 1 <= len(eos) <= 4:
+            raise SpacerError(f"generate: between 1 and 4 eos ids are supported, got {eos}")
+        pad = merged.get("pad_token_id")
+        pad = d.pad_id if pad is None else int(pad)
+        temperature = float(g["temperature"])
+        greedy = (not g["do_sample"]) or temperature <= 0.05 or int(g["top_k"] or 0) == 1
+        if temperature <= 0.0 and g["do_sample"]:
+            raise SpacerError("generate: temperature must be > 0")
+        sp = SamplingParams(greedy=bool(greedy), top_p=float(g["top_p"]), top_k=int(g["top_k"] or 0),
+                            temperature=1.0 if greedy else temperature,
+                            repetition_penalty=float(g["repetition_penalty"]), eos_ids=tuple(eos), pad_id=pad)
+        if not 0.0 < sp.top_p <= 1.0:
+            raise SpacerError(f"generate: top_p must be in (0, 1], got {sp.top_p}")
+        return sp, int(g["max_new_tokens"]), int(g["min_new_tokens"] or 0), int(g["num_return_sequences"])
+
     @torch.no_grad()
-    def generate(self, input_ids, pixel_values_videos=None, video_grid_thw=None, *, max_new_tokens=1024,
-                 num_return_sequences=1, top_p=0.95, temperature=1.0, do_sample=True, seed=0, min_new_tokens=0,
-                 pixel_values_videos_2=None, num_return_sequences_2=0, use_graph=True, attention_mask=None,
+    def generate(self, input_ids, pixel_values_videos=None, video_grid_thw=None, *, generation_config=None,
+                 max_new_tokens=None, num_return_sequences=None, top_p=None, top_k=None, temperature=None,
+                 do_sample=None, repetition_penalty=None, eos_token_id=None, pad_token_id=None, min_new_tokens=None,
+                 seed=0, pixel_values_videos_2=None, num_return_sequences_2=0, use_graph=True, attention_mask=None,
                  return_stats=False, second_per_grid_ts=None, pixel_values=None, image_grid_thw=None,
-                 keep_vit_tape=False, **unused):
-        """Sampled rollout: `num_return_sequences` completions of ONE prompt (TRN:463-467; generate() with
-        do_sample, top_p, temperature 1).  Returns LongTensor [G, P + C'] (prompt echoed, finished rows padded).
+                 keep_vit_tape=False, use_cache=True, mm_token_type_ids=None):
+        """Rollout of ONE prompt: `num_return_sequences` completions (TRN:463-467: generate(**prompt_inputs,
+        generation_config=GenerationConfig(max_new_tokens, do_sample, top_p, temperature, num_return_sequences,
+        pad_token_id))).  Returns LongTensor [G, P + C'] (prompt echoed, finished rows padded with pad_token_id).
+        Sampling parameters: see `resolve_generation`.  `attention_mask` must be all ones (one un-padded prompt; use the
+        HF-facing wrapper in hf_api.py for left-padded batches); `mm_token_type_ids` (transformers 5.x processors emit
+        it) carries no information beyond the placeholder ids and is accepted for that reason only.
 
         `pixel_values_videos_2` / `num_return_sequences_2` add a second group decoded in the same batch from
         the same text with another video (T-GRPO's frame-shuffled rollout, TRN:442-458, 469-475); the result is
-        then a tuple (ids_main, ids_second)."""
+        then a tuple (ids_main, ids_second), each cut to its own longest completion."""
         d = self.dims
+        if not use_cache:
+            raise SpacerError("generate: use_cache=False is not supported (the rollout engine is a KV-cache decoder)")
+        if attention_mask is not None and not bool(torch.as_tensor(attention_mask).bool().all()):
+            raise SpacerError("generate: padded prompts are not supported here (attention_mask has zeros)")
         if pixel_values is not None:
             # image prompt (`pixel_values` / `image_grid_thw`, the other visual input the reference's processor can
             # produce, TRN:417-425): same tower, grids with t = 1, image placeholder tokens
             if pixel_values_videos is not None:
                 raise SpacerError("generate: one visual input per prompt (image or video)")
             pixel_values_videos, video_grid_thw = pixel_values, image_grid_thw
-        if not do_sample or temperature <= 0.05:
-            # evaluation mode (SpaceR-Eval: temperature 0.01 over the checkpoint's top_k = 1 config): greedy argmax.
-            # (repetition_penalty of the released generation_config.json is not applied.)
-            top_p = 0.0
-        elif temperature != 1.0:
-            raise SpacerError("generate: sampling is implemented for temperature 1 (the reference's training configuration); "
-                              "temperature <= 0.05 or do_sample=False selects greedy decoding")
+        sp, max_new_tokens, min_new_tokens, G1 = self.resolve_generation(
+            generation_config, max_new_tokens=max_new_tokens, num_return_sequences=num_return_sequences, top_p=top_p,
+            top_k=top_k, temperature=temperature, do_sample=do_sample, repetition_penalty=repetition_penalty,
+            eos_token_id=eos_token_id, pad_token_id=pad_token_id, min_new_tokens=min_new_tokens)
         if min_new_tokens not in (0, max_new_tokens):
             raise SpacerError("generate: min_new_tokens must be 0 or max_new_tokens")
+        if torch.as_tensor(input_ids).dim() == 2 and input_ids.shape[0] != 1:
+            raise SpacerError("generate: one prompt per call (input_ids [1, P]); hf_api loops over a batch")
         ids = input_ids.reshape(-1)
         P = ids.numel()
-        G1, G2 = int(num_return_sequences), int(num_return_sequences_2 if pixel_values_videos_2 is not None else 0)
+        G2 = int(num_return_sequences_2 if pixel_values_videos_2 is not None else 0)
         R = G1 + G2
         if R > 32:
             raise SpacerError("generate: at most 32 rows per prompt")
@@ -1207,6 +1315,10 @@ class Qwen2VLB200:
         pixel_sets = [pixel_values_videos] + ([pixel_values_videos_2] if G2 > 0 else [])
         st = self._decode_state(R, P, max_new_tokens, len(pixel_sets))
         st["seed"].fill_(int(seed))
+        if sp.repetition_penalty != 1.0:
+            # RepetitionPenaltyLogitsProcessor looks at prompt + generated tokens (logits_process.py)
+            st["seen"].zero_()
+            ops.call("sb_token_bitmap_set", ids_dev, P, st["seen"], st["seen"].shape[1], R, d.vocab)
         self.vit_cache = None
         for k, pix in enumerate(pixel_sets):
             if keep_vit_tape and k == 0 and pix is not None:
@@ -1227,11 +1339,11 @@ class Qwen2VLB200:
             del hf, vis
         self._gemv(self.params["lm_head"], st["xn"], st["logits"], 1)
         suppress = min_new_tokens > 0
-        self._sample(st, top_p, suppress)
+        self._sample(st, sp, suppress)
         n_steps = max_new_tokens - 1
         graph, graph_nodes, replays = None, 0, 0
         if n_steps > 0 and use_graph:
-            graph, graph_nodes = self._decode_graph(st, nxt, G1, top_p, suppress)
+            graph, graph_nodes = self._decode_graph(st, nxt, G1, sp, suppress)
         ev[1].record()
         done = 0
         while done < n_steps:
@@ -1241,25 +1353,35 @@ class Qwen2VLB200:
                     graph.replay()
                     replays += 1
                 else:
-                    self._decode_step(st, nxt, G1, top_p, suppress)
+                    self._decode_step(st, nxt, G1, sp, suppress)
             done += burst
             if not suppress and done < n_steps and bool(st["finished"][:R].all().item()):
                 break
         ops.note_graph_replay(graph_nodes * replays)
         ev[2].record()
         out = st["out_ids"].long()
-        if not suppress:
-            is_eos = out == d.eos_id
-            first = torch.where(is_eos.any(1), is_eos.int().argmax(1), torch.full((R,), out.shape[1] - 1, device=self.device))
-            width = int(first.max().item()) + 1
-            width = min(width, int(st["step"].item()) + 1)
-            out = out[:, :width]
-            # rows that finished early are padded (generation/utils.py:2797)
-            col = torch.arange(width, device=self.device)[None]
-            out = torch.where(col > first[:, None], torch.full_like(out, d.pad_id), out)
-        prompt = ids.to(self.device).long()[None]
-        res1 = torch.cat([prompt.expand(G1, -1), out[:G1]], dim=1)
         steps_done = int(st["step"].item())      # host sync: everything above has completed
+        widths = [out.shape[1]] * 2
+
+        def cut(block):
+            """One generate() call of the reference = one group: width = its longest completion (generation stops when
+            every row of the CALL is finished), rows that finished early padded (generation/utils.py:2797)."""
+            if suppress or block.shape[0] == 0:
+                return block
+            is_eos = torch.zeros_like(block, dtype=torch.bool)
+            for e in sp.eos_ids:
+                is_eos |= block == e
+            n = block.shape[0]
+            first = torch.where(is_eos.any(1), is_eos.int().argmax(1),
+                                torch.full((n,), block.shape[1] - 1, device=self.device))
+            width = min(int(first.max().item()) + 1, steps_done + 1)
+            block = block[:, :width]
+            col = torch.arange(width, device=self.device)[None]
+            return torch.where(col > first[:, None], torch.full_like(block, sp.pad_id), block)
+
+        prompt = ids.to(self.device).long()[None]
+        out1 = cut(out[:G1])
+        res1 = torch.cat([prompt.expand(G1, -1), out1], dim=1)
         dec_ms = ev[1].elapsed_time(ev[2])
         n_loop = max(1, done)
         # algorithmic HBM bytes of one decode step (SURVEY.md 8(d)): every LLM-layer weight + lm_head once, the shared
@@ -1275,6 +1397,6 @@ class Qwen2VLB200:
         self.last_generate_stats = stats
         self._last_decode_state = st   # the cached decode state (parity tests read the final step's logits)
         if G2 > 0:
-            res2 = torch.cat([prompt.expand(G2, -1), out[G1:]], dim=1)
+            res2 = torch.cat([prompt.expand(G2, -1), cut(out[G1:])], dim=1)
             return (res1, res2, stats) if return_stats else (res1, res2)
         return (res1, stats) if return_stats else res1

@@ -11,7 +11,7 @@ import torch
 
 from . import _lib
 from ._lib import (EPI_DEC_QKV, EPI_DEC_RESID, EPI_DLOGITS, EPI_F32T, EPI_F32T_SWIGLU, EPI_GELU, EPI_LMHEAD,
-                   EPI_QUICKGELU, EPI_STORE, EPI_SWIGLU, DecFuse, GemmArgs, SpacerError, check)
+                   EPI_QUICKGELU, EPI_STORE, EPI_SWIGLU, DecFuse, GemmArgs, SampleArgs, SpacerError, check)
 
 
 # ------------------------------------------------------------------------------------------------

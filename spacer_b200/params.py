@@ -82,6 +82,7 @@ class ParamStore:
         self.mat = torch.zeros(sizes["mat"], device=self.device, dtype=torch.bfloat16)
         self.vec = torch.zeros(sizes["vec"], device=self.device, dtype=torch.bfloat16)
         self.views = {n: self.view_of(n, self.mat, self.vec) for n in self.index}
+        self.version = 0      # bumped whenever the weights are replaced wholesale (optimizers resync their fp32 masters)
 
     def view_of(self, name, mat, vec):
         arena, off, shape = self.index[name]
@@ -105,6 +106,7 @@ class ParamStore:
     # -------------------------------------------------------------------------------------------
     def init_random(self, seed: int = 0, std: float = 0.02):
         """Random-init weights (normal(0, std); norm weights 1) generated on the device."""
+        self.version += 1
         g = torch.Generator(device=self.device).manual_seed(seed)
         chunk = 1 << 26
         for base in (self.mat, self.vec):
@@ -197,6 +199,7 @@ class ParamStore:
 
     def load_state_dict(self, sd: dict):
         """Load an HF-named state dict (any float dtype, any device)."""
+        self.version += 1
         d = self.dims
         nq, nk = d.heads * d.head_dim, d.kv_heads * d.head_dim
 

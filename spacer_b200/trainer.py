@@ -23,6 +23,8 @@ from .params import ParamStore
 
 # hard-coded constants of the reference, named
 TOP_P = 0.95                 # TRN:277-284
+TOP_K = 50                   # not in the reference's GenerationConfig(...) call: HF fills top_k = 50 for every field left
+                             # unset (generation/configuration_utils.py:551-581; class default in transformers 4.x)
 KL_CLAMP = 10.0              # TRN:551 (inside the fused loss kernel)
 TEMPORAL_RATIO = 0.8         # TRN:604
 TEMPORAL_BONUS = 0.3         # TRN:606
@@ -51,12 +53,87 @@ class GRPOConfig:
     max_steps: int = 1000
     warmup_steps: int = 0
     seed: int = 42
+    top_k: int = TOP_K              # 0 = nucleus sampling only
+    eos_token_ids: tuple = ()       # ids that end a rollout row (HF: generation_config.eos_token_id); () = the model's
     moments_bf16: bool = False      # fp32 moments like DeepSpeed unless memory forces otherwise
     min_new_tokens: int = 0         # = max_completion_length disables EOS (timing runs)
     overlap_allreduce: bool = True  # per-layer gradient buckets all-reduced during the backward (N > 1)
     zero1: bool = False             # N > 1: shard the optimizer state (fp32 master + moments) over the ranks:
                                     # reduce-scatter gradients -> AdamW on the own 1/N of the matrix arena -> all-gather
                                     # the updated bf16 weights (what the reference gets from DeepSpeed, zero3.json)
+
+
+def completion_lengths(completion_ids: torch.Tensor, eos_id: int) -> torch.Tensor:
+    """`completion_mask.sum(1)` of TRN:489-494 without building the mask: tokens up to and INCLUDING the first EOS."""
+    is_eos = completion_ids == eos_id
+    n, C = completion_ids.shape
+    eos_idx = torch.where(is_eos.any(1), is_eos.int().argmax(1), torch.full((n,), C, device=completion_ids.device))
+    return torch.clamp(eos_idx + 1, max=C)
+
+
+def reward_tail(rewards_per_func: torch.Tensor, shuffled_rewards_per_func, lengths: torch.Tensor, num_generations: int,
+                temporal: bool = True, len_control: bool = True):
+    """TRN:598-638: T-GRPO temporal bonus, summed reward, length-control bonus, group-relative advantages.
+
+    rewards_per_func [B*G, n_funcs] (column 0 = accuracy), shuffled_rewards_per_func [G/2, n_funcs] or None (no video /
+    temporal off), lengths [B*G] = completion_mask.sum(1).  Returns (rewards [B*G], advantages [B*G], std [B*G],
+    temporal_rewards float: 1 bonus granted, 0 refused, 0.5 not applicable)."""
+    G = num_generations
+    temporal_rewards = 0.5
+    summed = rewards_per_func
+    if temporal and shuffled_rewards_per_func is not None:
+        summed = rewards_per_func.clone()                                       # TRN:598-611
+        if summed[:, 0].mean() >= TEMPORAL_RATIO * shuffled_rewards_per_func[:, 0].mean():
+            sel = summed[:, 0] > ACC_THRESHOLD
+            summed[sel, 0] = summed[sel, 0] + TEMPORAL_BONUS
+            temporal_rewards = 1.0
+        else:
+            temporal_rewards = 0.0
+    rewards = summed.sum(dim=1)                                                 # TRN:613-617
+    if len_control:                                                             # TRN:620-629 (pre-temporal accuracy)
+        sel = torch.nonzero(rewards_per_func[:, 0] > ACC_THRESHOLD, as_tuple=True)[0].tolist()
+        if len(sel) > 1:
+            ll = lengths.tolist()
+            for i in sel:
+                if LEN_WINDOW[0] <= ll[i] <= LEN_WINDOW[1]:
+                    rewards[i] += LEN_BONUS
+    mean = rewards.view(-1, G).mean(dim=1).repeat_interleave(G, dim=0)          # TRN:632-638
+    std = rewards.view(-1, G).std(dim=1).repeat_interleave(G, dim=0)            # unbiased; G = 1 gives NaN like the reference
+    adv = (rewards - mean) / (std + STD_EPS)
+    return rewards, adv, std, temporal_rewards
+
+
+def pack_step_stats(lengths, rewards_per_func, rewards, std, mean_kl, temporal_rewards) -> torch.Tensor:
+    """The per-rank quantities TRN:650-683 gathers one by one, as one fp32 vector (one all-gather per step)."""
+    dev = rewards.device
+    return torch.cat([lengths.float(), rewards_per_func.reshape(-1).float(), rewards.float(), std.float(),
+                      torch.stack([torch.as_tensor(mean_kl, device=dev).float().reshape(()),
+                                   torch.tensor(float(temporal_rewards), device=dev)])])
+
+
+def step_metrics(gathered: torch.Tensor, num_generations: int, reward_names: Sequence[str], temporal: bool) -> dict:
+    """TRN:650-683 on the gathered [world, len(pack_step_stats)] matrix: completion_length, rewards/<func>, all_wrong
+    (every reward of a prompt <= 1), all_correct (every reward >= 2), temporal_rewards, reward, reward_std, kl."""
+    G, nf = num_generations, len(reward_names)
+    n = (gathered.shape[1] - 2) // (3 + nf)            # rows per rank (B*G)
+    gl = gathered[:, :n]
+    grpf = gathered[:, n:n + n * nf].reshape(-1, nf)
+    grew = gathered[:, n + n * nf:2 * n + n * nf]
+    gstd = gathered[:, 2 * n + n * nf:3 * n + n * nf]
+    tail = gathered[:, -2:]
+    mt = {"completion_length": gl.mean().item()}
+    rpf_mean = grpf.mean(0)
+    for i, name in enumerate(reward_names):
+        mt[f"rewards/{name}"] = rpf_mean[i].item()
+    per_dev = grew.reshape(-1, G)                      # one row per prompt ("device" in the reference: 1 prompt / rank)
+    mt["all_wrong"] = (per_dev <= 1).all(dim=1).sum().item() / per_dev.shape[0]
+    mt["all_correct"] = (per_dev >= 2).all(dim=1).sum().item() / per_dev.shape[0]
+    if temporal:
+        mt["temporal_rewards"] = tail[:, 1].mean().item()
+    mt["reward"] = grew.mean().item()
+    mt["reward_std"] = gstd.mean().item()
+    mt["kl"] = tail[:, 0].mean().item()
+    return mt
 
 
 class AdamW:
@@ -80,12 +157,20 @@ class AdamW:
         n_own = self.hi - self.lo
         sizes = {"mat": n_own, "vec": params.sizes["vec"]}
         self.master = [torch.empty(sizes[k], device=dev, dtype=torch.float32) for k in ("mat", "vec")]
-        ops.call("sb_bf16_to_f32", params.mat[self.lo:self.hi], self.master[0], n_own)
-        ops.call("sb_bf16_to_f32", params.vec, self.master[1], params.vec.numel())
+        self.resync_master()
         self.m = [torch.zeros(sizes[k], device=dev, dtype=mdt) for k in ("mat", "vec")]
         self.v = [torch.zeros(sizes[k], device=dev, dtype=mdt) for k in ("mat", "vec")]
         self.total_sq = torch.zeros(1, device=dev, dtype=torch.float32)
         self.t = 0
+
+    def resync_master(self):
+        """fp32 master weights := the bf16 arenas.  Called at construction and whenever the weights were replaced from
+        outside the optimizer (`load_state_dict` / `from_pretrained` after the trainer exists: ParamStore.version changes),
+        so that the next step does not publish stale masters."""
+        p = self.p
+        ops.call("sb_bf16_to_f32", p.mat[self.lo:self.hi], self.master[0], self.hi - self.lo)
+        ops.call("sb_bf16_to_f32", p.vec, self.master[1], p.vec.numel())
+        self._seen_version = getattr(p, "version", 0)
 
     def lr_at(self, step: int) -> float:
         c = self.cfg
@@ -109,6 +194,8 @@ class AdamW:
 
     def step(self, grads: GradStore, grad_scale: float = 1.0, sumsq_ready: bool = False):
         c = self.cfg
+        if getattr(self.p, "version", 0) != self._seen_version:
+            self.resync_master()
         if not sumsq_ready:
             self.grad_sumsq(grads)
         lr = self.lr_at(self.t)
@@ -184,7 +271,8 @@ class SGRLVRTrainerB200:
         if c.max_prompt_length is not None and ids.shape[-1] > c.max_prompt_length:
             ids = ids[..., -c.max_prompt_length:]                    # TRN:432-440
         # Qwen2.5-VL: the rollout sees the processor's second_per_grid_ts; the scoring forwards do not (TRN:519-520)
-        kw = dict(max_new_tokens=c.max_completion_length, top_p=TOP_P, seed=seed, min_new_tokens=c.min_new_tokens,
+        kw = dict(max_new_tokens=c.max_completion_length, top_p=TOP_P, top_k=c.top_k, temperature=1.0, do_sample=True,
+                  seed=seed, min_new_tokens=c.min_new_tokens, eos_token_id=list(c.eos_token_ids) or None,
                   second_per_grid_ts=example.get("second_per_grid_ts"), keep_vit_tape=True)
         if c.temporal and pix is not None:
             if frames is not None:
@@ -230,10 +318,16 @@ class SGRLVRTrainerB200:
             per_func[:, i] = torch.tensor([float(x) for x in out], device=self.model.device)
         return per_func
 
+    def rollout_seed(self) -> int:
+        """Seed of this step's rollout: differs per step AND per data-parallel rank (the reference's ranks draw from
+        independent torch generators; identical Philox keys would make two ranks that meet the same prompt emit
+        bit-identical completions)."""
+        return self.cfg.seed + 1000003 * self.global_step + 7919 * D.rank(self.pg)
+
     def training_step(self, example) -> dict:
         c, m = self.cfg, self.model
         G = c.num_generations
-        seed = c.seed + 1000003 * self.global_step
+        seed = self.rollout_seed()
         marks = []
 
         def mark(name):
@@ -255,33 +349,12 @@ class SGRLVRTrainerB200:
         mark("ref_scoring")
         # rewards on decoded text (TRN:555-593)
         rewards_per_func = self.compute_rewards(self.decode_completions(completion_ids), example, G)
-        temporal_rewards = 0.5
-        summed = rewards_per_func
+        shuf_rpf = None
         if c.temporal and shuf is not None:
             shuf_rpf = self.compute_rewards(self.decode_completions(shuf[:, P:]), example, G // 2)
-            summed = rewards_per_func.clone()                                       # TRN:598-611
-            if summed[:, 0].mean() >= TEMPORAL_RATIO * shuf_rpf[:, 0].mean():
-                sel = summed[:, 0] > ACC_THRESHOLD
-                summed[sel, 0] = summed[sel, 0] + TEMPORAL_BONUS
-                temporal_rewards = 1.0
-            else:
-                temporal_rewards = 0.0
-        rewards = summed.sum(dim=1)                                                 # TRN:613-617
-        # completion mask lengths are needed for the length bonus before the loss kernel runs (TRN:489-494, 620-629)
-        is_eos = completion_ids == m.dims.eos_id
-        C = completion_ids.shape[1]
-        eos_idx = torch.where(is_eos.any(1), is_eos.int().argmax(1), torch.full((G,), C, device=m.device))
-        lengths = torch.clamp(eos_idx + 1, max=C)
-        if c.len_control:
-            sel = torch.nonzero(rewards_per_func[:, 0] > ACC_THRESHOLD, as_tuple=True)[0].tolist()
-            if len(sel) > 1:
-                ll = lengths.tolist()
-                for i in sel:
-                    if LEN_WINDOW[0] <= ll[i] <= LEN_WINDOW[1]:
-                        rewards[i] += LEN_BONUS
-        mean = rewards.mean()
-        std = rewards.std()                                                         # unbiased, TRN:633
-        adv = (rewards - mean) / (std + STD_EPS)                                    # TRN:638
+        # completion lengths are needed for the length bonus before the loss kernel runs (TRN:489-494, 620-629)
+        lengths = completion_lengths(completion_ids, m.dims.eos_id)
+        rewards, adv, std, temporal_rewards = reward_tail(rewards_per_func, shuf_rpf, lengths, G, c.temporal, c.len_control)
         mark("rewards")
         if self.reducer is not None:
             self.reducer.begin_step()
@@ -297,25 +370,9 @@ class SGRLVRTrainerB200:
             torch.distributed.all_gather_into_tensor(m.params.mat, m.params.mat[o.lo:o.hi], group=self.pg)
         mark("adamw")
         self.global_step += 1
-        # metrics (TRN:650-683), one gather per quantity like the reference but on a packed struct
-        packed = torch.cat([lengths.float(), rewards_per_func.reshape(-1), rewards,
-                            torch.stack([std, out["mean_kl"], torch.tensor(temporal_rewards, device=m.device)])])
-        allp = self._gather(packed)
-        nf = len(self.reward_funcs)
-        gl = allp[:, :G]
-        grpf = allp[:, G:G + G * nf].reshape(-1, nf)
-        grew = allp[:, G + G * nf:G + G * nf + G]
-        tail = allp[:, -3:]
-        mt = {"completion_length": gl.mean().item()}
-        for i, fn in enumerate(self.reward_funcs):
-            mt[f"rewards/{fn.__name__}"] = grpf[:, i].mean().item()
-        mt["all_wrong"] = (grew <= 1).all(dim=1).float().mean().item()
-        mt["all_correct"] = (grew >= 2).all(dim=1).float().mean().item()
-        if c.temporal:
-            mt["temporal_rewards"] = tail[:, 2].mean().item()
-        mt["reward"] = grew.mean().item()
-        mt["reward_std"] = tail[:, 0].mean().item()
-        mt["kl"] = tail[:, 1].mean().item()
+        # metrics (TRN:650-683): the reference gathers nine quantities one by one; here one packed vector per rank
+        allp = self._gather(pack_step_stats(lengths, rewards_per_func, rewards, std, out["mean_kl"], temporal_rewards))
+        mt = step_metrics(allp, G, [fn.__name__ for fn in self.reward_funcs], c.temporal)
         mt["loss"] = out["loss"].item()
         mt["learning_rate"] = lr
         for k, v in mt.items():
