@@ -771,24 +771,13 @@ class Qwen2VLB200:
         n_c = B * (L - P)
         return torch.cat([lp[n_c:].view(1, P - 1).expand(B, -1), lp[:n_c].view(B, L - P)], dim=1)
 
-    def grpo_forward_backward(self, batch: PackedBatch, pixel_values, grid_thw, ref_logps, advantages, beta,
-                              grads: GradStore, lm_chunk: int = 4096, vit_cache: dict | None = None):
-        """One GRPO forward/backward (TRN:526-528, 551-552, 640-643 + autograd's backward).
-        Returns dict(loss, mean_kl, logps [G,C], mask [G,C], lengths [G]); gradients land in `grads`."""
-        d = self.dims
-        H = d.hidden
-        G_, C = batch.G, batch.C
-        R = G_ * C
+    # ---- training forward / backward, in reusable pieces ---------------------------------------------
+    def forward_hidden(self, batch: PackedBatch, pixel_values, grid_thw, vit_cache: dict | None = None, mark=None):
+        """Vision tower + packed LLM forward with the activations saved for the backward.  Returns (hf [T, H], state);
+        `state` goes to backward_hidden.  `vit_cache` (from generate(keep_vit_tape=True)) supplies the rollout's ViT
+        forward and prompt prefill when pixels, prompt ids and position ids are the ones the rollout saw."""
+        mark = mark or (lambda name: None)
         vtape, ltape = {}, {}
-        marks = self.phase_marks      # optional list: (name, CUDA event) per sub-phase (tools/profile_phases.py)
-
-        def mark(name):
-            if marks is not None:
-                e = torch.cuda.Event(enable_timing=True)
-                e.record()
-                marks.append((name, e))
-
-        mark("start")
         if (vit_cache is not None and pixel_values is not None and vit_cache["pixels"] is pixel_values
                 and vit_cache.get("tape") is not None):
             vis, vtape = vit_cache["vis"], vit_cache["tape"]     # forward already done by the rollout (generate)
@@ -809,6 +798,75 @@ class Qwen2VLB200:
         else:
             hf = self.llm_forward(batch.ids, vis, batch.pos, batch.meta, ltape)
         mark("llm_fwd")
+        ltape["embed_plan"] = batch.embed_plan
+        return hf, dict(vis=vis, vtape=vtape, ltape=ltape)
+
+    def lm_head_backward(self, hsel, targets, lse, coef, grads: GradStore, lm_chunk: int = 4096):
+        """Backward of `logprob = logit[target] - logsumexp(logits)` through lm_head for the selected hidden rows, given
+        coef = dLoss/dlogprob per row: logits are recomputed tile by tile in the DLOGITS epilogue
+        (coef * (onehot - softmax)), never stored as fp32 [rows, V].  Accumulates dW into grads["lm_head"] (which is the
+        embedding table when tied: call grads.zero_for_step() first) and returns d_hsel [rows, H]."""
+        d = self.dims
+        R = hsel.shape[0]
+        d_hsel = torch.empty((R, d.hidden), device=self.device, dtype=BF16)
+        g_lm = grads["lm_head"]
+        first = True
+        for r0 in range(0, R, lm_chunk):
+            r1 = min(r0 + lm_chunk, R)
+            dl = ops.gemm(hsel[r0:r1], self.params["lm_head"], epilogue=EPI_DLOGITS, targets=targets[r0:r1],
+                          lse=lse[r0:r1], coef=coef[r0:r1])
+            ops.gemm(dl, self.params["lm_head"], b_mn=True, out=d_hsel[r0:r1])
+            ops.gemm(dl, hsel[r0:r1], a_mn=True, b_mn=True, out=g_lm, residual=None if (first and not d.tie) else g_lm)
+            first = False
+            del dl
+        if not d.tie:
+            grads.ready("lm_head")
+        return d_hsel
+
+    def scatter_rows(self, d_hsel, rows, rows_plan, T):
+        """d_hf [T, H] with d_hsel's rows added at `rows` (deterministic when a segment plan is given: repeated rows --
+        the last prompt row predicts the first token of every completion -- are summed in fp32 in a fixed order)."""
+        H = self.dims.hidden
+        d_hf = torch.zeros((T, H), device=self.device, dtype=BF16)
+        if rows_plan is not None:
+            order, off, dst, n_seg = rows_plan
+            ops.call("sb_segment_sum_rows", d_hsel, order, off, dst, n_seg, d_hf, H, 0)
+        else:
+            ops.call("sb_scatter_add_rows", d_hsel, rows, d_hf, d_hsel.shape[0], H)
+        return d_hf
+
+    def backward_hidden(self, state: dict, d_hf, grads: GradStore, mark=None):
+        """Backward of forward_hidden from d(final hidden states): decoder layers, embedding, vision tower."""
+        mark = mark or (lambda name: None)
+        d_vis = self.llm_backward(state["ltape"], d_hf, grads)
+        mark("llm_bwd")
+        state["ltape"] = None
+        if state["vis"] is not None:
+            self.vit_backward(state["vtape"], d_vis, grads)
+        else:
+            grads.zero_range("v.")
+        state["vtape"] = None
+        mark("vit_bwd")
+        grads.ready("v.")         # the whole vision tower as one bucket (1.3 GB of bf16 at 7B)
+
+    def grpo_forward_backward(self, batch: PackedBatch, pixel_values, grid_thw, ref_logps, advantages, beta,
+                              grads: GradStore, lm_chunk: int = 4096, vit_cache: dict | None = None):
+        """One GRPO forward/backward (TRN:526-528, 551-552, 640-643 + autograd's backward).
+        Returns dict(loss, mean_kl, logps [G,C], mask [G,C], lengths [G]); gradients land in `grads`."""
+        d = self.dims
+        H = d.hidden
+        G_, C = batch.G, batch.C
+        R = G_ * C
+        marks = self.phase_marks      # optional list: (name, CUDA event) per sub-phase (tools/profile_phases.py)
+
+        def mark(name):
+            if marks is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((name, e))
+
+        mark("start")
+        hf, state = self.forward_hidden(batch, pixel_values, grid_thw, vit_cache, mark)
         hsel = torch.empty((R, H), device=self.device, dtype=BF16)
         ops.call("sb_gather_rows", hf, batch.rows, hsel, R, H)
         part, tl, nt = self._lmhead_partials(hsel, batch.targets)
@@ -828,37 +886,13 @@ class Qwen2VLB200:
         mark("lm_head_loss")
         # backward through lm_head: recompute logits tile by tile, emit dlogits, two GEMMs
         grads.zero_for_step()
-        d_hsel = torch.empty((R, H), device=self.device, dtype=BF16)
-        g_lm = grads["lm_head"]
-        first = True
-        for r0 in range(0, R, lm_chunk):
-            r1 = min(r0 + lm_chunk, R)
-            dl = ops.gemm(hsel[r0:r1], self.params["lm_head"], epilogue=EPI_DLOGITS, targets=batch.targets[r0:r1],
-                          lse=lse[r0:r1], coef=coef[r0:r1])
-            ops.gemm(dl, self.params["lm_head"], b_mn=True, out=d_hsel[r0:r1])
-            ops.gemm(dl, hsel[r0:r1], a_mn=True, b_mn=True, out=g_lm, residual=None if (first and not d.tie) else g_lm)
-            first = False
-            del dl
-        if not d.tie:
-            grads.ready("lm_head")
-        d_hf = torch.zeros_like(hf)
-        if batch.rows_plan is not None:    # deterministic: repeated rows (the last prompt row) summed in fp32, fixed order
-            order, off, dst, n_seg = batch.rows_plan
-            ops.call("sb_segment_sum_rows", d_hsel, order, off, dst, n_seg, d_hf, H, 0)
-        else:
-            ops.call("sb_scatter_add_rows", d_hsel, batch.rows, d_hf, R, H)
-        ltape["embed_plan"] = batch.embed_plan
-        del hsel, d_hsel, hf
+        d_hsel = self.lm_head_backward(hsel, batch.targets, lse, coef, grads, lm_chunk)
+        T = hf.shape[0]
+        del hsel, hf
+        d_hf = self.scatter_rows(d_hsel, batch.rows, batch.rows_plan, T)
+        del d_hsel
         mark("lm_head_bwd")
-        d_vis = self.llm_backward(ltape, d_hf, grads)
-        mark("llm_bwd")
-        del ltape, d_hf
-        if vis is not None:
-            self.vit_backward(vtape, d_vis, grads)
-        else:
-            grads.zero_range("v.")
-        mark("vit_bwd")
-        grads.ready("v.")         # the whole vision tower as one bucket (1.3 GB of bf16 at 7B)
+        self.backward_hidden(state, d_hf, grads, mark)
         return dict(loss=out2[0], mean_kl=out2[1], logps=lp.view(G_, C), mask=mask.view(G_, C), lengths=row_len)
 
     # ---- supervised fine-tuning ---------------------------------------------
@@ -1065,22 +1099,11 @@ class Qwen2VLB200:
         """Next token per row from st["logits"] under the sampling parameters `sp` (SamplingParams): HF's processor chain
         repetition penalty -> temperature -> top-k -> top-p -> multinomial (TRN:277-302 generation configs), or greedy
         argmax (evaluation, SpaceR-Eval/data_utils/vsibench.py:174)."""
-        import ctypes
-        d, R = self.dims, st["R"]
-        a = ops.SampleArgs()
-        a.logits, a.ld, a.R, a.V = st["logits"].data_ptr(), d.vocab, R, d.vocab
-        a.mode = 1 if sp.greedy else 0
-        a.top_p, a.top_k, a.temperature = float(sp.top_p), int(sp.top_k), float(sp.temperature)
-        a.repetition_penalty = float(sp.repetition_penalty)
-        if sp.repetition_penalty != 1.0:
-            a.seen, a.seen_ld = st["seen"].data_ptr(), st["seen"].shape[1]
-        a.seed, a.seed_dev = 0, st["seed"].data_ptr()
-        a.step_ptr, a.finished, a.out_tokens = st["step"].data_ptr(), st["finished"].data_ptr(), st["tokens"].data_ptr()
-        a.out_ids, a.out_ld = st["out_ids"].data_ptr(), st["c_max"]
-        for k, e in enumerate(sp.eos_ids):
-            a.eos_ids[k] = int(e)
-        a.n_eos, a.pad_id, a.suppress_eos = len(sp.eos_ids), int(sp.pad_id), int(suppress_eos)
-        ops.check(ops._lib.load().sb_sample(ctypes.byref(a), ops._stream()), "sb_sample")
+        ops.sample(st["logits"], st["step"], st["tokens"], V=self.dims.vocab, R=st["R"], greedy=sp.greedy, top_p=sp.top_p,
+                   top_k=sp.top_k, temperature=sp.temperature, repetition_penalty=sp.repetition_penalty,
+                   seen=st["seen"] if sp.repetition_penalty != 1.0 else None, seed_dev=st["seed"],
+                   finished=st["finished"], out_ids=st["out_ids"], eos_ids=sp.eos_ids, pad_id=sp.pad_id,
+                   suppress_eos=suppress_eos)
 
     def _decode_step(self, st, rope_base, rows_group0, sp, suppress_eos):
         """Enqueue one decode step (feeds tokens at slot *step, samples the next token into slot *step + 1)."""

@@ -129,6 +129,36 @@ def call(name: str, *args):
     check(fn(*conv, torch.cuda.current_stream().cuda_stream), name)
 
 
+def sample(logits, step, out_tokens, *, V=None, R=None, greedy=False, top_p=1.0, top_k=0, temperature=1.0,
+           repetition_penalty=1.0, seen=None, seed=0, seed_dev=None, finished=None, out_ids=None, out_logprob=None,
+           eos_ids=(), pad_id=0, suppress_eos=False):
+    """sb_sample: one token per row of fp32 `logits` [R, ld] (HF's processor chain repetition penalty -> temperature ->
+    top-k -> top-p -> multinomial, or greedy argmax)."""
+    _req(logits, torch.float32, "logits")
+    a = SampleArgs()
+    a.logits, a.ld = logits.data_ptr(), logits.stride(0)
+    a.R = logits.shape[0] if R is None else R
+    a.V = logits.shape[1] if V is None else V
+    a.mode = 1 if greedy else 0
+    a.top_p, a.top_k, a.temperature, a.repetition_penalty = float(top_p), int(top_k), float(temperature), float(repetition_penalty)
+    if seen is not None:
+        _req(seen, torch.int32, "seen")
+        a.seen, a.seen_ld = seen.data_ptr(), seen.stride(0)
+    a.seed = int(seed)
+    a.seed_dev = None if seed_dev is None else seed_dev.data_ptr()
+    a.step_ptr, a.out_tokens = step.data_ptr(), out_tokens.data_ptr()
+    a.finished = None if finished is None else finished.data_ptr()
+    if out_ids is not None:
+        a.out_ids, a.out_ld = out_ids.data_ptr(), out_ids.stride(0)
+    a.out_logprob = None if out_logprob is None else out_logprob.data_ptr()
+    if len(eos_ids) > 4:
+        raise SpacerError("sample: at most 4 eos ids")
+    for k, e in enumerate(eos_ids):
+        a.eos_ids[k] = int(e)
+    a.n_eos, a.pad_id, a.suppress_eos = len(eos_ids), int(pad_id), int(bool(suppress_eos))
+    check(_lib.load().sb_sample(C.byref(a), _stream()), "sb_sample")
+
+
 def cast_f32_bf16(src, dst=None):
     _req(src, torch.float32, "src")
     if dst is None:

@@ -231,6 +231,121 @@ def test_sampler_eos_and_finished():
     assert toks.tolist() == [6, 6, 6] and fin.tolist() == [0, 0, 0]
 
 
+def _draw(logits, n_draws, seed=1234, **opts):
+    from spacer_b200 import ops
+    R = logits.shape[0]
+    step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    toks = torch.empty(R, dtype=torch.int32, device="cuda")
+    ids = torch.zeros((R, n_draws), dtype=torch.int32, device="cuda")
+    for _ in range(n_draws):
+        ops.sample(logits, step, toks, seed=seed, out_ids=ids, **opts)
+        ops.call("sb_step_advance", step)
+    torch.cuda.synchronize()
+    return ids.cpu().long()
+
+
+def _hf_chain(logits_bf16_f32, context, rep_pen, temperature, top_k, top_p, reround):
+    """The real transformers processors in generate()'s order (generation/utils.py `_get_logits_processor`): repetition
+    penalty, temperature, top-k, top-p.  `reround` reproduces this engine's one deliberate deviation (values changed by
+    penalty / temperature go back to bf16 before the cuts)."""
+    from transformers.generation.logits_process import (RepetitionPenaltyLogitsProcessor, TemperatureLogitsWarper,
+                                                        TopKLogitsWarper, TopPLogitsWarper)
+    s = logits_bf16_f32.clone()
+    changed = torch.zeros_like(s, dtype=torch.bool)
+    if rep_pen != 1.0:
+        s2 = RepetitionPenaltyLogitsProcessor(rep_pen)(context, s)
+        changed |= s2 != s
+        s = s2
+    if temperature != 1.0:
+        s = TemperatureLogitsWarper(temperature)(context, s)
+        changed |= True
+    if reround:
+        s = torch.where(changed, s.bfloat16().float(), s)
+    if top_k > 0:
+        s = TopKLogitsWarper(top_k)(context, s)
+    if top_p < 1.0:
+        s = TopPLogitsWarper(top_p)(context, s)
+    return torch.softmax(s, dim=-1)
+
+
+@pytest.mark.parametrize("V,rep_pen,temperature,top_k,top_p", [
+    (4096, 1.0, 1.0, 50, 0.95),        # the reference's rollout: HF's implicit top_k = 50 under top_p 0.95
+    (152064, 1.0, 1.0, 50, 0.95),
+    (4096, 1.05, 0.7, 20, 0.9),
+    (152064, 1.3, 1.5, 50, 1.0),
+    (5003, 1.0, 0.5, 0, 0.8),
+    (2048, 1.2, 1.0, 3, 1.0),
+])
+def test_sampler_matches_hf_processor_chain(V, rep_pen, temperature, top_k, top_p):
+    """Support and frequencies of sb_sample against transformers' own RepetitionPenalty / Temperature / TopK / TopP
+    processors + softmax on the same logits."""
+    from spacer_b200 import ops
+    R, n_draws, n_ctx = 4, 3000, 40
+    logits = rnd((R, V), 31, 2.5 if V < 10000 else 1.2, torch.float32)
+    logits[0, 11] = logits[0].max() + 1.0
+    if top_k > 0:
+        logits[3, :8] = 9.0           # ties at the k-th value: TopKLogitsWarper keeps all of them
+    g = torch.Generator().manual_seed(3)
+    context = torch.randint(0, V, (R, n_ctx), generator=g)
+    context[:, :5] = torch.arange(5)[None] + 9   # make sure some high-probability tokens are penalised
+    seen = torch.zeros((R, (V + 31) // 32), dtype=torch.int32, device="cuda")
+    for r in range(R):
+        ops.call("sb_token_bitmap_set", context[r].to(torch.int32).cuda(), n_ctx, seen[r:], seen.stride(0), 1, V)
+    seen0 = seen.clone()
+    ids = _draw(logits, n_draws, top_p=top_p, top_k=top_k, temperature=temperature, repetition_penalty=rep_pen,
+                seen=seen if rep_pen != 1.0 else None)
+    lb = logits.bfloat16().float().cpu()
+    exact = _hf_chain(lb, context, rep_pen, temperature, top_k, top_p, reround=True)
+    hf = _hf_chain(lb, context, rep_pen, temperature, top_k, top_p, reround=False)
+    for r in range(R):
+        got = torch.bincount(ids[r], minlength=V).float() / n_draws
+        kept = int((exact[r] > 0).sum())
+        assert (exact[r][ids[r]] > 0).all() or top_p < 1.0, f"row {r}: sampled a token the processor chain removes"
+        tv = 0.5 * (got - exact[r]).abs().sum().item()
+        bound = 3 * math.sqrt(max(kept, 1) / (2 * math.pi * n_draws)) + 0.02
+        assert tv < bound, f"row {r}: TV {tv} vs own-rounding chain (kept {kept}, bound {bound})"
+        tv_hf = 0.5 * (got - hf[r]).abs().sum().item()
+        assert tv_hf < bound + 0.03, f"row {r}: TV {tv_hf} vs the fp32 HF chain"
+        if top_k > 0 and top_p >= 1.0:
+            assert set(ids[r].tolist()) <= set(torch.nonzero(exact[r] > 0).flatten().tolist())
+    if top_k > 0 and top_p >= 1.0:
+        assert int((exact[3] > 0).sum()) >= 8 or rep_pen != 1.0          # the tie group survives whole
+    if rep_pen != 1.0:   # the sampled tokens were OR-ed into the bitmap (they count for the next step's penalty)
+        new_bits = (seen ^ seen0).cpu()
+        for r in range(R):
+            last = int(ids[r, -1])
+            assert (int(seen[r, last >> 5].item()) >> (last & 31)) & 1
+        assert int((new_bits != 0).sum()) > 0 or top_k == 1
+
+
+def test_sampler_greedy_with_repetition_penalty_and_eos_list():
+    """Evaluation decoding (checkpoint generation_config: repetition_penalty 1.05, top_k 1; vsibench.py:174): argmax of
+    the penalised logits; ANY id of the eos list finishes a row."""
+    from spacer_b200 import ops
+    V, R = 1000, 3
+    logits = torch.zeros((R, V), device="cuda")
+    logits[:, 5] = 10.0
+    logits[:, 6] = 9.8
+    logits[2, 7] = 10.5
+    seen = torch.zeros((R, (V + 31) // 32), dtype=torch.int32, device="cuda")
+    step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    fin = torch.zeros(R, dtype=torch.int32, device="cuda")
+    toks = torch.empty(R, dtype=torch.int32, device="cuda")
+    kw = dict(greedy=True, repetition_penalty=1.05, seen=seen, finished=fin, eos_ids=(7, 900), pad_id=3)
+    ops.sample(logits, step, toks, **kw)
+    assert toks.tolist() == [5, 5, 7] and fin.tolist() == [0, 0, 1]
+    ops.sample(logits, step, toks, **kw)             # 5 was emitted: 10 / 1.05 = 9.52 < 9.8 -> 6; row 2 pads
+    assert toks.tolist() == [6, 6, 3]
+    ops.sample(logits, step, toks, **kw)             # 6 penalised too: 9.33 < 9.52 -> 5 again
+    assert toks.tolist() == [5, 5, 3]
+    logits[0, 900] = 50.0
+    ops.sample(logits, step, toks, **kw)
+    assert toks.tolist()[0] == 900 and fin.tolist() == [1, 0, 1]
+    fin.zero_()
+    ops.sample(logits, step, toks, suppress_eos=True, **kw)     # both eos ids suppressed
+    assert toks.tolist()[0] not in (7, 900) and toks.tolist()[2] not in (7, 900) and fin.tolist() == [0, 0, 0]
+
+
 @pytest.mark.parametrize("G,C,V", [(4, 37, 1000), (4, 150, 1200), (4, 64, 256)])
 def test_grpo_loss_matches_oracle(G, C, V):
     from oracle import grpo_ref as GR
