@@ -31,6 +31,8 @@ CONFIGS = {
                workload="cfg3: Qwen2-VL-7B random-init, 16 frames x 448^2 (grid 8x32x32, 2048 vision tokens), P=2304, G=8 (+4 frame-shuffled, T-GRPO), C=512 (EOS disabled), beta=0.04"),
     "c3q25": dict(preset="25-7b", frames=16, res=448, G=8, text=256, C=512,
                   workload="cfg3 on Qwen2.5-VL-7B random-init (the family run_SpaceR_SG_RLVR.sh trains; windowed ViT): 16 frames x 448^2, P=2304, G=8 (+4 frame-shuffled), C=512 (EOS disabled), beta=0.04"),
+    "c1": dict(preset="2b", frames=2, res=224, G=2, text=64, C=16,
+               workload="cfg1: Qwen2-VL-2B random-init, 2 frames x 224^2 (grid 1x16x16, 64 vision tokens), P=128, G=2 (+1 shuffled), C=16 -- the reference's CPU-runnable case"),
     "c2": dict(preset="2b", frames=8, res=336, G=4, text=256, C=512,
                workload="cfg2: Qwen2-VL-2B random-init, 8 frames x 336^2 (grid 4x24x24, 576 vision tokens), P=832, G=4 (+2 shuffled), C=512"),
     "c4": dict(preset="7b", frames=32, res=448, G=8, text=256, C=512,
@@ -250,25 +252,111 @@ def cpu_reference_sample(cfg_name, threads=None):
     return total, desc, threads, dict(vit=t_vit, prefill=t_prefill, decode=t_decode, gen=gen_main + gen_shuf, policy=policy, ref=ref)
 
 
+def cpu_full_step(cfg_name, steps=1, threads=None):
+    """A REAL full GRPO step of the reference's model stack on the host cores: stock HF `Qwen2VLForConditionalGeneration`
+    (eager attention, fp32) driven by the restated trainer loop of tools/hf_gpu_baseline.py -- generate x (G + G/2),
+    reference-policy forward, policy forward (gradient checkpointing) + backward, clip, AdamW.  No extrapolation.
+    Feasible for cfg1 / cfg2 (2B); 7B fp32 policy + reference + gradients do not fit the host RAM."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from hf_gpu_baseline import HFStep
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    cfg = CONFIGS[cfg_name]
+    hs = HFStep(cfg, "cpu")
+    t0 = time.perf_counter()
+    phases = {}
+    for _ in range(steps):
+        for k, v in hs.step().items():
+            phases[k] = phases.get(k, 0.0) + v / steps
+    total = (time.perf_counter() - t0) / steps
+    hs.free()
+    return {"value": cfg["G"] / total, "unit": "samples/s", "s_per_step": total, "cores": threads, "kind": "port",
+            "phase_s": {k: round(v, 3) for k, v in phases.items() if k != "loss"},
+            "sample": f"{steps} REAL full step(s) of {cfg['workload']}: transformers {__import__('transformers').__version__} "
+                      f"Qwen2VLForConditionalGeneration, eager attention, fp32, {threads} host threads, the reference "
+                      "trainer's loop restated (trl/accelerate absent); nothing extrapolated"}
+
+
+def hf_gpu_leg(cfg, dev, world, rank, local, steps=3):
+    """The comparator of BASELINE's '>= 5x the reference HF/PyTorch GRPO step' target on the SAME GPUs: the reference's
+    step on stock HF transformers (bf16, flash_attention_2, gradient checkpointing, fused torch AdamW; data parallel over
+    the N ranks with an NCCL gradient all-reduce), none of this repo's kernels.  Timed like the main arm: warm-up, barrier +
+    synchronize on both sides, CUDA events, max over ranks, clocks sampled during the timed region."""
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from hf_gpu_baseline import HFStep
+    hs = HFStep(cfg, dev, seed=1234 + rank, world=world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    hs.step(4)                       # warm-up: allocator, kernel selection
+    hs.step(4)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    phases = {}
+    e0.record()
+    for _ in range(steps):
+        for k, v in hs.step().items():
+            phases[k] = phases.get(k, 0.0) + v / steps
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if sampler else None
+    attn = hs.attn
+    hs.free()
+    G, C = cfg["G"], cfg["C"]
+    s_per_step = ms.item() / 1000.0 / steps
+    return {"value": world * G / s_per_step, "unit": "samples/s", "s_per_step": s_per_step, "steps": steps, "warmup": 2,
+            "n_gpus": world, "attn_implementation": attn, "dtype": "bf16",
+            "rollout_tok_per_s": world * (G + G // 2) * C / phases["rollout"],
+            "phase_s": {k: round(v, 3) for k, v in phases.items() if k != "loss"}, "clocks": clocks,
+            "what": "reference trainer step restated over stock transformers Qwen2VLForConditionalGeneration "
+                    f"{__import__('transformers').__version__} on the same GPU(s); none of this repo's kernels"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     K, W = args.steps, args.warmup
-    vals = []
-    desc, threads = "", 0
-    for i in range(max(1, min(K, 2)) + (1 if W > 0 else 0)):
-        total, desc, threads, parts = cpu_reference_sample(args.config)
-        vals.append(total)
-    total = sum(vals[(1 if W > 0 and len(vals) > 1 else 0):]) / max(1, len(vals) - (1 if W > 0 and len(vals) > 1 else 0))
     cfg = CONFIGS[args.config]
+    note = "reference-executed step on host cores"
+    if cfg["preset"] in ("2b", "tiny") and args.config != "c2" or args.cpu_full_step:
+        # the reference's model stack for real: full steps, nothing extrapolated (cfg2 takes ~10 min per step on 8
+        # cores, so it needs --cpu-full-step; its committed log is profiles/r02_cpu_full_step_c2.json)
+        cb = cpu_full_step(args.config, steps=max(1, min(K, 2)))
+        total = cb["s_per_step"]
+        cb.pop("s_per_step")
+        note += ", REAL full steps on stock HF transformers (fp32, eager)"
+    else:
+        vals = []
+        desc, threads = "", 0
+        for i in range(max(1, min(K, 2)) + (1 if W > 0 else 0)):
+            total, desc, threads, parts = cpu_reference_sample(args.config)
+            vals.append(total)
+        total = sum(vals[(1 if W > 0 and len(vals) > 1 else 0):]) / max(1, len(vals) - (1 if W > 0 and len(vals) > 1 else 0))
+        cb = {"value": cfg["G"] / total, "unit": "samples/s", "cores": threads, "kind": "port", "sample": desc,
+              "extrapolated": True}
+        note += ", extrapolated from a bounded sample (7B in fp32 does not fit the host for a full step)"
+        if not args.no_cfg1_step:
+            try:        # ... and one configuration the host CAN run in full, for real
+                cb["full_step_cfg1"] = cpu_full_step("c1", steps=1)
+            except Exception as e:  # noqa: BLE001
+                cb["full_step_cfg1"] = {"error": str(e)[:200]}
     value = cfg["G"] / total
     line = {
         "impl": "reference", "metric": "grpo_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": K, "warmup": W, "ms_per_step": total * 1000.0, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg["workload"], "note": "reference-executed step on host cores, extrapolated from a bounded sample"},
-        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port", "sample": desc},
+        "config": {"workload": cfg["workload"], "note": note},
+        "cpu_baseline": cb,
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -283,6 +371,11 @@ def main():
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="spacer", choices=["spacer", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-full-step", action="store_true", help="CPU baseline as a REAL full step of the HF stack on the "
+                    "host cores (default for c1; minutes per step for c2; impossible for the 7B configs)")
+    ap.add_argument("--no-cfg1-step", action="store_true", help="reference arm: skip the real cfg1 full step next to an extrapolated 7B line")
+    ap.add_argument("--no-hf-baseline", action="store_true", help="skip the HF/PyTorch-on-GPU leg (hf_gpu_baseline)")
+    ap.add_argument("--hf-steps", type=int, default=3)
     ap.add_argument("--moments-bf16", action="store_true")
     ap.add_argument("--no-temporal", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="gradient all-reduce after the backward instead of overlapped")
@@ -308,6 +401,17 @@ def main():
     cfg = CONFIGS[args.config]
     dims = mcfg.PRESETS[cfg["preset"]]()
     K, W = args.steps, max(args.warmup, 0)
+
+    # the reference's step on the reference's own model stack, on these same GPUs (before this engine takes the memory)
+    hf_leg = None
+    if not args.no_hf_baseline and cfg["preset"] in ("7b", "2b"):
+        try:
+            hf_leg = hf_gpu_leg(cfg, dev, world, rank, local, steps=max(1, args.hf_steps))
+        except Exception as e:  # noqa: BLE001
+            hf_leg = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
 
     # weights: policy random-init (seed 0 on every rank), reference = copy of the initial policy
     policy = Qwen2VLB200(dims, dev)
@@ -395,8 +499,9 @@ def main():
     ach = stats.get("decode_gbs") or 0.0
     # DRAM bytes of one decode step measured under ncu (--cache-control none), committed with the profile it came from
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", f"r01_decode_traffic_{args.config}.json")
-    if os.path.exists(tpath):
+    tpath = next((q for q in (os.path.join(ROOT, "profiles", f"r0{r}_decode_traffic_{args.config}.json") for r in (2, 1))
+                  if os.path.exists(q)), "")
+    if tpath:
         with open(tpath) as f:
             tj = json.load(f)
         if tj.get("rows") == rows:
@@ -426,8 +531,12 @@ def main():
         cpu_b = None
         if world == 1 and not args.no_cpu_baseline:
             try:
-                total, desc, threads, _ = cpu_reference_sample(args.config)
-                cpu_b = {"value": cfg["G"] / total, "unit": "samples/s", "cores": threads, "kind": "port", "sample": desc}
+                if args.cpu_full_step or args.config == "c1":
+                    cpu_b = cpu_full_step(args.config, steps=1)
+                else:
+                    total, desc, threads, _ = cpu_reference_sample(args.config)
+                    cpu_b = {"value": cfg["G"] / total, "unit": "samples/s", "cores": threads, "kind": "port", "sample": desc,
+                             "extrapolated": True}
             except Exception as e:  # noqa: BLE001
                 cpu_b = {"value": None, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
         line = {
@@ -443,6 +552,8 @@ def main():
                        "decode_ms_per_token_step": stats.get("decode_ms_per_step"), "phase_ms": phase_ms},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_b,
+            "hf_gpu_baseline": hf_leg,
+            "speedup_vs_hf_gpu": (e2e_value / hf_leg["value"]) if hf_leg and hf_leg.get("value") else None,
             "ranks_in_sync": in_sync,
             "last_step_metrics": {k: (round(v, 6) if isinstance(v, float) else v) for k, v in (mt or {}).items()},
         }

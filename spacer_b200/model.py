@@ -1099,7 +1099,7 @@ class Qwen2VLB200:
         """Next token per row from st["logits"] under the sampling parameters `sp` (SamplingParams): HF's processor chain
         repetition penalty -> temperature -> top-k -> top-p -> multinomial (TRN:277-302 generation configs), or greedy
         argmax (evaluation, SpaceR-Eval/data_utils/vsibench.py:174)."""
-        ops.sample(st["logits"], st["step"], st["tokens"], V=self.dims.vocab, R=st["R"], greedy=sp.greedy, top_p=sp.top_p,
+        ops.sample(st["logits"][0], st["step"], st["tokens"], V=self.dims.vocab, R=st["R"], greedy=sp.greedy, top_p=sp.top_p,
                    top_k=sp.top_k, temperature=sp.temperature, repetition_penalty=sp.repetition_penalty,
                    seen=st["seen"] if sp.repetition_penalty != 1.0 else None, seed_dev=st["seed"],
                    finished=st["finished"], out_ids=st["out_ids"], eos_ids=sp.eos_ids, pad_id=sp.pad_id,

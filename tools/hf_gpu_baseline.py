@@ -1,12 +1,19 @@
 #!/usr/bin/env python
-"""The comparator of BASELINE's ">= 5x the reference HF/PyTorch GRPO step" target, measured on the same B200: the
-reference trainer's step (SG_RLVR_trainer.py:384-686) restated over the stock Hugging Face `Qwen2VLForConditionalGeneration`
-(transformers 5.5.0, random-init weights of the real config, bf16) -- none of this repo's kernels.  trl / accelerate /
-deepspeed are absent, so the HF Trainer plumbing is replaced by the plain loop below; the model calls are the reference's:
+"""The reference's GRPO step on the reference's own model stack -- NONE of this repo's kernels.
+
+`HFStep` restates `SGRLVRTrainer.compute_loss` + the HF Trainer's backward/optimizer
+(SG_RLVR_trainer.py:384-686, run_SpaceR_SG_RLVR.sh:16-39) over the stock Hugging Face
+`Qwen2VLForConditionalGeneration` (transformers 5.5.0, random-init weights of the real config).  trl / accelerate /
+deepspeed are absent from this image, so the Trainer plumbing is the plain loop below; the model calls are the reference's:
     generate(num_return_sequences=G, do_sample, top_p .95)  (+ G/2 on the frame-shuffled video)     TRN:463-481
-    reference-policy forward over the G full sequences with xG-repeated pixels, no grad            TRN:534-547
+    reference-policy forward over the G full sequences with xG-repeated pixels, inference_mode     TRN:534-547
     policy forward (gradient checkpointing, as run_SpaceR_SG_RLVR.sh:27) -> per-row log_softmax/gather -> GRPO loss
-    -> backward -> clip 5 -> AdamW                                                                  TRN:353-366, 640-643
+    -> backward -> (N > 1: gradient all-reduce over NCCL) -> clip 5 -> AdamW                        TRN:353-366, 640-643
+Two uses:
+  * on the B200 (bf16, flash_attention_2 as run_SpaceR_SG_RLVR.sh:31 configures): the comparator of BASELINE's
+    ">= 5x the reference HF/PyTorch GRPO step" target -- `bench.py` runs it as its `hf_gpu_baseline` leg, at N ranks;
+  * on the host cores (fp32, eager attention): the reference's CPU path as a REAL full step at cfg1 / cfg2
+    (`tools/cpu_reference_step.py`, bench.py's cpu_baseline).
     python tools/hf_gpu_baseline.py [--config c3] [--attn sdpa|flash_attention_2|eager] [--steps 1] [--device cuda]
 Prints one JSON line (samples/s, ms per phase)."""
 import argparse
@@ -18,10 +25,6 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
-
-import bench  # noqa: E402
-from spacer_b200 import config as mcfg  # noqa: E402  (dimensions and host-side position ids only; no kernels)
-from spacer_b200.model import rope_index  # noqa: E402
 
 
 def hf_config(d):
@@ -60,59 +63,70 @@ def grpo_loss(lp, ref_lp, adv, mask, beta):
     return ((per_tok * mask).sum(1) / mask.sum(1)).mean()
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--config", default="c3")
-    ap.add_argument("--attn", default="sdpa")
-    ap.add_argument("--steps", type=int, default=1)
-    ap.add_argument("--device", default="cuda")
-    ap.add_argument("--completion", type=int, default=0, help="override C (debug)")
-    a = ap.parse_args()
-    from transformers import Qwen2VLForConditionalGeneration
-    cfg = dict(bench.CONFIGS[a.config])
-    if a.completion:
-        cfg["C"] = a.completion
-    d = mcfg.PRESETS[cfg["preset"]]()
-    dev = torch.device(a.device)
-    dt = torch.bfloat16 if dev.type == "cuda" else torch.float32
-    hc = hf_config(d)
-    hc._attn_implementation = a.attn
-    torch.manual_seed(0)
-    with torch.device(dev):
-        model = Qwen2VLForConditionalGeneration(hc).to(dt)
-        ref = Qwen2VLForConditionalGeneration(hc).to(dt)
-    ref.load_state_dict(model.state_dict())
-    ref.eval()
-    model.gradient_checkpointing_enable()
-    model.config.use_cache = True
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-6, weight_decay=0.01, fused=dev.type == "cuda")
-    ex = bench.synth_example(d, cfg, 1234)
-    pix = ex["pixel_values_host"].to(dev, dt)
-    grid = ex["video_grid_thw"].to(dev)
-    ids = ex["input_ids"].to(dev)
-    P = ids.shape[1]
-    G, C = cfg["G"], cfg["C"]
-    mm = ((ids == d.video_token_id).long() * 2 + (ids == d.image_token_id).long())
-    pix2 = pix.flip(0).contiguous()
+class HFStep:
+    """One process = one rank = one prompt per step, like the reference (per_device_train_batch_size 1)."""
 
-    def sync():
-        if dev.type == "cuda":
+    def __init__(self, cfg: dict, device, attn: str | None = None, seed: int = 1234, dist_group=None, world: int = 1):
+        import bench
+        from spacer_b200 import config as mcfg   # dimensions and the host-side position-id helper only; no kernels
+        from transformers import Qwen2VLForConditionalGeneration
+        self.cfg, self.dev = cfg, torch.device(device)
+        self.d = d = mcfg.PRESETS[cfg["preset"]]()
+        gpu = self.dev.type == "cuda"
+        self.dt = torch.bfloat16 if gpu else torch.float32
+        if attn is None:
+            attn = "eager"
+            if gpu:
+                try:
+                    import flash_attn  # noqa: F401
+                    attn = "flash_attention_2"
+                except Exception:
+                    attn = "sdpa"
+        self.attn = attn
+        hc = hf_config(d)
+        hc._attn_implementation = attn
+        torch.manual_seed(0)
+        with torch.device(self.dev):
+            self.model = Qwen2VLForConditionalGeneration(hc).to(self.dt)
+            self.ref = Qwen2VLForConditionalGeneration(hc).to(self.dt)
+        self.ref.load_state_dict(self.model.state_dict())
+        self.ref.eval()
+        self.model.gradient_checkpointing_enable()
+        self.model.config.use_cache = True
+        self.opt = torch.optim.AdamW(self.model.parameters(), lr=1e-6, weight_decay=0.01, fused=gpu)
+        ex = bench.synth_example(d, cfg, seed)
+        self.pix = ex["pixel_values_host"].to(self.dev, self.dt)
+        self.grid = ex["video_grid_thw"].to(self.dev)
+        self.ids = ex["input_ids"].to(self.dev)
+        self.pix2 = self.pix.flip(0).contiguous()
+        self.group, self.world = dist_group, world
+
+    def sync(self):
+        if self.dev.type == "cuda":
             torch.cuda.synchronize()
 
-    def step(C_):
+    def step(self, C=None, temporal=True):
+        from spacer_b200.model import rope_index
+        d, dev, model, ref = self.d, self.dev, self.model, self.ref
+        ids, pix, grid = self.ids, self.pix, self.grid
+        G = self.cfg["G"]
+        C_ = self.cfg["C"] if C is None else C
+        P = ids.shape[1]
+        mm = (ids == d.video_token_id).long() * 2 + (ids == d.image_token_id).long()
         t = {}
-        sync(); t0 = time.perf_counter()
+        self.sync(); t0 = time.perf_counter()
         model.eval()
         with torch.no_grad():
             kw = dict(max_new_tokens=C_, min_new_tokens=C_, do_sample=True, top_p=0.95, temperature=1.0,
                       pad_token_id=d.pad_id, use_cache=True)
             out = model.generate(input_ids=ids, mm_token_type_ids=mm, pixel_values_videos=pix, video_grid_thw=grid,
                                  num_return_sequences=G, **kw)
-            model.generate(input_ids=ids, mm_token_type_ids=mm, pixel_values_videos=pix2, video_grid_thw=grid,
-                           num_return_sequences=G // 2, **kw)
-        sync(); t["rollout"] = time.perf_counter() - t0
+            if temporal:
+                model.generate(input_ids=ids, mm_token_type_ids=mm, pixel_values_videos=self.pix2, video_grid_thw=grid,
+                               num_return_sequences=G // 2, **kw)
+        self.sync(); t["rollout"] = time.perf_counter() - t0
         full = out                                            # [G, P + C]
-        mmf = ((full == d.video_token_id).long() * 2 + (full == d.image_token_id).long())
+        mmf = (full == d.video_token_id).long() * 2 + (full == d.image_token_id).long()
         pos = torch.stack([rope_index(row, grid.cpu(), d, "classic")[0] for row in full.cpu()], dim=1).to(dev)
         pixG, gridG = pix.repeat(G, 1), grid.repeat(G, 1)
         t0 = time.perf_counter()
@@ -121,7 +135,7 @@ def main():
                      use_cache=False).logits
             ref_lp = per_token_logps(rl, full)[:, P - 1:]
             del rl
-        sync(); t["ref_scoring"] = time.perf_counter() - t0
+        self.sync(); t["ref_scoring"] = time.perf_counter() - t0
         t0 = time.perf_counter()
         model.train()
         logits = model(input_ids=full, pixel_values_videos=pixG, video_grid_thw=gridG, position_ids=pos, mm_token_type_ids=mmf,
@@ -137,25 +151,58 @@ def main():
         adv = (rewards - rewards.mean()) / (rewards.std() + 1e-4)             # TRN:632-638
         loss = grpo_loss(lp.float(), ref_lp.float().clone(), adv, mask, 0.04)
         loss.backward()
+        self.sync(); t["policy_fwd_bwd"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        if self.world > 1:       # data parallel like the reference (one prompt per rank): gradients averaged over ranks
+            import torch.distributed as dist
+            grads = [p.grad for p in model.parameters() if p.grad is not None]
+            for g in grads:
+                dist.all_reduce(g, group=self.group)
+            torch._foreach_div_(grads, float(self.world))
+            self.sync(); t["grad_allreduce"] = time.perf_counter() - t0
+            t0 = time.perf_counter()
         torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0)
-        opt.step()
-        opt.zero_grad(set_to_none=True)
-        sync(); t["policy_fwd_bwd_adamw"] = time.perf_counter() - t0
+        self.opt.step()
+        self.opt.zero_grad(set_to_none=True)
+        self.sync(); t["clip_adamw"] = time.perf_counter() - t0
+        t["loss"] = float(loss.item())
         return t
 
-    step(min(C, 4))                                           # warm-up (allocator, kernels, autotune)
+    def free(self):
+        self.model = self.ref = self.opt = None
+        import gc
+        gc.collect()
+        if self.dev.type == "cuda":
+            torch.cuda.empty_cache()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="c3")
+    ap.add_argument("--attn", default=None)
+    ap.add_argument("--steps", type=int, default=1)
+    ap.add_argument("--device", default="cuda")
+    ap.add_argument("--completion", type=int, default=0, help="override C (debug)")
+    a = ap.parse_args()
+    import bench
+    cfg = dict(bench.CONFIGS[a.config])
+    if a.completion:
+        cfg["C"] = a.completion
+    hs = HFStep(cfg, a.device, a.attn)
+    G, C = cfg["G"], cfg["C"]
+    hs.step(min(C, 4))                                        # warm-up (allocator, kernels, autotune)
     tot = {}
     t0 = time.perf_counter()
     for _ in range(a.steps):
-        for k, v in step(C).items():
+        for k, v in hs.step(C).items():
             tot[k] = tot.get(k, 0.0) + v
-    sync()
+    hs.sync()
     wall = (time.perf_counter() - t0) / a.steps
-    print(json.dumps({"impl": "hf_gpu_restatement", "config": cfg["workload"], "attn_implementation": a.attn, "device": str(dev),
-                      "transformers": __import__("transformers").__version__, "dtype": str(dt), "steps": a.steps,
+    print(json.dumps({"impl": "hf_restatement", "config": cfg["workload"], "attn_implementation": hs.attn, "device": str(hs.dev),
+                      "transformers": __import__("transformers").__version__, "dtype": str(hs.dt), "steps": a.steps,
                       "s_per_step": round(wall, 3), "samples_per_s": round(G / wall, 4),
                       "rollout_tok_per_s": round((G + G // 2) * C / (tot["rollout"] / a.steps), 1),
-                      "phase_s": {k: round(v / a.steps, 3) for k, v in tot.items()}}))
+                      "phase_s": {k: round(v / a.steps, 3) for k, v in tot.items() if k != "loss"}}))
 
 
 if __name__ == "__main__":
