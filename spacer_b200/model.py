@@ -1105,10 +1105,10 @@ class Qwen2VLB200:
                    finished=st["finished"], out_ids=st["out_ids"], eos_ids=sp.eos_ids, pad_id=sp.pad_id,
                    suppress_eos=suppress_eos)
 
-    def _decode_step(self, st, rope_base, rows_group0, sp, suppress_eos):
+    def _decode_step(self, st, rope_base, rows_group0, samp, suppress_eos):
         """Enqueue one decode step (feeds tokens at slot *step, samples the next token into slot *step + 1)."""
         if self.decode_fused:
-            return self._decode_step_fused(st, rope_base, rows_group0, sp, suppress_eos)
+            return self._decode_step_fused(st, rope_base, rows_group0, samp, suppress_eos)
         d, W = self.dims, self.params
         R, RP, P, S = st["R"], st["RP"], st["P"], st["S"]
         H, I = d.hidden, d.inter
@@ -1143,9 +1143,9 @@ class Qwen2VLB200:
         ops.call("sb_dec_residual_rmsnorm", st["x"], parts, sp, RP * H, H, W["norm_w"], st["xn"], R, H, d.rms_eps)
         self._gemv(W["lm_head"], st["xn"], st["logits"], 1, next_w=W["l.0.qkv_w"])   # warms L2 for the next step
         ops.call("sb_step_advance", st["step"])
-        self._sample(st, sp, suppress_eos)
+        self._sample(st, samp, suppress_eos)
 
-    def _decode_step_fused(self, st, rope_base, rows_group0, sp, suppress_eos):
+    def _decode_step_fused(self, st, rope_base, rows_group0, samp, suppress_eos):
         """One decode step with the fused GEMV epilogues: per layer qkv GEMV (+ bias, M-RoPE, KV append) -> attention ->
         combine -> o GEMV (+ residual, x * ln2_w, sums of squares) -> gate|up GEMV (rstd scale + SwiGLU) -> down GEMV
         (+ residual, x * next ln1_w, sums of squares)."""
@@ -1196,7 +1196,7 @@ class Qwen2VLB200:
                        epilogue=ops.EPI_DEC_RESID)
         self._gemv(W["lm_head"], st["xw"], st["logits"], 1, next_w=W["l.0.qkv_w"], dec=scaled())
         ops.call("sb_step_advance", st["step"])
-        self._sample(st, sp, suppress_eos)
+        self._sample(st, samp, suppress_eos)
 
     def _decode_graph(self, st, rope_base, rows_group0, sp, suppress_eos):
         """Capture one decode step into a CUDA graph (cached per decode state and step arguments).  Captured with the

@@ -115,8 +115,6 @@ def _run(preset, frames, res, text, G, C, tag, fp32_truth, ckpt=False, beta=0.04
     ref_lp = lp_hf0 + 0.05 * torch.randn(lp_hf0.shape, generator=torch.Generator().manual_seed(9)).cuda()
     lp_hf, loss_hf, g_hf = _hf_scores(hf, d, case, G, ref_lp, adv, mask, beta, torch.bfloat16, ckpt)
     del hf
-    if not fp32_truth:
-        del sd
     torch.cuda.empty_cache()
     # this engine, same weights, same inputs
     batch = pack_prompt_completions(case["prompt"], case["comp"], case["grid"], d, eng.device)
@@ -141,7 +139,19 @@ def _run(preset, frames, res, text, G, C, tag, fp32_truth, ckpt=False, beta=0.04
              "grad_norm_ratio_range_vs_hf": [min(v[1] for v in st.values()), max(v[1] for v in st.values())],
              "worst_tensors_vs_hf": sorted(((k, round(v[0], 5), round(v[1], 4)) for k, v in st.items()), key=lambda t: t[1])[:6],
              "n_tensors": len(st)}
-    if fp32_truth:
+    if fp32_truth == "forward":      # 7B: the fp32 network fits for a forward only (no gradients next to everything else)
+        del g_hf, g_me, grads, st
+        torch.cuda.empty_cache()
+        hf32 = _hf_model(d, torch.float32, "sdpa")
+        hf32.load_state_dict({k: v.float() for k, v in sd.items()}, strict=False)
+        del sd
+        lp32, _, _ = _hf_scores(hf32, d, case, G, None, adv, mask, beta, torch.float32)
+        e_me, e_hf = (lp - lp32).abs()[m], (lp_hf - lp32).abs()[m]
+        stats.update({"lp_max_err_vs_fp32": e_me.max().item(), "lp_mean_err_vs_fp32": e_me.mean().item(),
+                      "hf_bf16_lp_max_err_vs_fp32": e_hf.max().item(), "hf_bf16_lp_mean_err_vs_fp32": e_hf.mean().item()})
+        del hf32
+        grads = None
+    elif fp32_truth:
         hf32 = _hf_model(d, torch.float32, "eager")
         hf32.load_state_dict({k: v.float() for k, v in sd.items()}, strict=False)
         lp32, loss32, g32 = _hf_scores(hf32, d, case, G, ref_lp, adv, mask, beta, torch.float32)
@@ -168,33 +178,46 @@ def _run(preset, frames, res, text, G, C, tag, fp32_truth, ckpt=False, beta=0.04
 
 
 def _common_asserts(s):
-    # two bf16 implementations of the same network (different GEMM tilings / accumulation orders, fp32 vs bf16 softmax
-    # statistics): each is within bf16 noise of the fp32 network; between themselves up to twice that
-    assert s["lp_max_err_vs_hf_bf16"] < 1.5e-1 and s["lp_mean_err_vs_hf_bf16"] < 2.5e-2, s
+    # Two bf16 implementations of the same network (different GEMM tilings / accumulation orders; HF also rounds the
+    # logits themselves to bf16: one ulp at |logit| ~ 4 is 0.03) sit within bf16 noise of the fp32 network EACH, so up to
+    # twice that apart.  Measured on B200 (gpurun_out/hf_parity_*.json, copies under profiles/): mean 0.021 / 0.031 / 0.048,
+    # max 0.059 / 0.196 / 0.187 at cfg1 / cfg2 / cfg3 dims; gradient cosines >= 0.9845 for all 729 / 730 tensors.
+    assert s["lp_max_err_vs_hf_bf16"] < 0.3 and s["lp_mean_err_vs_hf_bf16"] < 0.07, s
     assert abs(s["loss"] - s["loss_hf_bf16"]) < 5e-3 * max(1.0, abs(s["loss_hf_bf16"])) + 2e-3, s
-    assert s["grad_cos_weighted_vs_hf"] > 0.99 and s["grad_cos_mean_vs_hf"] > 0.98, s
-    assert s["grad_cos_min_vs_hf"] > 0.9, s["worst_tensors_vs_hf"]
+    assert s["grad_cos_weighted_vs_hf"] > 0.99 and s["grad_cos_mean_vs_hf"] > 0.99, s
+    assert s["grad_cos_min_vs_hf"] > 0.97, s["worst_tensors_vs_hf"]
     lo, hi = s["grad_norm_ratio_range_vs_hf"]
-    assert 0.85 < lo and hi < 1.15, s["worst_tensors_vs_hf"]
+    assert 0.93 < lo and hi < 1.07, s["worst_tensors_vs_hf"]
+
+
+def _not_further_from_fp32_than_hf(s, grads=True):
+    """The yardstick that licenses any tolerance above SURVEY 8(c)'s 2e-2 / 3e-3: against the fp32 network this engine's
+    error is at most 1.2 x the error of HF's own bf16 path (measured: 1.09 x mean / 0.75 x max at cfg1)."""
+    assert s["lp_mean_err_vs_fp32"] <= 1.2 * s["hf_bf16_lp_mean_err_vs_fp32"] + 1e-3, s
+    assert s["lp_max_err_vs_fp32"] <= 1.2 * s["hf_bf16_lp_max_err_vs_fp32"] + 1e-2, s
+    if grads:
+        assert (1 - s["grad_cos_mean_vs_fp32"]) <= 1.2 * (1 - s["hf_bf16_grad_cos_mean_vs_fp32"]) + 1e-3, s
+        assert (1 - s["grad_cos_min_vs_fp32"]) <= 1.5 * (1 - s["hf_bf16_grad_cos_min_vs_fp32"]) + 2e-3, s
+        assert abs(s["loss"] - s["loss_fp32"]) <= 1.2 * abs(s["loss_hf_bf16"] - s["loss_fp32"]) + 1e-3, s
 
 
 def test_cfg1_dims_vs_hf_bf16_and_fp32():
     """cfg1 (BASELINE configs[0]): Qwen2-VL-2B, 2 frames 224^2 (grid 1x16x16), P = 128, G = 2, C = 16."""
     s = _run("2b", 2, 224, 64, 2, 16, "cfg1", fp32_truth=True)
     _common_asserts(s)
-    # the engine is not further from the fp32 network than HF's own bf16 path is
-    assert s["lp_mean_err_vs_fp32"] <= 1.2 * s["hf_bf16_lp_mean_err_vs_fp32"] + 1e-3, s
-    assert s["lp_max_err_vs_fp32"] <= 1.2 * s["hf_bf16_lp_max_err_vs_fp32"] + 1e-2, s
-    assert (1 - s["grad_cos_mean_vs_fp32"]) <= 1.2 * (1 - s["hf_bf16_grad_cos_mean_vs_fp32"]) + 1e-3, s
-    assert abs(s["loss"] - s["loss_fp32"]) <= 1.2 * abs(s["loss_hf_bf16"] - s["loss_fp32"]) + 1e-3, s
+    _not_further_from_fp32_than_hf(s)
 
 
 def test_cfg2_dims_vs_hf_bf16():
     """cfg2 (configs[1]): Qwen2-VL-2B, 8 frames 336^2 (grid 4x24x24), P = 832, G = 4, C = 512."""
-    _common_asserts(_run("2b", 8, 336, 256, 4, 512, "cfg2", fp32_truth=False))
+    s = _run("2b", 8, 336, 256, 4, 512, "cfg2", fp32_truth=True)
+    _common_asserts(s)
+    _not_further_from_fp32_than_hf(s)
 
 
 def test_cfg3_dims_vs_hf_bf16():
     """cfg3 dims (configs[2], the headline): Qwen2-VL-7B, 16 frames 448^2 (grid 8x32x32), P = 2304; G = 2 rows of C = 64
     (HF with gradient checkpointing) -- every one of the 7B model's parameter gradients against HF's."""
-    _common_asserts(_run("7b", 16, 448, 256, 2, 64, "cfg3", fp32_truth=False, ckpt=True))
+    s = _run("7b", 16, 448, 256, 2, 64, "cfg3", fp32_truth="forward", ckpt=True)
+    _common_asserts(s)
+    _not_further_from_fp32_than_hf(s, grads=False)
