@@ -378,6 +378,9 @@ def main():
     ap.add_argument("--hf-steps", type=int, default=3)
     ap.add_argument("--moments-bf16", action="store_true")
     ap.add_argument("--no-temporal", action="store_true")
+    ap.add_argument("--grad-ckpt", choices=["auto", "on", "off"], default="auto", help="selective activation recompute "
+                    "(gate|up projection) in the policy backward; auto = on for cfg4 / cfg5, whose 8448 / 10496 packed "
+                    "tokens do not fit next to fp32 Adam state otherwise")
     ap.add_argument("--no-overlap", action="store_true", help="gradient all-reduce after the backward instead of overlapped")
     ap.add_argument("--no-zero1", action="store_true", help="N > 1: all-reduce + replicated AdamW instead of the default ZeRO-1 "
                     "(reduce-scatter, AdamW on the own 1/N of the arena, all-gather of the bf16 weights)")
@@ -413,6 +416,7 @@ def main():
             gc.collect()
             torch.cuda.empty_cache()
 
+    torch.cuda.reset_peak_memory_stats()
     # weights: policy random-init (seed 0 on every rank), reference = copy of the initial policy
     policy = Qwen2VLB200(dims, dev)
     policy.params.init_random(seed=0)
@@ -425,7 +429,9 @@ def main():
         dist.broadcast(policy.params.mat, 0)
         dist.broadcast(policy.params.vec, 0)
     RW.set_map_data(SYN_MAP)
+    grad_ckpt = args.grad_ckpt == "on" or (args.grad_ckpt == "auto" and args.config in ("c4", "c5"))
     tcfg = GRPOConfig(num_generations=cfg["G"], max_completion_length=cfg["C"], min_new_tokens=cfg["C"],
+                      gradient_checkpointing=grad_ckpt,
                       temporal=not args.no_temporal, moments_bf16=args.moments_bf16, max_steps=1000,
                       overlap_allreduce=not args.no_overlap, zero1=not args.no_zero1)
     trainer = SGRLVRTrainerB200(policy, ref, [RW.accuracy_reward, RW.format_reward], tcfg, synth_decode)
@@ -545,6 +551,8 @@ def main():
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": cfg["workload"], "parallelism": f"dp{world}", "inputs": "larger than L2 (14 GB of weights streamed per decode step); step input = uint8 video frames",
                        "adam_moments": "bf16" if args.moments_bf16 else "fp32", "temporal": tcfg.temporal,
+                       "activation_recompute": "gate|up projection" if grad_ckpt else "none",
+                       "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
                        "grad_sync": ("zero1" if not args.no_zero1 else ("allreduce" if args.no_overlap else "overlapped allreduce")) if world > 1 else None,
                        "rollout_tok_per_s": (world * (toks / K) / (stats["rollout_ms"] / 1000.0)) if stats.get("rollout_ms") else None,
                        "tok_per_s_of_step": world * toks / (ms_res / 1000.0),

@@ -238,11 +238,12 @@ class Qwen2VLForConditionalGenerationB200(torch.nn.Module):
         return torch.bfloat16
 
     def gradient_checkpointing_enable(self, gradient_checkpointing_kwargs=None):
-        """Accepted (HF Trainer calls it under --gradient_checkpointing true): the activations of one step fit in HBM
-        next to the weights on a 180 GB part, nothing is recomputed."""
+        """HF Trainer calls it under --gradient_checkpointing true (run_SpaceR_SG_RLVR.sh:27): the engine then recomputes
+        its widest activation (the gate|up projection) in the backward instead of keeping it."""
+        self.engine.gradient_checkpointing_enable()
 
     def gradient_checkpointing_disable(self):
-        pass
+        self.engine.gradient_checkpointing_disable()
 
     def enable_input_require_grads(self):
         pass

@@ -331,11 +331,19 @@ class Qwen2VLB200:
         from . import hub
         hub.save_pretrained(self, path, **kw)
 
-    def gradient_checkpointing_enable(self, **kw):
-        """Accepted for API compatibility (HF Trainer calls it): activations of one step fit in HBM, nothing is recomputed."""
+    # Selective activation recompute: the raw gate|up projection (2 x 18944 of the ~53k bf16 values a decoder layer saves
+    # per token at 7B: 71 % of the activation memory) is not kept for the backward but recomputed there from the saved
+    # layer input with one extra GEMM per layer (+1/3 of a forward's FLOPs).  cfg3 fits without it (149 GB of state +
+    # ~26 GB of activations); cfg4 / cfg5 (8448 / 10496 packed tokens) need it on a 180 GB part with fp32 Adam moments.
+    recompute_mlp = False
+
+    def gradient_checkpointing_enable(self, gradient_checkpointing_kwargs=None, **kw):
+        """What HF Trainer calls under `--gradient_checkpointing true` (run_SpaceR_SG_RLVR.sh:27).  The reference recomputes
+        whole decoder layers; here only the widest activation is recomputed (see `recompute_mlp`)."""
+        self.recompute_mlp = True
 
     def gradient_checkpointing_disable(self):
-        pass
+        self.recompute_mlp = False
 
     def named_parameters(self):
         return list(self.params.hf_items())
@@ -584,7 +592,7 @@ class Qwen2VLB200:
             a = r2[0] if save else r2
             x2 = ops.gemm(a, W[p + "o_w"], residual=x)
             r3 = ops.rmsnorm_fwd(x2, W[p + "ln2_w"], d.rms_eps, save_stats=save, out=h)
-            gu = torch.empty((T, 2 * d.inter), device=self.device, dtype=BF16) if save else None
+            gu = torch.empty((T, 2 * d.inter), device=self.device, dtype=BF16) if save and not self.recompute_mlp else None
             act = ops.gemm(h, W[p + "gu_w"], epilogue=EPI_SWIGLU, aux=gu)
             x3 = ops.gemm(act, W[p + "down_w"], residual=x2)
             if save:
@@ -637,9 +645,11 @@ class Qwen2VLB200:
             x2[:P].copy_(pt["x2"])
             ops.gemm(a[P:], W[p + "o_w"], residual=x[P:], out=x2[P:])
             r3 = ops.rmsnorm_fwd(x2[P:], W[p + "ln2_w"], d.rms_eps, save_stats=True, out=h)
-            gu = torch.empty((T, 2 * d.inter), device=self.device, dtype=BF16)
-            gu[:P].copy_(pt["gu"])
-            act = ops.gemm(h, W[p + "gu_w"], epilogue=EPI_SWIGLU, aux=gu[P:])
+            gu = None
+            if not self.recompute_mlp and pt["gu"] is not None:
+                gu = torch.empty((T, 2 * d.inter), device=self.device, dtype=BF16)
+                gu[:P].copy_(pt["gu"])
+            act = ops.gemm(h, W[p + "gu_w"], epilogue=EPI_SWIGLU, aux=None if gu is None else gu[P:])
             x3 = torch.empty((T, H), device=self.device, dtype=BF16)
             x3[:P].copy_(pl[i + 1]["x"] if i + 1 < d.layers else ptape["x_last"])
             ops.gemm(act, W[p + "down_w"], residual=x2[P:], out=x3[P:])
@@ -667,13 +677,19 @@ class Qwen2VLB200:
         d_a = torch.empty((T, nq), device=self.device, dtype=BF16)
         d_qkv = torch.empty((T, d.qkv_dim), device=self.device, dtype=BF16)
         delta = torch.empty((nh, T), device=self.device, dtype=F32)
+        gu_buf = None
         for i in reversed(range(d.layers)):
             p = f"l.{i}."
             t = tape["layers"][i]
             ops.gemm(dx, W[p + "down_w"], b_mn=True, out=d_act)
-            ops.call("sb_swiglu_bwd", t["gu"], d_act, d_gu, act, T, I)
-            ops.gemm(dx, act, a_mn=True, b_mn=True, out=G[p + "down_w"])
+            gu = t["gu"]
             ops.rmsnorm_fwd(t["x2"], W[p + "ln2_w"], d.rms_eps, out=h)
+            if gu is None:        # recompute_mlp: the raw gate|up projection again, bit-identical to the forward's
+                if gu_buf is None:
+                    gu_buf = torch.empty((T, 2 * I), device=self.device, dtype=BF16)
+                gu = ops.gemm(h, W[p + "gu_w"], out=gu_buf)
+            ops.call("sb_swiglu_bwd", gu, d_act, d_gu, act, T, I)
+            ops.gemm(dx, act, a_mn=True, b_mn=True, out=G[p + "down_w"])
             ops.gemm(d_gu, h, a_mn=True, b_mn=True, out=G[p + "gu_w"])
             ops.gemm(d_gu, W[p + "gu_w"], b_mn=True, out=d_h)
             dx2 = ops.rmsnorm_bwd(t["x2"], W[p + "ln2_w"], t["s2"], d_h, G[p + "ln2_w"], dres=dx)

@@ -53,6 +53,7 @@ class GRPOConfig:
     max_steps: int = 1000
     warmup_steps: int = 0
     seed: int = 42
+    gradient_checkpointing: bool = False   # run_SpaceR_SG_RLVR.sh:27; here: recompute the gate|up activation (model.py)
     top_k: int = TOP_K              # 0 = nucleus sampling only
     eos_token_ids: tuple = ()       # ids that end a rollout row (HF: generation_config.eos_token_id); () = the model's
     moments_bf16: bool = False      # fp32 moments like DeepSpeed unless memory forces otherwise
@@ -221,6 +222,8 @@ class SGRLVRTrainerB200:
                  process_group=None):
         self.model, self.ref_model, self.reward_funcs, self.cfg = model, ref_model, list(reward_funcs), cfg
         self.decode_completions = decode_completions
+        if cfg.gradient_checkpointing:
+            model.gradient_checkpointing_enable()
         self.grads = GradStore(model.params)
         self.pg = process_group
         self.zero1 = bool(cfg.zero1) and D.world_size(process_group) > 1

@@ -112,6 +112,39 @@ def test_grpo_forward_backward_matches_oracle():
     assert mean_cos > 0.999, mean_cos
 
 
+def test_activation_recompute_is_bit_identical():
+    """gradient_checkpointing_enable() (HF Trainer under --gradient_checkpointing true, run_SpaceR_SG_RLVR.sh:27): the
+    gate|up projection is recomputed in the backward instead of saved -- same loss, bit-identical gradients, with and
+    without the rollout's prefix reuse."""
+    from spacer_b200.model import GradStore, pack_prompt_completions
+    R, d_or, d, m, w, wb = _setup()
+    case = _case(d_or)
+    grid, pix = case["grid_thw"], case["pixel_values"].cuda()
+    G = case["input_ids"].shape[0]
+    adv = torch.tensor([0.7, -1.1, 0.2, 0.4]).cuda()
+    ref_lp = torch.load(os.path.join(GOLD, "tiny_model.pt"), weights_only=False)["ref_logps"].cuda()
+    batch = pack_prompt_completions(case["prompt_ids"], case["completion_ids"], grid, d, m.device)
+    res = {}
+    for mode in ("keep", "recompute", "recompute+prefix_reuse"):
+        m.gradient_checkpointing_disable()
+        if mode != "keep":
+            m.gradient_checkpointing_enable()
+        vc = None
+        if mode.endswith("prefix_reuse"):
+            m.generate(case["prompt_ids"], pix, grid, max_new_tokens=2, num_return_sequences=G, seed=1, min_new_tokens=2,
+                       keep_vit_tape=True)
+            vc = m.vit_cache
+            assert vc is not None and vc["llm_tape"]["layers"][0]["gu"] is None
+        grads = GradStore(m.params)
+        out = m.grpo_forward_backward(batch, pix, grid, ref_lp, adv, 0.04, grads, vit_cache=vc)
+        torch.cuda.synchronize()
+        res[mode] = (out["loss"].item(), grads.mat.clone(), grads.vec.clone())
+    for mode in ("recompute", "recompute+prefix_reuse"):
+        assert res[mode][0] == res["keep"][0]
+        assert torch.equal(res[mode][1], res["keep"][1]) and torch.equal(res[mode][2], res["keep"][2]), mode
+    m.gradient_checkpointing_disable()
+
+
 def test_generate_semantics_and_decode_parity():
     """generate(): prompt echoed, C' columns, EOS/pad handling, seed determinism; the logits of the LAST decode
     step (decode kernels + KV caches) match the oracle's full forward on the generated ids."""
