@@ -37,6 +37,23 @@ constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int GEMM_THREADS = 192;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 
+// Decode GEMVs run SB_GEMV_PIPES independent producer/MMA-issuer thread pairs per CTA.  One pair tops out at ~48 GB/s of
+// weights whatever the number of CTAs: its per-stage work is SERIAL (mbarrier try_wait ~90 cycles + expect_tx + two TMA
+// issues on one thread; try_wait + fence + four tcgen05.mma + commit on the other) and costs ~0.34 us per 16 KB stage.
+// Two pairs on alternating K blocks, each with its own half of the stage ring and its own TMEM accumulator (summed by
+// the epilogue), reach 62 GB/s per CTA at 112 CTAs (HBM-bound, 6.9 TB/s) and 82-88 GB/s at <= 74 CTAs
+// (tools/labs/ingest_dual_lab.cu, profiles/r02_ingest_dual_lab.md) -- which is what lets the cluster-fused epilogues, that
+// can only occupy 108-112 SMs, stream at full HBM speed.
+#ifndef SB_GEMV_PIPES
+#define SB_GEMV_PIPES 2
+#endif
+constexpr bool is_dec_epi(int epi) {
+  return epi == SB_EPI_F32T || epi == SB_EPI_F32T_SWIGLU || epi == SB_EPI_DEC_QKV || epi == SB_EPI_DEC_RESID;
+}
+constexpr int gemm_pipes(int epi) { return (is_dec_epi(epi) && !SB_GEMV_ACT_A) ? SB_GEMV_PIPES : 1; }
+// warps: 0 producer, 1 MMA issuer (+ TMEM allocator), 2-5 epilogue, then one (producer, MMA) warp pair per extra pipeline
+constexpr int gemm_threads(int epi) { return GEMM_THREADS + 64 * (gemm_pipes(epi) - 1); }
+
 struct GemmParams {
   int M, N, K;
   int m_tiles, n_tiles, k_splits, k_iters, k_iters_per_split;
@@ -74,12 +91,21 @@ struct Cfg {
   // the narrow decode tiles (BN <= 32) are latency-bound: throughput per CTA = bytes in flight / slot round trip
   // (tools/labs/ingest_mma_lab.cu), so they take every stage that fits; the wide tiles are MMA-bound at 4-8 stages
   static constexpr int NSTAGES_CAP = BN <= 32 ? SB_GEMV_STAGES : 8;
-  static constexpr int NSTAGES = NSTAGES_RAW > NSTAGES_CAP ? NSTAGES_CAP : NSTAGES_RAW;
+  static constexpr int NSTAGES_FIT = NSTAGES_RAW > NSTAGES_CAP ? NSTAGES_CAP : NSTAGES_RAW;
+  // decode tiles: a whole number of stages per pipeline
+  static constexpr int NSTAGES = BN <= 32 ? (NSTAGES_FIT / SB_GEMV_PIPES) * SB_GEMV_PIPES : NSTAGES_FIT;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  // decode tiles: 2 accumulators (epilogue overlap) x SB_GEMV_PIPES pipelines x BN columns, a power of two >= 32
+  static constexpr int TMEM_COLS_DEC = (2 * SB_GEMV_PIPES * BN <= 32) ? 32 : (2 * SB_GEMV_PIPES * BN <= 64) ? 64 :
+                                       (2 * SB_GEMV_PIPES * BN <= 128) ? 128 : 256;
   // gate/up exchange of the fused decode SwiGLU epilogue / rotary-partner exchange of DEC_QKV / cross-warp scratch of
   // DEC_RESID, then 32 per-row scales of the fused decode epilogues
   static constexpr int XBUF_BYTES = 128 * 33 * 4 + 256;
   static constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + XBUF_BYTES;
+  // cluster-fused decode epilogues: rank 0 also holds the partial tiles of the other ranks (dec_red_bytes), so the ring
+  // is 8 stages (2 pipelines x 4: still 62 GB/s per CTA at 112 CTAs, i.e. HBM-bound; tools/labs/ingest_dual_lab.cu)
+  static constexpr int NSTAGES_CLU = NSTAGES < 8 ? NSTAGES : (8 / SB_GEMV_PIPES) * SB_GEMV_PIPES;
+  static constexpr int SMEM_BYTES_CLU = NSTAGES_CLU * STAGE_BYTES + 1024 + 256 + XBUF_BYTES;
 };
 
 SB_DEVICE float quick_gelu(float x) { return x / (1.f + __expf(-1.702f * x)); }
@@ -182,12 +208,34 @@ SB_DEVICE void dec_resid_finish(const GemmParams& p, int mt, int e, const float*
   epi_bar();
 }
 
+// this thread's BN accumulator columns of a decode tile, summed over the pipelines that hold a share of it (fixed order)
+template <int BN, int NP>
+SB_DEVICE void dec_load_acc(uint32_t taddr, int n_pl, uint32_t* r) {
+  if constexpr (BN == 16) tmem_ld_32x16(taddr, r);
+  else tmem_ld_32x32(taddr, r);
+  tmem_ld_wait();
+#pragma unroll
+  for (int pl = 1; pl < NP; ++pl) {
+    if (pl < n_pl) {
+      uint32_t r2[BN];
+      if constexpr (BN == 16) tmem_ld_32x16(taddr + pl * BN, r2);
+      else tmem_ld_32x32(taddr + pl * BN, r2);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < BN; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+    }
+  }
+}
+
 template <bool A_MN, bool B_MN, int BN, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(gemm_threads(EPI), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const GemmParams p) {
   using C = Cfg<BN>;
-  constexpr int NSTAGES = C::NSTAGES;
+  constexpr int NSTAGES = (EPI == SB_EPI_DEC_QKV || EPI == SB_EPI_DEC_RESID) ? C::NSTAGES_CLU : C::NSTAGES;
+  constexpr int NP = gemm_pipes(EPI);            // producer / MMA-issuer pairs (pipelines) in this CTA
+  static_assert(NSTAGES % NP == 0, "the stage ring is split evenly between the pipelines");
+  constexpr int NSUB = NSTAGES / NP;             // stages per pipeline: pipeline pl owns stages pl, pl + NP, ...
   // the swap-AB weight-streaming GEMVs of the decode step (PDL launch, early weight ring, L2 prefetch of the next matrix)
   constexpr bool kDec = EPI == SB_EPI_F32T || EPI == SB_EPI_F32T_SWIGLU || EPI == SB_EPI_DEC_QKV || EPI == SB_EPI_DEC_RESID;
   // kActA: the <= 16 decode rows are the A operand (M = 64, rows 16.. are whatever follows in shared memory and produce
@@ -196,7 +244,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   // CTAs (tools/labs/ingest_mma_lab.cu, profiles/r01_ingest_labs.md), and each epilogue thread owns one decode row.
   constexpr bool kActA = (EPI == SB_EPI_F32T || EPI == SB_EPI_F32T_SWIGLU) && BN == 16 && SB_GEMV_ACT_A;
   constexpr int ACC_COLS = kActA ? BM : BN;                 // TMEM columns of one accumulator
-  constexpr int TMEM_COLS = kActA ? 2 * BM : C::TMEM_COLS;
+  constexpr int TMEM_COLS = kActA ? 2 * BM : (NP > 1 ? C::TMEM_COLS_DEC : C::TMEM_COLS);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -228,7 +276,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(empty0 + 8 * s, 1);
     }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(tfull0 + 8 * a, 1);
+      mbar_init(tfull0 + 8 * a, NP);        // every pipeline's issuer reports its share of the tile
       mbar_init(tempty0 + 8 * a, 4);
     }
     if constexpr (kClu) mbar_init(redbar, csize > 1 ? csize - 1 : 1);
@@ -248,31 +296,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if constexpr (kClu) { t_begin = (int)crank * p.m_tiles + (int)(blockIdx.x / csize); t_step = total_tiles; }
 
   pdl_launch_dependents();
-  if (warp == 0) {
+  // pipeline of this warp when it is a producer / an MMA issuer (-1 otherwise)
+  const int prod_pl = warp == 0 ? 0 : ((NP > 1 && warp >= 6 && ((warp - 6) & 1) == 0) ? 1 + (warp - 6) / 2 : -1);
+  const int mma_pl = warp == 1 ? 0 : ((NP > 1 && warp >= 6 && ((warp - 6) & 1) == 1) ? 1 + (warp - 6) / 2 : -1);
+  if (prod_pl >= 0) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
+      const int pl = prod_pl;
       // Decode GEMVs (F32T, launched with PDL): the A operand is a weight matrix nobody writes during decode, so the
       // first ring of A tiles is requested BEFORE waiting for the preceding kernels -- the weight stream starts while
       // the small kernel that produces the activations (B operand) is still running.
       int pre = 0;
       int tr = -1;
       if constexpr (kDec) {
-        if (blockIdx.x == 0) { tr = sb_trace_begin(SB_TR_GEMV); *reinterpret_cast<volatile int*>(tmem_slot + 1) = tr; }
-        for (int t = t_begin; t < total_tiles && pre < NSTAGES; t += t_step) {
+        if (blockIdx.x == 0 && pl == 0) { tr = sb_trace_begin(SB_TR_GEMV); *reinterpret_cast<volatile int*>(tmem_slot + 1) = tr; }
+        for (int t = t_begin; t < total_tiles && pre < NSUB; t += t_step) {
           const int mt = t % p.m_tiles;
           const int ks = t / (p.m_tiles * p.n_tiles);
           const int kb0 = ks * p.k_iters_per_split;
           const int kb1 = min(kb0 + p.k_iters_per_split, p.k_iters);
-          for (int kb = kb0; kb < kb1 && pre < NSTAGES; ++kb, ++pre) {
-            const uint32_t fb = full0 + 8 * pre;
+          for (int kb = kb0 + pl; kb < kb1 && pre < NSUB; kb += NP, ++pre) {
+            const int st = pl + NP * pre;
+            const uint32_t fb = full0 + 8 * st;
             mbar_expect_tx(fb, C::STAGE_BYTES);
-            tma_load_2d(smem_base + pre * C::STAGE_BYTES, &tmA, fb, kb * BK, mt * BM);
+            tma_load_2d(smem_base + st * C::STAGE_BYTES, &tmA, fb, kb * BK, mt * BM);
           }
         }
       }
       pdl_wait();
       sb_trace_mark(tr, 1);
-      int stage = 0;
+      int si = 0;                 // position in this pipeline's sub-ring; stage = pl + NP * si
       uint32_t phase = 0;
       int issued = 0;
       for (int t = t_begin; t < total_tiles; t += t_step) {
@@ -281,7 +334,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int ks = t / (p.m_tiles * p.n_tiles);
         const int kb0 = ks * p.k_iters_per_split;
         const int kb1 = min(kb0 + p.k_iters_per_split, p.k_iters);
-        for (int kb = kb0; kb < kb1; ++kb, ++issued) {
+        for (int kb = kb0 + pl; kb < kb1; kb += NP, ++issued) {
+          const int stage = pl + NP * si;
           const uint32_t fb = full0 + 8 * stage;
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
           const uint32_t sb = sa + A_STAGE_BYTES;
@@ -303,10 +357,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int j = 0; j < BN / 64; ++j)
               tma_load_2d(sb + j * 8192, &tmB, fb, nt * BN + j * 64, kb * BK);
           }
-          if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+          if (++si == NSUB) { si = 0; phase ^= 1; }
         }
       }
-      if constexpr (kDec) {
+      if (kDec && pl == 0) {
         // Weight streaming never pauses: while the small kernels between two GEMVs run (HBM otherwise idle), the
         // next weight matrix is already on its way into L2.  Each CTA prefetches its 1/gridDim slice.
         constexpr long long CH = 16384;
@@ -323,15 +377,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (mma_pl >= 0) {
     // ------------------------------ MMA issuer ------------------------------
     pdl_wait();
     if (lane == 0) {
+      const int pl = mma_pl;
       constexpr uint32_t idesc = kActA ? umma_idesc_bf16(64, BM, false, false) : umma_idesc_bf16(BM, BN, A_MN, B_MN);
       // per-UMMA_K(16) start-address advance inside a stage, in 16-byte units
       constexpr uint32_t a_adv = A_MN ? (2048 >> 4) : (32 >> 4);
       constexpr uint32_t b_adv = B_MN ? (2048 >> 4) : (32 >> 4);
-      int stage = 0;
+      int si = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
@@ -341,8 +396,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int kb1 = min(kb0 + p.k_iters_per_split, p.k_iters);
         mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
-        for (int kb = kb0; kb < kb1; ++kb) {
+        const uint32_t d_tmem = tmem_base + (acc * NP + pl) * ACC_COLS;   // this pipeline's own accumulator
+        for (int kb = kb0 + pl; kb < kb1; kb += NP) {
+          const int stage = pl + NP * si;
           mbar_wait(full0 + 8 * stage, phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
@@ -353,19 +409,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int k = 0; k < BK / 16; ++k) {
             if constexpr (kActA)   // D[decode row][weight row] = X * W^T
               tc_mma_bf16(d_tmem, bdesc + (uint64_t)(k * b_adv), adesc + (uint64_t)(k * a_adv), idesc,
-                          (kb > kb0 || k > 0) ? 1u : 0u);
+                          (kb > kb0 + pl || k > 0) ? 1u : 0u);
             else
               tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * a_adv), bdesc + (uint64_t)(k * b_adv), idesc,
-                          (kb > kb0 || k > 0) ? 1u : 0u);
+                          (kb > kb0 + pl || k > 0) ? 1u : 0u);
           }
           tc_commit(empty0 + 8 * stage);  // frees the smem slot when these MMAs retire
-          if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+          if (++si == NSUB) { si = 0; phase ^= 1; }
         }
-        tc_commit(tfull0 + 8 * acc);  // accumulator complete -> epilogue
+        // accumulator share complete -> epilogue (a pipeline without a K block in this tile just reports in: the epilogue
+        // does not read its accumulator)
+        if (kb0 + pl < kb1) tc_commit(tfull0 + 8 * acc);
+        else mbar_arrive(tfull0 + 8 * acc);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else {
+  } else if (warp >= 2 && warp < 6) {
     // ------------------------------ epilogue (4 warps) ------------------------------
     pdl_wait();
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
@@ -392,7 +451,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int ks = t / (p.m_tiles * p.n_tiles);
       mbar_wait(tfull0 + 8 * acc, acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * NP * ACC_COLS;
+      // pipelines that hold a share of this tile's sum (pipeline pl took K blocks kb0 + pl, kb0 + pl + NP, ...)
+      const int n_kb = min(p.k_iters_per_split, p.k_iters - ks * p.k_iters_per_split);
+      const int n_pl = n_kb < NP ? n_kb : NP;
       const int row = mt * BM + row_in_tile;
       const bool row_ok = row < p.M;
       const int col_base = nt * BN;
@@ -449,9 +511,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // split-K / swap-AB partial: out[ks][col][row] fp32 (row = weight row, col = decode row)
         static_assert(BN == 16 || BN == 32, "F32T epilogue is for the narrow decode tiles");
         uint32_t r[BN];
-        if constexpr (BN == 16) tmem_ld_32x16(taddr, r);
-        else tmem_ld_32x32(taddr, r);
-        tmem_ld_wait();
+        dec_load_acc<BN, NP>(taddr, n_pl, r);
         float* out = reinterpret_cast<float*>(p.D);
         if (row_ok) {
 #pragma unroll
@@ -477,9 +537,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
         uint32_t r[BN];
-        if constexpr (BN == 16) tmem_ld_32x16(taddr, r);
-        else tmem_ld_32x32(taddr, r);
-        tmem_ld_wait();
+        dec_load_acc<BN, NP>(taddr, n_pl, r);
         float accv[BN];
 #pragma unroll
         for (int j = 0; j < BN; ++j) accv[j] = __uint_as_float(r[j]);
@@ -514,9 +572,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // act[r][c] = bf16( bf16(silu(bf16 g)) * bf16 u ) for the <= BN decode rows r.
         static_assert(BN == 16 || BN == 32, "decode tile");
         uint32_t r[BN];
-        if constexpr (BN == 16) tmem_ld_32x16(taddr, r);
-        else tmem_ld_32x32(taddr, r);
-        tmem_ld_wait();
+        dec_load_acc<BN, NP>(taddr, n_pl, r);
         if (scaled) {
 #pragma unroll
           for (int j = 0; j < BN; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * sscale[j]);
@@ -751,13 +807,13 @@ template <int BN>
 int dec_clusters_fit(int k_splits, int m_tiles, int* fit) {
   using C = Cfg<BN>;
   auto kfn = gemm_kernel<false, false, BN, SB_EPI_DEC_RESID>;
-  const size_t smem = C::SMEM_BYTES + dec_red_bytes(k_splits, BN);
+  const size_t smem = C::SMEM_BYTES_CLU + dec_red_bytes(k_splits, BN);
   *fit = 0;
   if (smem > 227 * 1024) return 0;
   SB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(m_tiles * k_splits);
-  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.blockDim = dim3(gemm_threads(SB_EPI_DEC_RESID));
   cfg.dynamicSmemBytes = smem;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -818,7 +874,7 @@ int launch(const sb_gemm_args* a, cudaStream_t stream) {
   const int total = p.m_tiles * p.n_tiles * p.k_splits;
   if constexpr (EPI == SB_EPI_DEC_QKV || EPI == SB_EPI_DEC_RESID) {
     // one cluster of k_splits CTAs per 128-row weight tile; every cluster must be resident at once (one tile per CTA)
-    const size_t smem = C::SMEM_BYTES + dec_red_bytes(p.k_splits, BN);
+    const size_t smem = C::SMEM_BYTES_CLU + dec_red_bytes(p.k_splits, BN);
     static size_t smem_set = 0;
     if (smem > smem_set) {
       SB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -826,7 +882,7 @@ int launch(const sb_gemm_args* a, cudaStream_t stream) {
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(total);
-    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.blockDim = dim3(gemm_threads(EPI));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
@@ -848,7 +904,7 @@ int launch(const sb_gemm_args* a, cudaStream_t stream) {
   }
   const int grid = total < num_sms() ? total : num_sms();
   const bool pdl = (EPI == SB_EPI_F32T || EPI == SB_EPI_F32T_SWIGLU) && sb_pdl_enabled();
-  cudaError_t le = sb_launch(kfn, dim3(grid), dim3(GEMM_THREADS), (size_t)C::SMEM_BYTES, stream, pdl, tmA, tmB, p);
+  cudaError_t le = sb_launch(kfn, dim3(grid), dim3(gemm_threads(EPI)), (size_t)C::SMEM_BYTES, stream, pdl, tmA, tmB, p);
   if (le != cudaSuccess) {
     sb_set_error("sb_gemm: launch failed: %s", cudaGetErrorString(le));
     return 1;

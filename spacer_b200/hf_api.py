@@ -218,8 +218,9 @@ class Qwen2VLForConditionalGenerationB200(torch.nn.Module):
         self.engine.save_pretrained(path, **{k: v for k, v in kw.items() if k == "max_shard_bytes"})
 
     def state_dict(self, *args, **kwargs):
-        """HF parameter names (checkpoint save at open_r1/SG-RLVR.py:384), not the arena names."""
-        return self.engine.state_dict()
+        """HF parameter names (checkpoint save at open_r1/SG-RLVR.py:384), not the arena names; references to the live
+        weights where the layouts agree, like `nn.Module.state_dict()`."""
+        return self.engine.params.state_dict(clone=False)
 
     def load_state_dict(self, state_dict, strict=True, assign=False):
         self.engine.load_state_dict(state_dict)

@@ -194,8 +194,14 @@ class ParamStore:
         yield L + "norm.weight", V["norm_w"]
         yield "lm_head.weight", V["embed"] if d.tie else V["lm_head"]
 
-    def state_dict(self):
-        return {k: v.clone() for k, v in self.hf_items()}
+    def state_dict(self, clone: bool = True):
+        """HF-named tensors.  clone=False returns views of the arenas wherever the HF tensor is one (everything but the
+        de-interleaved gate/up projections), like `nn.Module.state_dict()` returns references.  The data pointers of the
+        last export are remembered so that a weight sync that hands them straight back (vllm_api.load_weights on the
+        colocated engine) is recognised as a no-op."""
+        sd = {k: (v.clone() if clone else v) for k, v in self.hf_items()}
+        self._export_ptrs = {k: v.data_ptr() for k, v in sd.items()}
+        return sd
 
     def load_state_dict(self, sd: dict):
         """Load an HF-named state dict (any float dtype, any device)."""

@@ -117,3 +117,50 @@ def test_overlapped_grad_reducer_equals_full_allreduce():
     for p in ps:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def _vllm_contract_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from spacer_b200.vllm_api import CompletionOutput, RequestOutput, SamplingParams, gather_generate_broadcast
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class FakeLLM:          # deterministic stand-in for the rollout engine: completion j of a prompt = f(prompt ids, j)
+        def __init__(self):
+            self.calls = []
+
+        def generate(self, prompts, sampling_params, use_tqdm=False):
+            self.calls.append(len(prompts))
+            return [RequestOutput(str(i), None, p["prompt_token_ids"],
+                                  [CompletionOutput(j, [sum(p["prompt_token_ids"]) + j] * (j + 1)) for j in range(sampling_params.n)])
+                    for i, p in enumerate(prompts)]
+    llm = FakeLLM() if rank == 0 else None
+    req = {"prompt_token_ids": [10 * (rank + 1), 1, 2], "multi_modal_data": {"video": torch.full((2, 3, 4, 4), float(rank))}}
+    mine = gather_generate_broadcast(llm, req, SamplingParams(n=3, max_tokens=4), main_rank=0)
+    q.put((rank, mine, llm.calls if llm else None))
+    dist.destroy_process_group()
+
+
+def test_vllm_trainer_gather_generate_broadcast_world2():
+    """vllm_grpo_trainer_modified.py:546-608 on torch.distributed (gloo, 2 ranks): prompts gathered, ONE generate call on
+    the main rank over both, token ids broadcast, every rank keeps its own n completions in order."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29621
+    ps = [ctx.Process(target=_vllm_contract_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+    (r0, c0, calls0), (r1, c1, calls1) = res
+    assert calls0 == [2] and calls1 is None                     # a single generate over both ranks' prompts, on rank 0 only
+    assert c0 == [[13], [14, 14], [15, 15, 15]]                 # 10 + 1 + 2 = 13 (+ j), completion j has j + 1 tokens
+    assert c1 == [[23], [24, 24], [25, 25, 25]]
+
+
+def test_vllm_pad_completions():
+    from spacer_b200.vllm_api import pad_completions
+    out = pad_completions([[1, 2, 3], [4], []], pad_token_id=9)
+    assert out.tolist() == [[1, 2, 3], [4, 9, 9], [9, 9, 9]]

@@ -14,7 +14,7 @@ import torch  # noqa: E402
 
 import bench  # noqa: E402
 from spacer_b200 import config as mcfg, ops  # noqa: E402
-from spacer_b200.model import Qwen2VLB200, rope_index  # noqa: E402
+from spacer_b200.model import Qwen2VLB200, SamplingParams, rope_index  # noqa: E402
 
 
 def timed(fn, reps):
@@ -44,6 +44,28 @@ def main():
     G, C = cfg["G"], cfg["C"]
     pix2 = pix.flip(0).contiguous()
     lib = ops._lib.load()
+    SP = SamplingParams(top_p=0.95, top_k=50, eos_ids=(dims.eos_id,), pad_id=dims.pad_id)   # the trainer's rollout options
+    if "ab" in a.exp:
+        # A/B of the decode step: the 9-kernel-per-layer chain vs the cluster-fused GEMV epilogues (model.decode_fused)
+        _, nxt = rope_index(ids.reshape(-1), grid, dims)
+        kv = 2 * dims.layers * dims.kv_heads * dims.head_dim * 2
+        byts = m.decode_weight_bytes() + 2 * ids.numel() * kv + (G + G // 2) * 250 * kv
+        for fused in (False, True, False, True):
+            m.decode_fused = fused
+            m._dec = None
+            st = m._decode_state(G + G // 2, ids.numel(), C, 2)
+            st["step"].fill_(200)
+            graph, nodes = m._decode_graph(st, nxt, G, SP, True)
+            st["step"].fill_(200)
+            for _ in range(5):
+                graph.replay()
+            st["step"].fill_(200)
+            ms = timed(graph.replay, 100)
+            prof = m.profile_decode_gemv(rows=G + G // 2, reps=3)
+            print(json.dumps({"exp": "ab", "fused": fused, "splits": st["S"], "ms": round(ms, 4), "gbs": round(byts / ms / 1e6, 1),
+                              "nodes": nodes, "gemv_only_gbs": round(prof["gbs"], 1), "gemv_sweep_ms": round(prof["ms_per_sweep"], 4)}), flush=True)
+        m.decode_fused = "fusedtrace" in a.exp
+        m._dec = None
     # build the decode state with a short rollout (full prefill, 3 decode steps)
     st = m._decode_state(G + G // 2, ids.numel(), C, 2)
     m.generate(ids, pix, grid, max_new_tokens=C, num_return_sequences=G, pixel_values_videos_2=pix2,
@@ -61,7 +83,7 @@ def main():
                 m.L2_PREFETCH_ATTN_BYTES = pfa << 20
                 st["graphs"].clear()
                 st["step"].fill_(200)
-                graph, nodes = m._decode_graph(st, nxt, G, 0.95, True)
+                graph, nodes = m._decode_graph(st, nxt, G, SP, True)
                 st["step"].fill_(200)
                 for _ in range(5):
                     graph.replay()
@@ -82,7 +104,7 @@ def main():
         buf = torch.zeros(1 + 4 * cap, device=dev, dtype=torch.int64)
         st["graphs"].clear()
         st["step"].fill_(200)
-        graph, nodes = m._decode_graph(st, nxt, G, 0.95, True)
+        graph, nodes = m._decode_graph(st, nxt, G, SP, True)
         for _ in range(3):
             graph.replay()
         torch.cuda.synchronize()
