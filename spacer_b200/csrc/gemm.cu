@@ -980,7 +980,7 @@ extern "C" int sb_gemm(const sb_gemm_args* a, sb_stream_t stream_) {
     SB_REQUIRE(d != nullptr, "sb_gemm: decode epilogue without sb_dec_fuse");
     SB_REQUIRE(a->N <= 32 && d->R > 0 && d->R <= a->N, "sb_gemm: decode epilogue needs R <= N <= 32 (R=%d, N=%d)", d->R, a->N);
     SB_REQUIRE(sb_gemm_effective_splits(a->K, a->k_splits) <= DEC_MAX_SPLITS, "sb_gemm: decode epilogues take at most %d K splits", DEC_MAX_SPLITS);
-    SB_REQUIRE((a->N <= 16 ? Cfg<16>::SMEM_BYTES : Cfg<32>::SMEM_BYTES) +
+    SB_REQUIRE((a->N <= 16 ? Cfg<16>::SMEM_BYTES_CLU : Cfg<32>::SMEM_BYTES_CLU) +
                        dec_red_bytes(sb_gemm_effective_splits(a->K, a->k_splits), a->N <= 16 ? 16 : 32) <= 227 * 1024,
                "sb_gemm: too many K splits for the cluster reduction buffer (use sb_gemm_dec_splits)");
     SB_REQUIRE(d->ssq_in == nullptr || (d->n_ssq_in > 0 && d->ld_ssq >= a->N && d->norm_dim > 0),

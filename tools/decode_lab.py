@@ -64,8 +64,8 @@ def main():
             prof = m.profile_decode_gemv(rows=G + G // 2, reps=3)
             print(json.dumps({"exp": "ab", "fused": fused, "splits": st["S"], "ms": round(ms, 4), "gbs": round(byts / ms / 1e6, 1),
                               "nodes": nodes, "gemv_only_gbs": round(prof["gbs"], 1), "gemv_sweep_ms": round(prof["ms_per_sweep"], 4)}), flush=True)
-        m.decode_fused = "fusedtrace" in a.exp
-        m._dec = None
+    m.decode_fused = "fusedtrace" in a.exp
+    m._dec = None
     # build the decode state with a short rollout (full prefill, 3 decode steps)
     st = m._decode_state(G + G // 2, ids.numel(), C, 2)
     m.generate(ids, pix, grid, max_new_tokens=C, num_return_sequences=G, pixel_values_videos_2=pix2,
@@ -75,7 +75,7 @@ def main():
     flush = torch.empty(512 << 20, device=dev, dtype=torch.uint8)
 
     if "step" in a.exp:
-        for pdl, pf, pfa in ((1, 16, 48), (1, 16, 0), (1, 16, 24), (1, 16, 72), (1, 32, 48), (1, 8, 48), (1, 0, 0), (0, 16, 48)):
+        for pdl, pf, pfa in ((1, 16, 48), (1, 0, 0), (1, 16, 72), (1, 16, 96), (1, 16, 120), (1, 32, 96), (1, 48, 96), (1, 0, 96), (1, 16, 48)):
             if True:
                 pf <<= 20
                 lib.sb_set_pdl(pdl)

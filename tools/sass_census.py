@@ -60,9 +60,10 @@ def main():
         dm = demangle(list(per))
         for k, c in per.items():
             if any(c[h] for h in ("tcgen05.mma", "TMA load", "TMEM ld", "TMEM st", "mma.sync HMMA")):
-                short = re.sub(r"\(.*", "", dm[k])
-                short = re.sub(r"\(anonymous namespace\)::", "", short)
-                detail.append((fn, short[:110], c))
+                short = dm[k].replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
+                short = re.sub(r"^void ", "", short)
+                short = re.sub(r">\(.*$", ">", short)            # drop the parameter list, keep the template arguments
+                detail.append((fn, short[:120], c))
     print("## Per object\n")
     print("| object | kernels | " + " | ".join(heads) + " |")
     print("|---|---|" + "---|" * len(heads))
