@@ -27,7 +27,7 @@ extern "C" {
 
 typedef struct CUstream_st* sb_stream_t;
 
-#define SB_ABI_VERSION 2
+#define SB_ABI_VERSION 3
 
 const char* sb_last_error(void);
 int sb_abi_version(void);
@@ -58,29 +58,9 @@ enum {
   SB_EPI_F32T = 4,      /* D_f32[split][n][m] = partial acc (swap-AB decode GEMV with split-K)      */
   SB_EPI_LMHEAD = 5,    /* per-row (max, sumexp) per N tile of bf16-rounded logits + target gather  */
   SB_EPI_DLOGITS = 6,   /* D = bf16(coef[m] * (onehot(target[m]) - exp(logit - lse[m])))            */
-  SB_EPI_F32T_SWIGLU = 7, /* swap-AB decode gate|up GEMV, A rows interleaved [64 gate | 64 up]:
+  SB_EPI_F32T_SWIGLU = 7  /* swap-AB decode gate|up GEMV, A rows interleaved [64 gate | 64 up]:
                            D_bf16[n][m/2] = silu(gate)*up for the N <= 32 decode rows (no split-K)         */
-  SB_EPI_DEC_QKV = 8,   /* swap-AB decode GEMV, split-K reduced inside a thread-block cluster (DSMEM); the tile owner
-                           adds bias, applies M-RoPE at the step's position, q -> q_out, k/v -> completion-cache
-                           slot: sb_dec_qkv_post fused in.  D is unused.                                         */
-  SB_EPI_DEC_RESID = 9  /* same reduction; the tile owner does x += sum, xw = x*w_next and the tile's sum of
-                           squares: the residual half of sb_dec_residual_rmsnorm fused in.  D is unused.         */
 };
-
-/* Fused decode-step epilogues (sb_gemm_args.dec; swap-AB GEMVs only).  They remove the small kernels between the
- * weight-streaming GEMVs of one decoder layer (MQ2:597-662 at q_len = 1): RMSNorm is split into "x * w" (done by the
- * GEMV that PRODUCES the residual stream, written to xw) and the per-row 1/rms (applied by the GEMV that CONSUMES xw,
- * computed from ssq = per-128-column-tile sums of x^2).  Row r of every [.][ld_ssq] array is decode row r. */
-typedef struct sb_dec_fuse {
-  int R;                      /* decode rows in use (<= N of the GEMM)                                              */
-  /* consumer side (F32T, F32T_SWIGLU, DEC_QKV): scale row r of the result by rsqrt(sum_t ssq_in[t][r]/norm_dim + eps) */
-  const float* ssq_in; int n_ssq_in; int ld_ssq; int norm_dim; float eps;
-  /* DEC_QKV (head_dim 128; bias = sb_gemm_args.bias): rotary position rope_base + *step_ptr, cache slot *step_ptr   */
-  const int* step_ptr; int rope_base; float theta; int n_heads, n_kv_heads;
-  void* q_out; void* k_cache; void* v_cache; long long cache_stride_r; int c_max;
-  /* DEC_RESID: x bf16 [R][M] in/out, w_next bf16 [M], xw bf16 [R][M] out, ssq_out fp32 [ceil(M/128)][ld_ssq] out   */
-  void* x; const void* w_next; void* xw; float* ssq_out;
-} sb_dec_fuse;
 
 typedef struct sb_gemm_args {
   int M, N, K;
@@ -102,16 +82,11 @@ typedef struct sb_gemm_args {
   long long prefetch_bytes;               /*   kernel's own loads (the NEXT weight matrix of the decode step) */
   const void* prefetch2;                  /* second L2-prefetch range (the matrix after next), 16-byte aligned */
   long long prefetch2_bytes;
-  const sb_dec_fuse* dec;                 /* HOST pointer, optional: fused decode-step epilogue arguments       */
 } sb_gemm_args;
 
 int sb_gemm(const sb_gemm_args* args, sb_stream_t stream);
 /* number of non-empty K splits sb_gemm will use for (K, k_splits) */
 int sb_gemm_effective_splits(int K, int k_splits);
-/* largest k_splits <= want for SB_EPI_DEC_QKV / SB_EPI_DEC_RESID on this device: the splits of a 128-row weight tile
- * form a thread-block cluster (split-K reduced through distributed shared memory) and all ceil(M/128) clusters must be
- * resident at once.  N = decode rows (<= 32). */
-int sb_gemm_dec_splits(int M, int N, int K, int want, int* splits_out);
 
 /* ------------------------------------------------------------------------------------------------
  * Bandwidth-bound kernels (fp32 math, bf16 storage)
@@ -227,10 +202,6 @@ int sb_attn_bwd_workspace(int T, int Tk, int n_heads, int n_kv_heads, int head_d
  * Qwen2VLDecoderLayer (MQ2:597-662) and DynamicCache.update (cache_utils.py:102-120).
  * ------------------------------------------------------------------------------------------------ */
 int sb_dec_embed(const int* tokens, const void* embed, void* x, int R, int H, sb_stream_t stream);
-/* fused-epilogue chain entry: x = embed[token], xw = bf16(x * w_next), ssq_out[t][r] = sum of x^2 over columns
- * [128 t, 128 t + 128) (see sb_dec_fuse); H % 8 == 0 */
-int sb_dec_embed_norm(const int* tokens, const void* embed, void* x, const void* w_next, void* xw, float* ssq_out,
-                      int ld_ssq, int R, int H, sb_stream_t stream);
 int sb_dec_residual_rmsnorm(void* x, const float* parts, int S, long long stride_s, long long stride_r, const void* w,
                             void* xn, int R, int H, float eps, sb_stream_t stream);
 int sb_dec_qkv_post(const float* parts, int S, long long stride_s, long long stride_r, const void* bias,

@@ -15,19 +15,6 @@ class SpacerError(RuntimeError):
     pass
 
 
-class DecFuse(C.Structure):
-    """sb_dec_fuse (include/spacer_b200.h): arguments of the fused decode-step GEMV epilogues."""
-    _fields_ = [
-        ("R", C.c_int),
-        ("ssq_in", C.c_void_p), ("n_ssq_in", C.c_int), ("ld_ssq", C.c_int), ("norm_dim", C.c_int), ("eps", C.c_float),
-        ("step_ptr", C.c_void_p), ("rope_base", C.c_int), ("theta", C.c_float), ("n_heads", C.c_int),
-        ("n_kv_heads", C.c_int),
-        ("q_out", C.c_void_p), ("k_cache", C.c_void_p), ("v_cache", C.c_void_p), ("cache_stride_r", C.c_longlong),
-        ("c_max", C.c_int),
-        ("x", C.c_void_p), ("w_next", C.c_void_p), ("xw", C.c_void_p), ("ssq_out", C.c_void_p),
-    ]
-
-
 class GemmArgs(C.Structure):
     _fields_ = [
         ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
@@ -42,12 +29,10 @@ class GemmArgs(C.Structure):
         ("lse", C.c_void_p), ("coef", C.c_void_p),
         ("prefetch", C.c_void_p), ("prefetch_bytes", C.c_longlong),
         ("prefetch2", C.c_void_p), ("prefetch2_bytes", C.c_longlong),
-        ("dec", C.POINTER(DecFuse)),
     ]
 
 
-(EPI_STORE, EPI_QUICKGELU, EPI_GELU, EPI_SWIGLU, EPI_F32T, EPI_LMHEAD, EPI_DLOGITS, EPI_F32T_SWIGLU, EPI_DEC_QKV,
- EPI_DEC_RESID) = range(10)
+EPI_STORE, EPI_QUICKGELU, EPI_GELU, EPI_SWIGLU, EPI_F32T, EPI_LMHEAD, EPI_DLOGITS, EPI_F32T_SWIGLU = range(8)
 
 _lib = None
 

@@ -24,46 +24,6 @@ __global__ void dec_embed_kernel(const int* __restrict__ tokens, const bf16* __r
   sb_trace_mark(tr, 2);
 }
 
-// entry of the fused-epilogue chain (sb_dec_fuse): x[r] = embed[token[r]], xw[r] = bf16(x * w_next),
-// ssq[t][r] = sum of x^2 over columns [128 t, 128 t + 128).  One CTA of 256 threads per row, 8 columns per thread
-// per pass: the 16 lanes of a half-warp cover exactly one 128-column tile.
-__global__ void __launch_bounds__(256)
-dec_embed_norm_kernel(const int* __restrict__ tokens, const bf16* __restrict__ embed, bf16* __restrict__ x,
-                      const bf16* __restrict__ w_next, bf16* __restrict__ xw, float* __restrict__ ssq, int ld_ssq,
-                      int H) {
-  pdl_launch_dependents();
-  const bool tr_on = blockIdx.x == 0 && threadIdx.x == 0;
-  const int tr = tr_on ? sb_trace_begin(SB_TR_EMBED) : -1;
-  pdl_wait();
-  sb_trace_mark(tr, 1);
-  const int r = blockIdx.x;
-  const bf16* src = embed + (long long)tokens[r] * H;
-  const int n8 = H / 8;
-  for (int i0 = 0; i0 < n8; i0 += 256) {       // uniform trip count: the shuffles below need whole warps
-    const int i = i0 + threadIdx.x;
-    const bool ok = i < n8;
-    float ss = 0.f;
-    if (ok) {
-      const uint4 u = *reinterpret_cast<const uint4*>(src + i * 8);
-      const uint4 wu = *reinterpret_cast<const uint4*>(w_next + i * 8);
-      *reinterpret_cast<uint4*>(x + (long long)r * H + i * 8) = u;
-      const uint32_t uu[4] = {u.x, u.y, u.z, u.w}, ww[4] = {wu.x, wu.y, wu.z, wu.w};
-      uint32_t oo[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 a = unpack_bf16(uu[j]), b = unpack_bf16(ww[j]);
-        ss += a.x * a.x + a.y * a.y;
-        oo[j] = pack_bf16(a.x * b.x, a.y * b.y);
-      }
-      *reinterpret_cast<uint4*>(xw + (long long)r * H + i * 8) = make_uint4(oo[0], oo[1], oo[2], oo[3]);
-    }
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    if (ok && (threadIdx.x & 15) == 0) ssq[(long long)(i / 16) * ld_ssq + r] = ss;
-  }
-  sb_trace_mark(tr, 2);
-}
-
 // x[r] += bf16(sum_s parts[s][r][:]) (if parts);  xn[r] = w * bf16(x * rstd)
 // one CTA of 1024 threads per row, 4 consecutive elements per thread per pass (float4 partial loads)
 constexpr int RN_THREADS = 1024;
@@ -240,14 +200,6 @@ extern "C" int sb_dec_embed(const int* tokens, const void* embed, void* x, int R
   return sb_check_launch("sb_dec_embed");
 }
 
-extern "C" int sb_dec_embed_norm(const int* tokens, const void* embed, void* x, const void* w_next, void* xw,
-                                 float* ssq_out, int ld_ssq, int R, int H, sb_stream_t stream) {
-  SB_REQUIRE(tokens && embed && x && w_next && xw && ssq_out && R > 0 && H % 8 == 0 && ld_ssq >= R,
-             "sb_dec_embed_norm: bad arguments");
-  SB_CUDA(sb_launch(dec_embed_norm_kernel, dim3(R), dim3(256), 0, STREAM(stream), sb_pdl_enabled(), tokens,
-                    (const bf16*)embed, (bf16*)x, (const bf16*)w_next, (bf16*)xw, ssq_out, ld_ssq, H));
-  return sb_check_launch("sb_dec_embed_norm");
-}
 
 extern "C" int sb_dec_residual_rmsnorm(void* x, const float* parts, int S, long long stride_s, long long stride_r,
                                        const void* w, void* xn, int R, int H, float eps, sb_stream_t stream) {

@@ -23,12 +23,6 @@
 
 namespace {
 
-// 1 = decode GEMVs with the activations as the A operand (M = 64) instead of swap-AB.  Parity-tested; measured in the
-// decode graph: split-K GEMVs unchanged (qkv 5.3, o 4.9, down 19.8 us), fused-SwiGLU gate|up 50 us instead of 41 us
-// (one epilogue warp owns all 16 rows), step 3.46 vs 3.16 ms -- off.  profiles/r01_ingest_labs.md
-#ifndef SB_GEMV_ACT_A
-#define SB_GEMV_ACT_A 0
-#endif
 #ifndef SB_GEMV_STAGES
 #define SB_GEMV_STAGES 10
 #endif
@@ -43,14 +37,13 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;
 // Two pairs on alternating K blocks, each with its own half of the stage ring and its own TMEM accumulator (summed by
 // the epilogue), reach 62 GB/s per CTA at 112 CTAs (HBM-bound, 6.9 TB/s) and 82-88 GB/s at <= 74 CTAs
 // (tools/labs/ingest_dual_lab.cu, profiles/r02_ingest_dual_lab.md) -- which is what lets the cluster-fused epilogues, that
-// can only occupy 108-112 SMs, stream at full HBM speed.
+// could only occupy 108-112 SMs, stream at full HBM speed (they were measured again, stayed slower than the plain
+// chain and were removed: profiles/r02_ingest_dual_lab.md).
 #ifndef SB_GEMV_PIPES
 #define SB_GEMV_PIPES 2
 #endif
-constexpr bool is_dec_epi(int epi) {
-  return epi == SB_EPI_F32T || epi == SB_EPI_F32T_SWIGLU || epi == SB_EPI_DEC_QKV || epi == SB_EPI_DEC_RESID;
-}
-constexpr int gemm_pipes(int epi) { return (is_dec_epi(epi) && !SB_GEMV_ACT_A) ? SB_GEMV_PIPES : 1; }
+constexpr bool is_dec_epi(int epi) { return epi == SB_EPI_F32T || epi == SB_EPI_F32T_SWIGLU; }
+constexpr int gemm_pipes(int epi) { return is_dec_epi(epi) ? SB_GEMV_PIPES : 1; }
 // warps: 0 producer, 1 MMA issuer (+ TMEM allocator), 2-5 epilogue, then one (producer, MMA) warp pair per extra pipeline
 constexpr int gemm_threads(int epi) { return GEMM_THREADS + 64 * (gemm_pipes(epi) - 1); }
 
@@ -73,10 +66,7 @@ struct GemmParams {
   long long prefetch_bytes;
   const uint8_t* prefetch2;      // second range (the matrix after next)
   long long prefetch2_bytes;
-  sb_dec_fuse dec;               // fused decode-step epilogues (zeroed when unused)
 };
-
-constexpr int DEC_MAX_SPLITS = 8;   // portable cluster size: the K splits of one tile form a cluster
 
 // 16 KB per instruction: cp.async.bulk.prefetch.L2 only warms L2, nothing is written to shared memory
 SB_DEVICE void l2_prefetch_bulk(const void* ptr, uint32_t bytes) {
@@ -98,14 +88,9 @@ struct Cfg {
   // decode tiles: 2 accumulators (epilogue overlap) x SB_GEMV_PIPES pipelines x BN columns, a power of two >= 32
   static constexpr int TMEM_COLS_DEC = (2 * SB_GEMV_PIPES * BN <= 32) ? 32 : (2 * SB_GEMV_PIPES * BN <= 64) ? 64 :
                                        (2 * SB_GEMV_PIPES * BN <= 128) ? 128 : 256;
-  // gate/up exchange of the fused decode SwiGLU epilogue / rotary-partner exchange of DEC_QKV / cross-warp scratch of
-  // DEC_RESID, then 32 per-row scales of the fused decode epilogues
+  // gate/up exchange of the fused decode SwiGLU epilogue
   static constexpr int XBUF_BYTES = 128 * 33 * 4 + 256;
   static constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + XBUF_BYTES;
-  // cluster-fused decode epilogues: rank 0 also holds the partial tiles of the other ranks (dec_red_bytes), so the ring
-  // is 8 stages (2 pipelines x 4: still 62 GB/s per CTA at 112 CTAs, i.e. HBM-bound; tools/labs/ingest_dual_lab.cu)
-  static constexpr int NSTAGES_CLU = NSTAGES < 8 ? NSTAGES : (8 / SB_GEMV_PIPES) * SB_GEMV_PIPES;
-  static constexpr int SMEM_BYTES_CLU = NSTAGES_CLU * STAGE_BYTES + 1024 + 256 + XBUF_BYTES;
 };
 
 SB_DEVICE float quick_gelu(float x) { return x / (1.f + __expf(-1.702f * x)); }
@@ -127,86 +112,7 @@ SB_DEVICE void ld8(const bf16* p, float* v) {
   v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
 }
 
-// ---------------------------------------------------------------------------------------------
-// Fused decode-step epilogues (SB_EPI_DEC_QKV / SB_EPI_DEC_RESID).  The k_splits CTAs that share one 128-row weight
-// tile form a thread-block CLUSTER (rank = K split).  Ranks > 0 push their fp32 partial tile straight into rank 0's
-// shared memory (st.shared::cluster) and signal an mbarrier there; rank 0 adds the partials in rank order
-// (deterministic) and finishes the tile in registers -- what used to be a separate kernel behind a global-memory
-// round trip.  The 128 epilogue threads act together; named barrier 1 is theirs.
-// ---------------------------------------------------------------------------------------------
-SB_DEVICE void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-
-// qkv tile mt = one head (BM == head_dim == 128), thread = head-dim index `e`, acc[j] = decode row j:
-// bf16(acc + bias), rotary at position rope_base + step for q and k heads (partner element e ^ 64 comes through
-// shared memory), q -> q_out, k/v -> completion-cache slot `step`.  Same arithmetic as dec_qkv_post_kernel.
-template <int BN>
-SB_DEVICE void dec_qkv_finish(const GemmParams& p, int mt, int e, float* acc, float* xch /*[128][BN+1]*/) {
-  const sb_dec_fuse& d = p.dec;
-  const int R = d.R, nh = d.n_heads, nkv = d.n_kv_heads;
-  const float bias = __bfloat162float(p.bias[mt * BM + e]);
-  const int step = *d.step_ptr;
-  const int slot = min(step, d.c_max - 1);
-  if (mt >= nh + nkv) {   // v head: bias only
-    bf16* vd = reinterpret_cast<bf16*>(d.v_cache) + (long long)slot * nkv * BM + (mt - nh - nkv) * BM + e;
-#pragma unroll
-    for (int j = 0; j < BN; ++j)
-      if (j < R) vd[j * d.cache_stride_r] = __float2bfloat16_rn(acc[j] + bias);
-    return;
-  }
-  const int i = e & 63;
-  const float pos = (float)(d.rope_base + step);
-  const float inv_freq = 1.0f / powf(d.theta, (float)(2 * i) / (float)BM);
-  float sn, cs;
-  sincosf(pos * inv_freq, &sn, &cs);
-  cs = bf16_round(cs);
-  sn = bf16_round(sn);
-  if (e < 64) sn = -sn;       // out[i] = a cs - b sn ; out[i + 64] = b cs + a sn   (a = element i, b = element i + 64)
-#pragma unroll
-  for (int j = 0; j < BN; ++j) {
-    acc[j] = bf16_round(acc[j] + bias);
-    xch[e * (BN + 1) + j] = acc[j];
-  }
-  epi_bar();
-  bf16* dst = (mt < nh) ? reinterpret_cast<bf16*>(d.q_out) + mt * BM + e
-                        : reinterpret_cast<bf16*>(d.k_cache) + (long long)slot * nkv * BM + (mt - nh) * BM + e;
-  const long long row_stride = (mt < nh) ? (long long)nh * BM : d.cache_stride_r;
-#pragma unroll
-  for (int j = 0; j < BN; ++j) {
-    const float partner = xch[(e ^ 64) * (BN + 1) + j];
-    const float o = bf16_round(bf16_round(acc[j] * cs) + bf16_round(partner * sn));
-    if (j < R) dst[j * row_stride] = __float2bfloat16_rn(o);
-  }
-  epi_bar();   // xch is free again
-}
-
-// residual tile mt = hidden columns [128 mt, 128 mt + 128), thread = column, acc[j] = decode row j:
-// x += bf16(acc) (dec_residual_rmsnorm's arithmetic; xin = the old x, loaded before the main loop finished),
-// xw = bf16(x * w_next) -- the NEXT norm's weight without its rstd, which the consuming GEMV applies per row in its
-// epilogue -- and ssq_out[mt][r] = sum over the tile of x^2.
-template <int BN>
-SB_DEVICE void dec_resid_finish(const GemmParams& p, int mt, int e, const float* acc, const float* xin, float wn,
-                                float* sred /*[4][32]*/) {
-  const sb_dec_fuse& d = p.dec;
-  const int R = d.R;
-  const int col = mt * BM + e;
-  const bool col_ok = col < p.M;
-  const int lane = e & 31, w = e >> 5;
-  bf16* x = reinterpret_cast<bf16*>(d.x);
-  bf16* xw = reinterpret_cast<bf16*>(d.xw);
-#pragma unroll
-  for (int j = 0; j < BN; ++j) {
-    const float c = bf16_round(bf16_round(acc[j]) + xin[j]);
-    if (col_ok && j < R) {
-      x[(long long)j * p.M + col] = __float2bfloat16_rn(c);
-      xw[(long long)j * p.M + col] = __float2bfloat16_rn(c * wn);
-    }
-    const float sq = warp_sum(col_ok ? c * c : 0.f);
-    if (lane == 0) sred[w * 32 + j] = sq;
-  }
-  epi_bar();
-  if (e < R) d.ssq_out[(long long)mt * d.ld_ssq + e] = (sred[e] + sred[32 + e]) + (sred[64 + e] + sred[96 + e]);
-  epi_bar();
-}
+SB_DEVICE void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 128 epilogue threads
 
 // this thread's BN accumulator columns of a decode tile, summed over the pipelines that hold a share of it (fixed order)
 template <int BN, int NP>
@@ -232,19 +138,14 @@ __global__ void __launch_bounds__(gemm_threads(EPI), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const GemmParams p) {
   using C = Cfg<BN>;
-  constexpr int NSTAGES = (EPI == SB_EPI_DEC_QKV || EPI == SB_EPI_DEC_RESID) ? C::NSTAGES_CLU : C::NSTAGES;
+  constexpr int NSTAGES = C::NSTAGES;
   constexpr int NP = gemm_pipes(EPI);            // producer / MMA-issuer pairs (pipelines) in this CTA
   static_assert(NSTAGES % NP == 0, "the stage ring is split evenly between the pipelines");
   constexpr int NSUB = NSTAGES / NP;             // stages per pipeline: pipeline pl owns stages pl, pl + NP, ...
   // the swap-AB weight-streaming GEMVs of the decode step (PDL launch, early weight ring, L2 prefetch of the next matrix)
-  constexpr bool kDec = EPI == SB_EPI_F32T || EPI == SB_EPI_F32T_SWIGLU || EPI == SB_EPI_DEC_QKV || EPI == SB_EPI_DEC_RESID;
-  // kActA: the <= 16 decode rows are the A operand (M = 64, rows 16.. are whatever follows in shared memory and produce
-  // ignored accumulator rows) and the 128-row weight tile is the B operand (N = 128).  Same TMA boxes and smem layout as
-  // the swap-AB form, but the slot round trip (TMA -> MMA -> commit -> refill) is shorter: 6.70 vs 5.89 TB/s at 148
-  // CTAs (tools/labs/ingest_mma_lab.cu, profiles/r01_ingest_labs.md), and each epilogue thread owns one decode row.
-  constexpr bool kActA = (EPI == SB_EPI_F32T || EPI == SB_EPI_F32T_SWIGLU) && BN == 16 && SB_GEMV_ACT_A;
-  constexpr int ACC_COLS = kActA ? BM : BN;                 // TMEM columns of one accumulator
-  constexpr int TMEM_COLS = kActA ? 2 * BM : (NP > 1 ? C::TMEM_COLS_DEC : C::TMEM_COLS);
+  constexpr bool kDec = is_dec_epi(EPI);
+  constexpr int ACC_COLS = BN;                              // TMEM columns of one accumulator
+  constexpr int TMEM_COLS = NP > 1 ? C::TMEM_COLS_DEC : C::TMEM_COLS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -255,14 +156,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t tempty0 = smem_u32(bars + 2 * NSTAGES + 2);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGES + 4);
   float* xbuf = reinterpret_cast<float*>(smem + NSTAGES * C::STAGE_BYTES + 256);
-  float* sscale = xbuf + 128 * 33;                                 // [32] per-decode-row scale (RMSNorm rstd)
-  // cluster split-K reduction (kClu): rank 0 receives the partial tiles of ranks 1.. in red[rank-1][128][BN+4]
-  constexpr bool kClu = EPI == SB_EPI_DEC_QKV || EPI == SB_EPI_DEC_RESID;
-  constexpr int RSTR = BN + 4;
-  float* red = sscale + 64;
-  const uint32_t redbar = smem_u32(bars + 2 * NSTAGES + 6);
-  uint32_t crank = 0, csize = 1;
-  if constexpr (kClu) { crank = cluster_ctarank(); csize = cluster_nctarank(); }
   const uint32_t smem_base = smem_u32(smem);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -279,7 +172,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(tfull0 + 8 * a, NP);        // every pipeline's issuer reports its share of the tile
       mbar_init(tempty0 + 8 * a, 4);
     }
-    if constexpr (kClu) mbar_init(redbar, csize > 1 ? csize - 1 : 1);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
@@ -287,13 +179,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if constexpr (kClu) cluster_sync_all();   // rank 0's mbarrier is initialised before any rank signals it
 
   const int total_tiles = p.m_tiles * p.n_tiles * p.k_splits;
-  // tile t = (ks * n_tiles + nt) * m_tiles + mt.  Persistent: CTA b takes t = b, b + grid, ...; cluster mode: exactly
-  // one tile per CTA, (mt, ks) = (cluster index, rank in cluster)
-  int t_begin = blockIdx.x, t_step = gridDim.x;
-  if constexpr (kClu) { t_begin = (int)crank * p.m_tiles + (int)(blockIdx.x / csize); t_step = total_tiles; }
+  // tile t = (ks * n_tiles + nt) * m_tiles + mt.  Persistent: CTA b takes t = b, b + grid, ...
+  const int t_begin = blockIdx.x, t_step = gridDim.x;
 
   pdl_launch_dependents();
   // pipeline of this warp when it is a producer / an MMA issuer (-1 otherwise)
@@ -382,7 +271,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     pdl_wait();
     if (lane == 0) {
       const int pl = mma_pl;
-      constexpr uint32_t idesc = kActA ? umma_idesc_bf16(64, BM, false, false) : umma_idesc_bf16(BM, BN, A_MN, B_MN);
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
       // per-UMMA_K(16) start-address advance inside a stage, in 16-byte units
       constexpr uint32_t a_adv = A_MN ? (2048 >> 4) : (32 >> 4);
       constexpr uint32_t b_adv = B_MN ? (2048 >> 4) : (32 >> 4);
@@ -407,12 +296,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const uint64_t bdesc = umma_desc_sw128(sb, B_MN ? 8192 : 0, 1024);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            if constexpr (kActA)   // D[decode row][weight row] = X * W^T
-              tc_mma_bf16(d_tmem, bdesc + (uint64_t)(k * b_adv), adesc + (uint64_t)(k * a_adv), idesc,
-                          (kb > kb0 + pl || k > 0) ? 1u : 0u);
-            else
-              tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * a_adv), bdesc + (uint64_t)(k * b_adv), idesc,
-                          (kb > kb0 + pl || k > 0) ? 1u : 0u);
+            tc_mma_bf16(d_tmem, adesc + (uint64_t)(k * a_adv), bdesc + (uint64_t)(k * b_adv), idesc,
+                        (kb > kb0 + pl || k > 0) ? 1u : 0u);
           }
           tc_commit(empty0 + 8 * stage);  // frees the smem slot when these MMAs retire
           if (++si == NSUB) { si = 0; phase ^= 1; }
@@ -431,20 +316,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int row_in_tile = q * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    bool scaled = false;
-    if constexpr (kDec) {
-      // the B rows hold bf16(x * w_norm): the RMSNorm's 1/rms is applied here, per decode row, from the per-tile sums
-      // of squares the producing GEMV left behind
-      scaled = p.dec.ssq_in != nullptr;
-      if (scaled) {
-        if (row_in_tile < BN) {
-          float ss = 0.f;
-          for (int t = 0; t < p.dec.n_ssq_in; ++t) ss += p.dec.ssq_in[(long long)t * p.dec.ld_ssq + row_in_tile];
-          sscale[row_in_tile] = rsqrtf(ss / (float)p.dec.norm_dim + p.dec.eps);
-        }
-        epi_bar();
-      }
-    }
     for (int t = t_begin; t < total_tiles; t += t_step) {
       const int mt = t % p.m_tiles;
       const int nt = (t / p.m_tiles) % p.n_tiles;
@@ -459,55 +330,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const bool row_ok = row < p.M;
       const int col_base = nt * BN;
 
-      if constexpr (kActA && EPI == SB_EPI_F32T) {
-        // accumulator lane = decode row, column = weight row of the tile: only the warp that owns TMEM lanes 0..31 works;
-        // out[ks][decode row][weight row] fp32, 128 consecutive floats per thread
-        if (q == 0) {
-          float* out = reinterpret_cast<float*>(p.D);
-          const float sc = (scaled && lane < BN) ? sscale[lane] : 1.f;
-#pragma unroll 1
-          for (int c = 0; c < BM / 32; ++c) {
-            uint32_t r[32];
-            tmem_ld_32x32(taddr + c * 32, r);
-            tmem_ld_wait();
-            const int n0 = mt * BM + c * 32;
-            if (lane < p.N && lane < BN) {
-              float* o = out + ((long long)ks * p.N + lane) * p.ldd + n0;
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                if (n0 + j < p.M)
-                  *reinterpret_cast<float4*>(o + j) = make_float4(__uint_as_float(r[j]) * sc, __uint_as_float(r[j + 1]) * sc,
-                                                                  __uint_as_float(r[j + 2]) * sc, __uint_as_float(r[j + 3]) * sc);
-              }
-            }
-          }
-        }
-      } else if constexpr (kActA && EPI == SB_EPI_F32T_SWIGLU) {
-        // tile columns [0, 64) = gate, [64, 128) = up of activation columns [64 mt, 64 mt + 64): SwiGLU is thread-local
-        if (q == 0) {
-          bf16* Dp = reinterpret_cast<bf16*>(p.D);
-          const float sc = (scaled && lane < BN) ? sscale[lane] : 1.f;
-#pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            uint32_t rg[32], ru[32];
-            tmem_ld_32x32(taddr + c * 32, rg);
-            tmem_ld_32x32(taddr + 64 + c * 32, ru);
-            tmem_ld_wait();
-            if (lane < p.N && lane < BN) {
-              float o[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float g = bf16_round(__uint_as_float(rg[j]) * sc);
-                const float u = bf16_round(__uint_as_float(ru[j]) * sc);
-                o[j] = bf16_round(silu(g)) * u;
-              }
-              bf16* dr = Dp + (long long)lane * p.ldd + mt * 64 + c * 32;
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) st8(dr + j, o + j);
-            }
-          }
-        }
-      } else if constexpr (EPI == SB_EPI_F32T) {
+      if constexpr (EPI == SB_EPI_F32T) {
         // split-K / swap-AB partial: out[ks][col][row] fp32 (row = weight row, col = decode row)
         static_assert(BN == 16 || BN == 32, "F32T epilogue is for the narrow decode tiles");
         uint32_t r[BN];
@@ -517,53 +340,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int j = 0; j < BN; ++j) {
             const int col = col_base + j;
-            float v = __uint_as_float(r[j]);
-            if (scaled) v *= sscale[j];
+            const float v = __uint_as_float(r[j]);
             if (col < p.N) out[((long long)ks * p.N + col) * p.ldd + row] = v;
           }
-        }
-      } else if constexpr (kClu) {
-        static_assert(BN == 16 || BN == 32, "decode tile");
-        // rank 0 owns the tile: operands of its finishing step that do not depend on this kernel are requested now
-        float xin[BN];
-        float wn = 0.f;
-        if constexpr (EPI == SB_EPI_DEC_RESID) {
-          if (crank == 0) {
-            const bool col_ok = row < p.M;
-            const bf16* xr = reinterpret_cast<const bf16*>(p.dec.x) + row;
-#pragma unroll
-            for (int j = 0; j < BN; ++j) xin[j] = (col_ok && j < p.dec.R) ? __bfloat162float(xr[(long long)j * p.M]) : 0.f;
-            wn = col_ok ? __bfloat162float(reinterpret_cast<const bf16*>(p.dec.w_next)[row]) : 0.f;
-          }
-        }
-        uint32_t r[BN];
-        dec_load_acc<BN, NP>(taddr, n_pl, r);
-        float accv[BN];
-#pragma unroll
-        for (int j = 0; j < BN; ++j) accv[j] = __uint_as_float(r[j]);
-        if (crank != 0) {
-          const uint32_t dst = mapa_shared(smem_u32(red + ((crank - 1) * BM + row_in_tile) * RSTR), 0);
-#pragma unroll
-          for (int j = 0; j < BN; j += 4) st_cluster_v4(dst + j * 4, accv[j], accv[j + 1], accv[j + 2], accv[j + 3]);
-          fence_acq_rel_cluster();
-          epi_bar();
-          if (row_in_tile == 0) mbar_arrive_cluster(mapa_shared(redbar, 0));
-        } else {
-          if (csize > 1) mbar_wait_cluster(redbar, 0);
-          for (uint32_t s2 = 1; s2 < csize; ++s2) {
-            const float4* src = reinterpret_cast<const float4*>(red + ((s2 - 1) * BM + row_in_tile) * RSTR);
-#pragma unroll
-            for (int j = 0; j < BN; j += 4) {
-              const float4 v = src[j >> 2];
-              accv[j] += v.x; accv[j + 1] += v.y; accv[j + 2] += v.z; accv[j + 3] += v.w;
-            }
-          }
-          if (scaled) {
-#pragma unroll
-            for (int j = 0; j < BN; ++j) accv[j] *= sscale[j];
-          }
-          if constexpr (EPI == SB_EPI_DEC_QKV) dec_qkv_finish<BN>(p, mt, row_in_tile, accv, xbuf);
-          else dec_resid_finish<BN>(p, mt, row_in_tile, accv, xin, wn, xbuf);
         }
       } else if constexpr (EPI == SB_EPI_F32T_SWIGLU) {
         // decode gate|up GEMV (swap-AB, no split-K) with SwiGLU fused: the tile's 128 weight rows are [64 gate | 64 up]
@@ -573,10 +352,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         static_assert(BN == 16 || BN == 32, "decode tile");
         uint32_t r[BN];
         dec_load_acc<BN, NP>(taddr, n_pl, r);
-        if (scaled) {
-#pragma unroll
-          for (int j = 0; j < BN; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * sscale[j]);
-        }
         if (q >= 2) {
 #pragma unroll
           for (int j = 0; j < BN; ++j) xbuf[(row_in_tile - 64) * 33 + j] = __uint_as_float(r[j]);
@@ -799,35 +574,6 @@ int num_sms() {
   return g_num_sms;
 }
 
-// shared memory of rank 0's receive buffer for the partial tiles of ranks 1..k_splits-1 (see gemm_kernel, kClu)
-size_t dec_red_bytes(int k_splits, int bn) { return (size_t)(k_splits > 1 ? k_splits - 1 : 0) * BM * (bn + 4) * 4; }
-
-// can `m_tiles` clusters of `k_splits` CTAs of the fused decode GEMV be resident at the same time?
-template <int BN>
-int dec_clusters_fit(int k_splits, int m_tiles, int* fit) {
-  using C = Cfg<BN>;
-  auto kfn = gemm_kernel<false, false, BN, SB_EPI_DEC_RESID>;
-  const size_t smem = C::SMEM_BYTES_CLU + dec_red_bytes(k_splits, BN);
-  *fit = 0;
-  if (smem > 227 * 1024) return 0;
-  SB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(m_tiles * k_splits);
-  cfg.blockDim = dim3(gemm_threads(SB_EPI_DEC_RESID));
-  cfg.dynamicSmemBytes = smem;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = k_splits;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  int n = 0;
-  SB_CUDA(cudaOccupancyMaxActiveClusters(&n, kfn, &cfg));
-  *fit = n >= m_tiles;
-  return 0;
-}
-
 template <bool A_MN, bool B_MN, int BN, int EPI>
 int launch(const sb_gemm_args* a, cudaStream_t stream) {
   using C = Cfg<BN>;
@@ -869,39 +615,7 @@ int launch(const sb_gemm_args* a, cudaStream_t stream) {
   p.prefetch_bytes = a->prefetch ? a->prefetch_bytes : 0;
   p.prefetch2 = reinterpret_cast<const uint8_t*>(a->prefetch2);
   p.prefetch2_bytes = a->prefetch2 ? a->prefetch2_bytes : 0;
-  if (a->dec) p.dec = *a->dec;
-  else memset(&p.dec, 0, sizeof(p.dec));
   const int total = p.m_tiles * p.n_tiles * p.k_splits;
-  if constexpr (EPI == SB_EPI_DEC_QKV || EPI == SB_EPI_DEC_RESID) {
-    // one cluster of k_splits CTAs per 128-row weight tile; every cluster must be resident at once (one tile per CTA)
-    const size_t smem = C::SMEM_BYTES_CLU + dec_red_bytes(p.k_splits, BN);
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-      SB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      smem_set = smem;
-    }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(total);
-    cfg.blockDim = dim3(gemm_threads(EPI));
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = p.k_splits;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = sb_pdl_enabled() ? 2 : 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, kfn, tmA, tmB, p);
-    if (le != cudaSuccess) {
-      sb_set_error("sb_gemm: cluster launch failed (%d clusters of %d CTAs, %zu B smem): %s", p.m_tiles, p.k_splits, smem,
-                   cudaGetErrorString(le));
-      return 1;
-    }
-    return sb_check_launch("sb_gemm");
-  }
   const int grid = total < num_sms() ? total : num_sms();
   const bool pdl = (EPI == SB_EPI_F32T || EPI == SB_EPI_F32T_SWIGLU) && sb_pdl_enabled();
   cudaError_t le = sb_launch(kfn, dim3(grid), dim3(gemm_threads(EPI)), (size_t)C::SMEM_BYTES, stream, pdl, tmA, tmB, p);
@@ -924,21 +638,6 @@ extern "C" int sb_gemm_effective_splits(int K, int k_splits) {
   return (k_iters + per - 1) / per;
 }
 
-extern "C" int sb_gemm_dec_splits(int M, int N, int K, int want, int* splits_out) {
-  SB_REQUIRE(splits_out && M > 0 && N > 0 && N <= 32 && K > 0, "sb_gemm_dec_splits: bad arguments");
-  const int m_tiles = (M + BM - 1) / BM;
-  int s = want < 1 ? 1 : (want > DEC_MAX_SPLITS ? DEC_MAX_SPLITS : want);
-  for (; s > 1; --s) {
-    const int eff = sb_gemm_effective_splits(K, s);
-    if (eff != s) continue;
-    int fit = 0;
-    if (N <= 16 ? dec_clusters_fit<16>(s, m_tiles, &fit) : dec_clusters_fit<32>(s, m_tiles, &fit)) return 1;
-    if (fit) break;
-  }
-  *splits_out = s;
-  return 0;
-}
-
 extern "C" int sb_gemm(const sb_gemm_args* a, sb_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   SB_REQUIRE(a != nullptr, "sb_gemm: null args");
@@ -956,8 +655,6 @@ extern "C" int sb_gemm(const sb_gemm_args* a, sb_stream_t stream_) {
     SB_REQUIRE(a->ldd >= a->M, "sb_gemm: F32T ldd (%lld) < M (%d)", a->ldd, a->M);
     SB_REQUIRE(a->prefetch == nullptr || ((reinterpret_cast<uintptr_t>(a->prefetch) & 15) == 0 && a->prefetch_bytes >= 0),
                "sb_gemm: prefetch pointer must be 16-byte aligned");
-    SB_REQUIRE(a->dec == nullptr || a->dec->ssq_in == nullptr || (a->dec->n_ssq_in > 0 && a->dec->ld_ssq >= a->N && a->dec->norm_dim > 0),
-               "sb_gemm: bad ssq_in description");
     if (a->N <= 16) return launch<false, false, 16, SB_EPI_F32T>(a, stream);
     return launch<false, false, 32, SB_EPI_F32T>(a, stream);
   }
@@ -969,34 +666,9 @@ extern "C" int sb_gemm(const sb_gemm_args* a, sb_stream_t stream_) {
     SB_REQUIRE(a->ldd >= a->M / 2, "sb_gemm: F32T_SWIGLU ldd (%lld) < M/2 (%d)", a->ldd, a->M / 2);
     SB_REQUIRE(a->prefetch == nullptr || (reinterpret_cast<uintptr_t>(a->prefetch) & 15) == 0,
                "sb_gemm: prefetch pointer must be 16-byte aligned");
-    SB_REQUIRE(a->dec == nullptr || a->dec->ssq_in == nullptr || (a->dec->n_ssq_in > 0 && a->dec->ld_ssq >= a->N && a->dec->norm_dim > 0),
-               "sb_gemm: bad ssq_in description");
     if (a->N <= 16) return launch<false, false, 16, SB_EPI_F32T_SWIGLU>(a, stream);
     return launch<false, false, 32, SB_EPI_F32T_SWIGLU>(a, stream);
   }
-  if (e == SB_EPI_DEC_QKV || e == SB_EPI_DEC_RESID) {
-    const sb_dec_fuse* d = a->dec;
-    SB_REQUIRE(!amn && !bmn, "sb_gemm: decode epilogues need K-major operands");
-    SB_REQUIRE(d != nullptr, "sb_gemm: decode epilogue without sb_dec_fuse");
-    SB_REQUIRE(a->N <= 32 && d->R > 0 && d->R <= a->N, "sb_gemm: decode epilogue needs R <= N <= 32 (R=%d, N=%d)", d->R, a->N);
-    SB_REQUIRE(sb_gemm_effective_splits(a->K, a->k_splits) <= DEC_MAX_SPLITS, "sb_gemm: decode epilogues take at most %d K splits", DEC_MAX_SPLITS);
-    SB_REQUIRE((a->N <= 16 ? Cfg<16>::SMEM_BYTES_CLU : Cfg<32>::SMEM_BYTES_CLU) +
-                       dec_red_bytes(sb_gemm_effective_splits(a->K, a->k_splits), a->N <= 16 ? 16 : 32) <= 227 * 1024,
-               "sb_gemm: too many K splits for the cluster reduction buffer (use sb_gemm_dec_splits)");
-    SB_REQUIRE(d->ssq_in == nullptr || (d->n_ssq_in > 0 && d->ld_ssq >= a->N && d->norm_dim > 0),
-               "sb_gemm: bad ssq_in description (n=%d ld=%d dim=%d)", d->n_ssq_in, d->ld_ssq, d->norm_dim);
-    if (e == SB_EPI_DEC_QKV) {
-      SB_REQUIRE(a->bias && d->step_ptr && d->q_out && d->k_cache && d->v_cache && d->c_max > 0, "sb_gemm: DEC_QKV needs bias, step_ptr, q_out and the caches");
-      SB_REQUIRE(d->n_heads > 0 && d->n_kv_heads > 0 && a->M == (d->n_heads + 2 * d->n_kv_heads) * BM,
-                 "sb_gemm: DEC_QKV needs head_dim 128 and M = (heads + 2 kv_heads) * 128, got M=%d", a->M);
-      if (a->N <= 16) return launch<false, false, 16, SB_EPI_DEC_QKV>(a, stream);
-      return launch<false, false, 32, SB_EPI_DEC_QKV>(a, stream);
-    }
-    SB_REQUIRE(d->x && d->w_next && d->xw && d->ssq_out && d->ld_ssq >= d->R, "sb_gemm: DEC_RESID needs x, w_next, xw, ssq_out");
-    if (a->N <= 16) return launch<false, false, 16, SB_EPI_DEC_RESID>(a, stream);
-    return launch<false, false, 32, SB_EPI_DEC_RESID>(a, stream);
-  }
-  SB_REQUIRE(a->dec == nullptr || e == SB_EPI_F32T || e == SB_EPI_F32T_SWIGLU, "sb_gemm: sb_dec_fuse only with the decode epilogues");
   SB_REQUIRE(a->N % 8 == 0 && a->ldd % 8 == 0, "sb_gemm: N and ldd must be multiples of 8");
   SB_REQUIRE(a->k_splits <= 1, "sb_gemm: split-K only with the F32T epilogue");
   if (e == SB_EPI_LMHEAD) {

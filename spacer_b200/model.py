@@ -1017,8 +1017,7 @@ class Qwen2VLB200:
     L2_PREFETCH_BYTES = 16 << 20          # default window after a GEMV (o, gate|up, down, lm_head)
     L2_PREFETCH_ATTN_BYTES = 48 << 20     # head of gate|up requested behind the qkv GEMV
 
-    def _gemv(self, w, x16, out_parts, splits, next_w=None, swiglu=False, next2_w=None, next_bytes=None, next2_bytes=0,
-              dec=None, epilogue=None, bias=None):
+    def _gemv(self, w, x16, out_parts, splits, next_w=None, swiglu=False, next2_w=None, next_bytes=None, next2_bytes=0):
         """parts[s][r][n] = x16[r] . w[n] over K split s   (swap-AB tcgen05 GEMM, weights streamed once).
         next_w / next2_w: weight matrices the decode step reads next; their heads are prefetched into L2 behind this
         GEMV.  swiglu: w is the interleaved gate|up matrix and out_parts the bf16 activation [rows, I] (fused epilogue)."""
@@ -1027,18 +1026,16 @@ class Qwen2VLB200:
         nb2 = 0 if next2_w is None else min(next2_w.numel() * 2, next2_bytes)
         kw = dict(prefetch=next_w if nb else None, prefetch_bytes=nb, prefetch2=next2_w if nb2 else None, prefetch2_bytes=nb2)
         if swiglu:
-            ops.gemm(w, x16, out=out_parts, epilogue=ops.EPI_F32T_SWIGLU, dec=dec, **kw)
+            ops.gemm(w, x16, out=out_parts, epilogue=ops.EPI_F32T_SWIGLU, **kw)
         else:
-            ops.gemm(w, x16, out=out_parts, epilogue=EPI_F32T if epilogue is None else epilogue, k_splits=splits,
-                     dec=dec, bias=bias, **kw)
+            ops.gemm(w, x16, out=out_parts, epilogue=EPI_F32T, k_splits=splits, **kw)
 
     def _splits_for(self, n_out, k):
         m_tiles = (n_out + 127) // 128
         if m_tiles >= 148:
             return 1
         s = max(1, 148 // m_tiles)
-        s = min(s, max(1, (k + 63) // 64))
-        return min(s, 8) if self.decode_fused else s   # fused epilogues: the splits of a tile form a cluster (<= 8)
+        return min(s, max(1, (k + 63) // 64))
 
     def _alloc_decode(self, R, P, c_max, n_prompts):
         d, dev = self.dims, self.device
@@ -1049,12 +1046,6 @@ class Qwen2VLB200:
         for name, (n_out, k) in dict(qkv=(d.qkv_dim, H), o=(H, d.heads * d.head_dim), gu=(2 * I, H), down=(H, I),
                                      lm=(d.vocab, H)).items():
             S[name] = 1 if name == "lm" else lib.sb_gemm_effective_splits(k, self._splits_for(n_out, k))
-            if self.decode_fused and name in ("qkv", "o", "down") and S[name] > 1:
-                # the K splits of a tile form a cluster; every cluster must be resident (sb_gemm_dec_splits)
-                import ctypes
-                got = ctypes.c_int(0)
-                ops._lib.check(lib.sb_gemm_dec_splits(n_out, RP, k, S[name], ctypes.byref(got)), "sb_gemm_dec_splits")
-                S[name] = got.value
         st = dict(
             R=R, RP=RP, P=P, c_max=c_max, S=S,
             x=torch.zeros((RP, H), device=dev, dtype=BF16), xn=torch.zeros((RP, H), device=dev, dtype=BF16),
@@ -1075,9 +1066,6 @@ class Qwen2VLB200:
             out_ids=torch.zeros((R, c_max), device=dev, dtype=I32),
             seed=torch.zeros(1, device=dev, dtype=torch.int64),
             seen=torch.zeros((RP, (d.vocab + 31) // 32), device=dev, dtype=I32),   # token bitmap (repetition penalty)
-            # fused-epilogue chain (sb_dec_fuse): x * w_norm and per-128-column-tile sums of squares
-            xw=torch.zeros((RP, H), device=dev, dtype=BF16),
-            ssq=torch.zeros(((H + 127) // 128, RP), device=dev, dtype=F32),
             graphs={},
         )
         st["attn_ws"] = None      # sized on first use (depends on the group split)
@@ -1104,13 +1092,6 @@ class Qwen2VLB200:
         st["step"].zero_(); st["finished"].zero_(); st["tokens"].zero_(); st["out_ids"].zero_()
         return st
 
-    # decode_fused: the small kernels between the GEMVs of a layer (both RMSNorms, qkv bias/RoPE/KV append) run inside
-    # the GEMV epilogues (SB_EPI_DEC_QKV / SB_EPI_DEC_RESID + per-row rstd in the consumers): 6 kernels per layer
-    # instead of 9.  Parity-tested, but OFF by default: on B200 a cluster of 4 fits only 33 times (132 SMs) and a
-    # cluster of 5 fewer than 28 times, so the fused GEMVs stream with 108-112 CTAs instead of 140-144 and every SM
-    # tops out at ~48 GB/s -- the step gets slower (3.30 vs 3.16 ms, profiles/r01_decode_fused_epilogues.md).
-    decode_fused = os.environ.get("SB_DECODE_FUSED") is not None
-
     def _sample(self, st, sp, suppress_eos):
         """Next token per row from st["logits"] under the sampling parameters `sp` (SamplingParams): HF's processor chain
         repetition penalty -> temperature -> top-k -> top-p -> multinomial (TRN:277-302 generation configs), or greedy
@@ -1123,8 +1104,6 @@ class Qwen2VLB200:
 
     def _decode_step(self, st, rope_base, rows_group0, samp, suppress_eos):
         """Enqueue one decode step (feeds tokens at slot *step, samples the next token into slot *step + 1)."""
-        if self.decode_fused:
-            return self._decode_step_fused(st, rope_base, rows_group0, samp, suppress_eos)
         d, W = self.dims, self.params
         R, RP, P, S = st["R"], st["RP"], st["P"], st["S"]
         H, I = d.hidden, d.inter
@@ -1161,64 +1140,11 @@ class Qwen2VLB200:
         ops.call("sb_step_advance", st["step"])
         self._sample(st, samp, suppress_eos)
 
-    def _decode_step_fused(self, st, rope_base, rows_group0, samp, suppress_eos):
-        """One decode step with the fused GEMV epilogues: per layer qkv GEMV (+ bias, M-RoPE, KV append) -> attention ->
-        combine -> o GEMV (+ residual, x * ln2_w, sums of squares) -> gate|up GEMV (rstd scale + SwiGLU) -> down GEMV
-        (+ residual, x * next ln1_w, sums of squares)."""
-        d, W = self.dims, self.params
-        R, RP, P, S = st["R"], st["RP"], st["P"], st["S"]
-        H, I = d.hidden, d.inter
-        nh, nkv, hd = d.heads, d.kv_heads, d.head_dim
-        ws = self._attn_workspace(st, rows_group0)
-        ssq, n_ssq = st["ssq"], st["ssq"].shape[0]
-
-        def fuse(**kw):
-            f = ops.DecFuse()
-            f.R = R
-            for k, v in kw.items():
-                setattr(f, k, v.data_ptr() if isinstance(v, torch.Tensor) else v)
-            return f
-
-        def scaled(**kw):
-            return fuse(ssq_in=ssq, n_ssq_in=n_ssq, ld_ssq=RP, norm_dim=H, eps=float(d.rms_eps), **kw)
-
-        def resid(w_next):
-            return fuse(x=st["x"], w_next=w_next, xw=st["xw"], ssq_out=ssq, ld_ssq=RP)
-
-        ops.call("sb_dec_embed_norm", st["tokens"], W["embed"], st["x"], W["l.0.ln1_w"], st["xw"], ssq, RP, R, H)
-        for i in range(d.layers):
-            p = f"l.{i}."
-            qkv = scaled(step_ptr=st["step"], rope_base=int(rope_base),
-                         theta=float(d.rope_theta), n_heads=nh, n_kv_heads=nkv, q_out=st["q"], k_cache=st["kc"][i],
-                         v_cache=st["vc"][i], cache_stride_r=st["c_max"] * nkv * hd, c_max=st["c_max"])
-            self._gemv(W[p + "qkv_w"], st["xw"], st["p_qkv"], S["qkv"], next_w=W[p + "o_w"], next_bytes=1 << 30,
-                       next2_w=W[p + "gu_w"], next2_bytes=self.L2_PREFETCH_ATTN_BYTES, dec=qkv,
-                       epilogue=ops.EPI_DEC_QKV, bias=W[p + "qkv_b"])
-            kp1 = st["kp"][1][i] if len(st["kp"]) > 1 else None
-            vp1 = st["vp"][1][i] if len(st["vp"]) > 1 else None
-            ops.call("sb_dec_attn", st["q"], st["kp"][0][i], st["vp"][0][i], kp1, vp1, rows_group0, P, st["kc"][i],
-                     st["vc"][i], st["c_max"] * nkv * hd, st["c_max"], st["step"], nh, nkv, hd, hd ** -0.5, ws,
-                     ws.numel(), st["attn"], R)
-            self._gemv(W[p + "o_w"], st["attn"], st["p_o"], S["o"], next_w=W[p + "gu_w"], dec=resid(W[p + "ln2_w"]),
-                       epilogue=ops.EPI_DEC_RESID)
-            if S["gu"] == 1:
-                self._gemv(W[p + "gu_w"], st["xw"], st["act"], 1, next_w=W[p + "down_w"], swiglu=True, dec=scaled())
-            else:                # small models: gate|up split along K, SwiGLU as its own kernel
-                self._gemv(W[p + "gu_w"], st["xw"], st["p_gu"], S["gu"], next_w=W[p + "down_w"], dec=scaled())
-                ops.call("sb_dec_swiglu", st["p_gu"], S["gu"], RP * 2 * I, 2 * I, st["act"], R, I)
-            nxt_norm = W[f"l.{i + 1}.ln1_w"] if i + 1 < d.layers else W["norm_w"]
-            self._gemv(W[p + "down_w"], st["act"], st["p_down"], S["down"],
-                       next_w=W[f"l.{i + 1}.qkv_w"] if i + 1 < d.layers else W["lm_head"], dec=resid(nxt_norm),
-                       epilogue=ops.EPI_DEC_RESID)
-        self._gemv(W["lm_head"], st["xw"], st["logits"], 1, next_w=W["l.0.qkv_w"], dec=scaled())
-        ops.call("sb_step_advance", st["step"])
-        self._sample(st, samp, suppress_eos)
-
     def _decode_graph(self, st, rope_base, rows_group0, sp, suppress_eos):
         """Capture one decode step into a CUDA graph (cached per decode state and step arguments).  Captured with the
         raw CUDAGraph API: the `torch.cuda.graph` context manager would empty the caching allocator, which makes
         every later phase of the training step re-map its memory."""
-        key = (int(rope_base), int(rows_group0), sp.key(), bool(suppress_eos), bool(self.decode_fused))
+        key = (int(rope_base), int(rows_group0), sp.key(), bool(suppress_eos))
         hit = st["graphs"].get(key)
         if hit is not None:
             return hit

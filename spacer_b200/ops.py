@@ -10,8 +10,8 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (EPI_DEC_QKV, EPI_DEC_RESID, EPI_DLOGITS, EPI_F32T, EPI_F32T_SWIGLU, EPI_GELU, EPI_LMHEAD,
-                   EPI_QUICKGELU, EPI_STORE, EPI_SWIGLU, DecFuse, GemmArgs, SampleArgs, SpacerError, check)
+from ._lib import (EPI_DLOGITS, EPI_F32T, EPI_F32T_SWIGLU, EPI_GELU, EPI_LMHEAD, EPI_QUICKGELU, EPI_STORE, EPI_SWIGLU,
+                   GemmArgs, SampleArgs, SpacerError, check)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -62,7 +62,7 @@ def _req(t: torch.Tensor, dtype, name: str):
 def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn=False, b_mn=False, out=None, epilogue=EPI_STORE,
          bias=None, residual=None, aux=None, k_splits=1, bn=0, targets=None, lse_part=None,
          tgt_logit=None, lse=None, coef=None, M=None, N=None, K=None, prefetch=None, prefetch_bytes=0,
-         prefetch2=None, prefetch2_bytes=0, dec=None):
+         prefetch2=None, prefetch2_bytes=0):
     """D[M,N] = epi(A * B^T).  a: [M,K] (or [K,M] if a_mn); b: [N,K] (or [K,N] if b_mn)."""
     lib = _lib.load()
     _req(a, torch.bfloat16, "a")
@@ -77,7 +77,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn=False, b_mn=False, out=None, 
     if kb != K:
         raise SpacerError(f"gemm: K mismatch {K} vs {kb}")
     if out is None:
-        if epilogue in (EPI_F32T, EPI_DEC_QKV, EPI_DEC_RESID):
+        if epilogue == EPI_F32T:
             splits = lib.sb_gemm_effective_splits(K, k_splits)
             out = torch.empty((splits, N, M), device=a.device, dtype=torch.float32)
         elif epilogue == EPI_SWIGLU:
@@ -106,8 +106,6 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn=False, b_mn=False, out=None, 
         g.prefetch, g.prefetch_bytes = prefetch.data_ptr(), int(prefetch_bytes)
     if prefetch2 is not None:
         g.prefetch2, g.prefetch2_bytes = prefetch2.data_ptr(), int(prefetch2_bytes)
-    if dec is not None:
-        g.dec = C.pointer(dec)
     check(lib.sb_gemm(C.byref(g), _stream()), "sb_gemm")
     return out
 

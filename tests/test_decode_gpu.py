@@ -420,135 +420,3 @@ def test_adamw_matches_torch(grad_f32, mom_bf16):
     tol = 2e-3 if mom_bf16 else 1e-5
     assert (master - ref_p.data).abs().max().item() < tol
     assert torch.equal(p, master.bfloat16())
-
-
-# ------------------------------------------------------------------------------------------------
-# fused decode-step GEMV epilogues (sb_dec_fuse): must reproduce the unfused kernels they replace
-# ------------------------------------------------------------------------------------------------
-def _dec_splits(M, RP, K, want):
-    import ctypes
-    from spacer_b200 import ops
-    got = ctypes.c_int(0)
-    ops._lib.check(ops._lib.load().sb_gemm_dec_splits(M, RP, K, want, ctypes.byref(got)), "sb_gemm_dec_splits")
-    assert 1 <= got.value <= want
-    return got.value
-
-
-def _fuse(R, **kw):
-    from spacer_b200 import ops
-    f = ops.DecFuse()
-    f.R = R
-    for k, v in kw.items():
-        setattr(f, k, v.data_ptr() if isinstance(v, torch.Tensor) else v)
-    return f
-
-
-@pytest.mark.parametrize("R,RP,nh,nkv,K,S", [(12, 16, 28, 4, 3584, 4), (6, 16, 2, 1, 256, 4), (24, 32, 12, 2, 1536, 8)])
-def test_dec_qkv_epilogue_matches_unfused(R, RP, nh, nkv, K, S):
-    """SB_EPI_DEC_QKV == F32T partials + sb_dec_qkv_post, bit for bit (q, the K/V cache slot, nothing else touched),
-    for several steps in a row (the tile tickets must return to zero)."""
-    from spacer_b200 import ops
-    hd, Cmax, rope_base = 128, 24, 57
-    M = (nh + 2 * nkv) * hd
-    w = rnd((M, K), 1, 0.05)
-    bias = rnd((M,), 2, 0.1)
-    S = _dec_splits(M, RP, K, S)
-    S_eff = ops._lib.load().sb_gemm_effective_splits(K, S)
-    for step in (0, 7, 23):
-        x = torch.zeros((RP, K), device="cuda", dtype=torch.bfloat16)
-        x[:R] = rnd((R, K), 3 + step, 1.0)
-        step_t = torch.tensor([step], dtype=torch.int32, device="cuda")
-        kc, vc = rnd((R, Cmax, nkv * hd), 4, 0.5), rnd((R, Cmax, nkv * hd), 5, 0.5)
-        kc2, vc2 = kc.clone(), vc.clone()
-        q1 = torch.zeros((RP, nh * hd), device="cuda", dtype=torch.bfloat16)
-        q2 = torch.zeros_like(q1)
-        parts = ops.gemm(w, x, epilogue=ops.EPI_F32T, k_splits=S)
-        assert parts.shape[0] == S_eff
-        ops.call("sb_dec_qkv_post", parts, S_eff, RP * M, M, bias, step_t, rope_base, 1e6, nh, nkv, hd, q1, kc, vc,
-                 Cmax * nkv * hd, Cmax, R)
-        f = _fuse(R, step_ptr=step_t, rope_base=rope_base, theta=1e6, n_heads=nh, n_kv_heads=nkv,
-                  q_out=q2, k_cache=kc2, v_cache=vc2, cache_stride_r=Cmax * nkv * hd, c_max=Cmax)
-        ops.gemm(w, x, out=torch.empty(8, device="cuda"), epilogue=ops.EPI_DEC_QKV, k_splits=S, bias=bias, dec=f)
-        torch.cuda.synchronize()
-        assert torch.equal(q1, q2), f"q differs at step {step}"
-        assert torch.equal(kc, kc2) and torch.equal(vc, vc2), f"cache differs at step {step}"
-
-
-@pytest.mark.parametrize("R,RP,H,K,S", [(12, 16, 3584, 18944, 5), (12, 16, 3584, 3584, 5), (6, 16, 256, 512, 8),
-                                        (24, 32, 1536, 8960, 8)])
-def test_dec_resid_epilogue_matches_unfused(R, RP, H, K, S):
-    """SB_EPI_DEC_RESID: the residual stream equals sb_dec_residual_rmsnorm's bit for bit; xw = bf16(x * w_next); the
-    per-tile sums of squares add up to sum(x^2); and a consumer GEMV scaled by them reproduces RMSNorm -> linear."""
-    from spacer_b200 import ops
-    w = rnd((H, K), 1, 0.03)
-    a = torch.zeros((RP, K), device="cuda", dtype=torch.bfloat16)
-    a[:R] = rnd((R, K), 2, 1.0)
-    x0 = torch.zeros((RP, H), device="cuda", dtype=torch.bfloat16)
-    x0[:R] = rnd((R, H), 3, 1.0)
-    wn = 1 + rnd((H,), 4, 0.1)
-    S = _dec_splits(H, RP, K, S)
-    n_t = (H + 127) // 128
-    for rep in range(2):
-        x1, x2 = x0.clone(), x0.clone()
-        parts = ops.gemm(w, a, epilogue=ops.EPI_F32T, k_splits=S)
-        xn = torch.zeros((RP, H), device="cuda", dtype=torch.bfloat16)
-        ops.call("sb_dec_residual_rmsnorm", x1, parts, parts.shape[0], RP * H, H, wn, xn, R, H, 1e-6)
-        xw = torch.zeros((RP, H), device="cuda", dtype=torch.bfloat16)
-        ssq = torch.zeros((n_t, RP), device="cuda", dtype=torch.float32)
-        f = _fuse(R, x=x2, w_next=wn, xw=xw, ssq_out=ssq, ld_ssq=RP)
-        ops.gemm(w, a, out=torch.empty(8, device="cuda"), epilogue=ops.EPI_DEC_RESID, k_splits=S, dec=f)
-        torch.cuda.synchronize()
-        assert torch.equal(x1, x2), "residual stream differs"
-        assert torch.equal(xw[:R], (x2[:R].float() * wn.float()).bfloat16())
-        ref_ss = x2[:R].float().pow(2).sum(-1)
-        assert torch.allclose(ssq.sum(0)[:R], ref_ss, rtol=1e-5)
-    # consumer: (xw @ W2^T) * rstd  vs  RMSNorm(x) @ W2^T computed from the unfused kernel's xn
-    N2 = 512
-    w2 = rnd((N2, H), 5, 0.05)
-    sc = _fuse(R, ssq_in=ssq, n_ssq_in=n_t, ld_ssq=RP, norm_dim=H, eps=1e-6)
-    y = ops.gemm(w2, xw, epilogue=ops.EPI_F32T, k_splits=1, dec=sc)[0]
-    ref = xn[:R].float() @ w2.float().t()
-    close(y[:R], ref, 1e-2, "scaled consumer GEMV")
-    exact = (x2[:R].float() * torch.rsqrt(x2[:R].float().pow(2).mean(-1, keepdim=True) + 1e-6) * wn.float()) @ w2.float().t()
-    assert (y[:R] - exact).abs().max() <= (ref - exact).abs().max() * 1.5 + 1e-3   # no worse than the bf16 two-step norm
-
-
-def test_dec_embed_norm():
-    from spacer_b200 import ops
-    R, RP, H, V = 12, 16, 3584, 1000
-    emb = rnd((V, H), 1, 1.0)
-    wn = 1 + rnd((H,), 2, 0.1)
-    tok = torch.randint(0, V, (RP,), dtype=torch.int32, device="cuda")
-    x = torch.zeros((RP, H), device="cuda", dtype=torch.bfloat16)
-    xw = torch.zeros_like(x)
-    n_t = H // 128
-    ssq = torch.zeros((n_t, RP), device="cuda", dtype=torch.float32)
-    ops.call("sb_dec_embed_norm", tok, emb, x, wn, xw, ssq, RP, R, H)
-    assert torch.equal(x[:R], emb[tok[:R].long()])
-    assert torch.equal(xw[:R], (x[:R].float() * wn.float()).bfloat16())
-    ref = x[:R].float().view(R, n_t, 128).pow(2).sum(-1).t()
-    assert torch.allclose(ssq[:, :R], ref, rtol=1e-5)
-
-
-def test_fused_decode_step_matches_unfused_chain():
-    """One rollout on the tiny model with the fused epilogues vs the 9-kernel chain: the first step's logits agree to
-    bf16 rounding noise, and both chains produce valid rollouts of the same shape."""
-    from oracle import qwen2vl_ref as R
-    from oracle.make_golden import tiny_case
-    from spacer_b200 import config
-    from spacer_b200.model import Qwen2VLB200
-    d_or, d = R.dims_tiny(2, 2), config.tiny(2, 2)
-    w = R.init_weights(d_or, seed=0)
-    case = tiny_case(d_or)
-    logits = {}
-    for fused in (False, True):
-        m = Qwen2VLB200(d, "cuda:0")
-        m.decode_fused = fused
-        m.load_state_dict(w)
-        out = m.generate(case["prompt_ids"], case["pixel_values"].cuda(), case["grid_thw"], max_new_tokens=2,
-                         num_return_sequences=4, top_p=0.95, seed=5, min_new_tokens=2, use_graph=False)
-        assert out.shape[0] == 4
-        logits[fused] = m._last_decode_state["logits"][0, :4].clone()
-    err = (logits[True] - logits[False]).abs().max().item()
-    scale = logits[False].abs().max().item()
-    assert err < 2e-2 * scale + 1e-3, (err, scale)

@@ -46,12 +46,11 @@ def main():
     lib = ops._lib.load()
     SP = SamplingParams(top_p=0.95, top_k=50, eos_ids=(dims.eos_id,), pad_id=dims.pad_id)   # the trainer's rollout options
     if "ab" in a.exp:
-        # A/B of the decode step: the 9-kernel-per-layer chain vs the cluster-fused GEMV epilogues (model.decode_fused)
+        # the decode step as bench.py runs it (graph replay at step 200) + the 113 GEMVs alone
         _, nxt = rope_index(ids.reshape(-1), grid, dims)
         kv = 2 * dims.layers * dims.kv_heads * dims.head_dim * 2
         byts = m.decode_weight_bytes() + 2 * ids.numel() * kv + (G + G // 2) * 250 * kv
-        for fused in (False, True, False, True):
-            m.decode_fused = fused
+        for _ in range(2):
             m._dec = None
             st = m._decode_state(G + G // 2, ids.numel(), C, 2)
             st["step"].fill_(200)
@@ -62,9 +61,8 @@ def main():
             st["step"].fill_(200)
             ms = timed(graph.replay, 100)
             prof = m.profile_decode_gemv(rows=G + G // 2, reps=3)
-            print(json.dumps({"exp": "ab", "fused": fused, "splits": st["S"], "ms": round(ms, 4), "gbs": round(byts / ms / 1e6, 1),
+            print(json.dumps({"exp": "ab", "splits": st["S"], "ms": round(ms, 4), "gbs": round(byts / ms / 1e6, 1),
                               "nodes": nodes, "gemv_only_gbs": round(prof["gbs"], 1), "gemv_sweep_ms": round(prof["ms_per_sweep"], 4)}), flush=True)
-    m.decode_fused = "fusedtrace" in a.exp
     m._dec = None
     # build the decode state with a short rollout (full prefill, 3 decode steps)
     st = m._decode_state(G + G // 2, ids.numel(), C, 2)
@@ -121,7 +119,7 @@ def main():
         idx = [i for i, r in enumerate(recs) if r[0] == 8]
         one = recs[idx[0] + 1: idx[1] + 1] if len(idx) >= 2 else recs
         t0 = one[0][1]
-        tag = "fused" if m.decode_fused else "unfused"
+        tag = "r02"
         out_path = os.path.join(ROOT, "gpurun_out", f"decode_trace_{tag}_pf{trace_cfg[0]}_{trace_cfg[1]}.txt")
         os.makedirs(os.path.dirname(out_path), exist_ok=True)
         agg = {}
@@ -136,7 +134,7 @@ def main():
                 d[0] += 1; d[1] += (tr_ - te) / 1e3; d[2] += (tn - tr_) / 1e3; d[3] += gap
                 prev_end = tn
         total = (one[-1][3] - t0) / 1e3
-        print(json.dumps({"exp": "trace", "fused": m.decode_fused, "splits": st["S"], "prefetch_mb": trace_cfg, "records": n, "step_kernels": len(one), "step_us": round(total, 1),
+        print(json.dumps({"exp": "trace", "splits": st["S"], "prefetch_mb": trace_cfg, "records": n, "step_kernels": len(one), "step_us": round(total, 1),
                           "per_kind": {k: {"n": v[0], "wait_us": round(v[1] / v[0], 2), "exec_us": round(v[2] / v[0], 2),
                                            "gap_after_prev_end_us": round(v[3] / v[0], 2), "exec_total_us": round(v[2], 1),
                                            "gap_total_us": round(v[3], 1)} for k, v in agg.items()}}), flush=True)

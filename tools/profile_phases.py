@@ -17,7 +17,7 @@ import torch  # noqa: E402
 
 import bench  # noqa: E402
 from spacer_b200 import config as mcfg  # noqa: E402
-from spacer_b200.model import GradStore, Qwen2VLB200, pack_prompt_completions  # noqa: E402
+from spacer_b200.model import GradStore, Qwen2VLB200, SamplingParams, pack_prompt_completions  # noqa: E402
 
 
 def main():
@@ -48,7 +48,7 @@ def main():
         pos, nxt = __import__("spacer_b200.model", fromlist=["rope_index"]).rope_index(ids.reshape(-1), grid, dims)
         prof.start()
         for _ in range(a.steps):
-            m._decode_step(st, nxt, G, 0.95, True)
+            m._decode_step(st, nxt, G, SamplingParams(top_p=0.95, top_k=50, eos_ids=(dims.eos_id,), pad_id=dims.pad_id), True)
             st["step"].fill_(n - 2)
         torch.cuda.synchronize()
         prof.stop()
