@@ -9,7 +9,10 @@ Host side (pure Python integers, checked against the reference's own functions v
 Device side:
     patchify(frames[, perm])  ->  pixel_values_videos (bf16 for the ViT and/or fp32 bit-exact with HF), video_grid_thw
     resize_frames(frames, h, w)  ->  the bicubic-antialias resize of fetch_video (QVU:310-315) on the GPU
-Video decoding (decord) is not part of this module: frames arrive decoded, as uint8 or float TCHW.
+Container decode (QVU:185-256, `_read_video_decord` / `_read_video_torchvision`): `read_video` opens the file with
+OpenCV's FFmpeg backend -- decord and PyAV are not in this image -- and decodes ONLY the sampled frames; `fetch_video`
+chains it with the GPU resize, i.e. the whole of the reference's `fetch_video` for a video path.  (Decoding on NVDEC is
+not built: SURVEY 8(f) row 2 remainder.)
 """
 from __future__ import annotations
 
@@ -211,3 +214,72 @@ def fetch_video_frames(video: torch.Tensor, video_fps: float, ele: dict | None =
     h, w = video_target_size(n, video.shape[2], video.shape[3], ele)
     sample_fps = n / max(total, 1e-6) * video_fps
     return resize_frames(frames, h, w), sample_fps
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# container decode (QVU:185-256) + the reference's fetch_video for a path (QVU:279-318)
+# ------------------------------------------------------------------------------------------------------------------
+def read_video(ele: dict):
+    """`_read_video_decord` / `_read_video_torchvision` (QVU:185-256): open `ele["video"]` (a path, "file://" allowed),
+    pick `smart_nframes` frames at `linspace(0, total - 1, n).round()` and return (uint8 CPU tensor [n, 3, H, W] RGB,
+    sample_fps).  `video_start` / `video_end` (seconds) restrict the clip like the torchvision backend does.  Only the
+    selected frames are colour-converted and kept; the frames between them are skipped with `grab()` (no decode output)."""
+    import cv2
+    path = ele["video"]
+    if not isinstance(path, str):
+        raise SpacerError("read_video: ele['video'] must be a path")
+    if path.startswith("file://"):
+        path = path[7:]
+    cap = cv2.VideoCapture(path)
+    if not cap.isOpened():
+        raise SpacerError(f"read_video: cannot open {path}")
+    try:
+        n_total = int(round(cap.get(cv2.CAP_PROP_FRAME_COUNT)))
+        video_fps = float(cap.get(cv2.CAP_PROP_FPS)) or FPS
+        first = 0
+        last = n_total - 1
+        if ele.get("video_start") is not None:
+            first = min(max(int(math.ceil(float(ele["video_start"]) * video_fps)), 0), max(n_total - 1, 0))
+        if ele.get("video_end") is not None:
+            last = min(int(math.floor(float(ele["video_end"]) * video_fps)), n_total - 1)
+        total = last - first + 1
+        if n_total <= 0 or total <= 0:
+            raise SpacerError(f"read_video: {path} holds no frames in the requested range")
+        n = smart_nframes(ele, total_frames=total, video_fps=video_fps)
+        wanted = [first + i for i in frame_indices(total, n)]
+        frames, pos, k = [], 0, 0
+        if wanted[0] > 64:                       # long lead-in: seek instead of grabbing frame by frame
+            cap.set(cv2.CAP_PROP_POS_FRAMES, wanted[0])
+            pos = wanted[0]
+        while k < len(wanted):
+            target = wanted[k]
+            while pos < target:                  # skip without retrieving
+                if not cap.grab():
+                    raise SpacerError(f"read_video: {path} ended at frame {pos} (container reports {n_total})")
+                pos += 1
+            ok, bgr = cap.read()
+            if not ok:
+                raise SpacerError(f"read_video: {path} ended at frame {pos} (container reports {n_total})")
+            pos += 1
+            rgb = torch.from_numpy(cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB)).permute(2, 0, 1).contiguous()
+            frames.append(rgb)
+            k += 1
+            while k < len(wanted) and wanted[k] == target:      # linspace can repeat an index on very short clips
+                frames.append(rgb)
+                k += 1
+    finally:
+        cap.release()
+    sample_fps = n / max(total, 1e-6) * video_fps
+    return torch.stack(frames), sample_fps
+
+
+def fetch_video(ele: dict, device="cuda", image_factor: int = IMAGE_FACTOR, return_video_sample_fps: bool = False):
+    """qwen-vl-utils' `fetch_video` for a video path (QVU:279-318): decode + sample (read_video), then the pixel budget /
+    `smart_resize` target and the bicubic-antialias resize on the GPU.  Returns float32 frames [n, 3, h, w] holding 0..255
+    (what the reference hands to the HF processor), optionally with sample_fps."""
+    video, sample_fps = read_video(ele)
+    video = video.pin_memory().to(device, non_blocking=True) if torch.cuda.is_available() else video.to(device)
+    n, _, height, width = video.shape
+    h, w = video_target_size(n, height, width, ele, image_factor)
+    out = resize_frames(video, h, w)
+    return (out, sample_fps) if return_video_sample_fps else out

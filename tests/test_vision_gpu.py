@@ -90,3 +90,33 @@ def test_fetch_video_frames_equals_reference_pipeline():
     assert frames.shape == ref.shape
     d = (frames.cpu() - ref).abs()
     assert d.max().item() <= 1.0 and (d > 0).float().mean().item() < 1e-3
+
+
+def test_fetch_video_from_a_container_file(tmp_path):
+    """The whole of qwen-vl-utils' fetch_video for a PATH (QVU:279-318): container decode (OpenCV/FFmpeg here, decord in
+    the reference), frame sampling, pixel budget / smart_resize, bicubic-antialias resize -- against torchvision's resize
+    of the same decoded frames; then straight into the patchify kernel (the trainer's rollout front-end)."""
+    cv2 = pytest.importorskip("cv2")
+    import numpy as np
+    import torchvision.transforms.functional as TF
+    from torchvision.transforms import InterpolationMode
+    from spacer_b200 import vision
+    path = str(tmp_path / "scene.mp4")
+    wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), 24.0, (320, 180))
+    rng = np.random.default_rng(0)
+    base = rng.integers(0, 256, (180, 320, 3), dtype=np.uint8)
+    for i in range(72):                              # 3 s at 24 fps -> 6 frames at the default 2 fps
+        wr.write(np.roll(base, 3 * i, axis=1))
+    wr.release()
+    ele = {"video": path}
+    frames, sample_fps = vision.fetch_video(ele, "cuda", return_video_sample_fps=True)
+    decoded, fps2 = vision.read_video(ele)
+    n = vision.smart_nframes({}, 72, 24.0)
+    h, w = vision.video_target_size(n, 180, 320)
+    assert n == 6 and decoded.shape == (6, 3, 180, 320) and frames.shape == (6, 3, h, w) and frames.dtype == torch.float32
+    assert abs(sample_fps - fps2) < 1e-9 and abs(sample_fps - 6 / 72 * 24.0) < 1e-6
+    ref = TF.resize(decoded, [h, w], interpolation=InterpolationMode.BICUBIC, antialias=True).float()
+    d = (frames.cpu() - ref).abs()
+    assert d.max().item() <= 1.0 and (d > 0).float().mean().item() < 1e-3
+    pv, _, grid = vision.patchify(frames)
+    assert grid.tolist() == [[3, h // 14, w // 14]] and pv.shape[1] == 1176
