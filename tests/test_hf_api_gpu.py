@@ -207,3 +207,44 @@ def test_fused_adamw_behind_torch_optim_interface():
     assert not torch.equal(before, model.mat.detach()) and torch.equal(model.mat.detach(), model.engine.params.mat)
     lp2 = model.per_token_logps(ids, **kw)
     assert lp2.mean().item() > lp.mean().item()          # one ascent step on the mean log-prob
+
+
+def test_processor_to_generate_end_to_end(tmp_path_factory):
+    """Rows a1-a3 chained into the rollout: conversation -> chat template -> processor(text, videos) (tokenisation,
+    placeholder expansion, GPU normalise/patchify) -> generate(**prompt_inputs, generation_config) -> batch_decode -> the
+    reward functions' input strings (TRN:390-467, 555-560)."""
+    from dataclasses import replace
+    from transformers import GenerationConfig
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_text_cpu import build_tok_dir
+    from oracle import qwen2vl_ref as R
+    from oracle.vision_ref import patchify_ref
+    from spacer_b200 import config
+    from spacer_b200.hf_api import Qwen2VLForConditionalGenerationB200
+    from spacer_b200.text import Qwen2Tokenizer, Qwen2VLProcessorB200
+    path, n = build_tok_dir(tmp_path_factory)
+    tok = Qwen2Tokenizer.from_pretrained(path)
+    d = replace(config.tiny(2, 2), image_token_id=tok.vocab["<|image_pad|>"], video_token_id=tok.vocab["<|video_pad|>"],
+                vision_start_id=tok.vocab["<|vision_start|>"], vision_end_id=tok.vocab["<|vision_end|>"],
+                eos_id=tok.vocab["<|im_end|>"], pad_id=tok.vocab["<|endoftext|>"])
+    model = Qwen2VLForConditionalGenerationB200.from_dims(d, "cuda", seed=0)
+    proc = Qwen2VLProcessorB200(tok, d, device="cuda")
+    conv = [{"role": "user", "content": [{"type": "video"}, {"type": "text", "text": "How many chairs are in this room?"}]}]
+    text = proc.apply_chat_template(conv, tokenize=False, add_generation_prompt=True)
+    frames = torch.randint(0, 256, (4, 3, 112, 112), generator=torch.Generator().manual_seed(2)).float()   # fetch_video output
+    inputs = proc(text=[text], images=None, videos=[frames], return_tensors="pt", padding=True, padding_side="left",
+                  add_special_tokens=False)
+    ref_pix, grid = patchify_ref(frames)
+    assert torch.equal(inputs["pixel_values_videos"].cpu(), ref_pix) and inputs["video_grid_thw"].tolist() == [list(grid)]
+    n_v = grid[0] * grid[1] * grid[2] // 4
+    ids = inputs["input_ids"]
+    assert ids.shape[0] == 1 and int((ids == d.video_token_id).sum()) == n_v and bool(inputs["attention_mask"].all())
+    assert tok.decode(ids[0]).replace("<|video_pad|>" * n_v, "<|video_pad|>") == text
+    G, C = 4, 10
+    out = model.generate(**inputs.to("cuda"), generation_config=GenerationConfig(
+        max_new_tokens=C, do_sample=True, top_p=0.95, temperature=1, num_return_sequences=G, pad_token_id=proc.pad_token_id))
+    P = ids.shape[1]
+    assert out.shape[0] == G and torch.equal(out[:, :P].cpu(), ids.expand(G, -1))
+    completions = proc.batch_decode(out[:, P:], skip_special_tokens=True)
+    assert len(completions) == G and all(isinstance(c, str) for c in completions)
+    assert all("<|im_end|>" not in c and "<|endoftext|>" not in c for c in completions)
