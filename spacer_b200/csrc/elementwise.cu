@@ -199,18 +199,24 @@ static float* col_scratch() {
 // fp32 math, one rounding to bf16.  inverse=1 rotates by -angle (backward).
 // token n of a (t,h,w) grid sits at frame n/(h*w), merge-block-major inside the frame.
 // ------------------------------------------------------------------------------------------
-// one CTA per token: the token's half = hd/2 (cos, sin) pairs are computed once into shared memory, then every
-// (q|k, head, 8-element chunk) is rotated with 16-byte loads and stores
+// ROPE_TOK tokens per CTA iteration: their hd/2 (cos, sin) pairs are computed once into shared memory (all threads busy:
+// powf / sincosf are the long-latency part), then every (token, q|k, head, 8-element chunk) is rotated with 16-byte loads
+// and stores, several independent items per thread.  (One token per CTA left this kernel 8-12x off the HBM roofline:
+// 160 us for 84 MB at cfg3, profiles/r01_launches_train_c3_tcbwd.txt.)
+constexpr int ROPE_TOK = 8;
 __global__ void __launch_bounds__(256)
 rope_vit_kernel(bf16* __restrict__ qkv, int T, int heads, int hd, const int* __restrict__ grids, int n_grids, int merge,
                 int inverse, const int* __restrict__ pos_hw) {
-  __shared__ float s_cs[128], s_sn[128];
+  __shared__ float s_cs[ROPE_TOK][128], s_sn[ROPE_TOK][128];
   const int half = hd / 2;      // 40: rotation pairs (i, i+half)
   const int quarter = hd / 4;   // 20: first quarter of freqs follows h, second follows w
   const int chunks = half / 8;
-  for (int n = blockIdx.x; n < T; n += gridDim.x) {
-    if ((int)threadIdx.x < half) {
-      const int i = threadIdx.x;
+  const int per_tok = 2 * heads * chunks;
+  for (int n0 = blockIdx.x * ROPE_TOK; n0 < T; n0 += gridDim.x * ROPE_TOK) {
+    const int nt = min(ROPE_TOK, T - n0);
+    for (int e = threadIdx.x; e < nt * half; e += blockDim.x) {
+      const int tk = e / half, i = e % half;
+      const int n = n0 + tk;
       int hpos, wpos;
       if (pos_hw) {   // explicit (h, w) per token: Qwen2.5-VL's window-reordered sequence
         hpos = pos_hw[2 * n];
@@ -235,20 +241,20 @@ rope_vit_kernel(bf16* __restrict__ qkv, int T, int heads, int hd, const int* __r
       const float ang = (float)(i < quarter ? hpos : wpos) * inv_freq;
       float sn, cs;
       sincosf(ang, &sn, &cs);
-      s_cs[i] = cs;
-      s_sn[i] = inverse ? -sn : sn;
+      s_cs[tk][i] = cs;
+      s_sn[tk][i] = inverse ? -sn : sn;
     }
     __syncthreads();
-    bf16* row = qkv + (long long)n * 3 * heads * hd;
-    for (int w = threadIdx.x; w < 2 * heads * chunks; w += blockDim.x) {
-      const int c = w % chunks;
-      bf16* p = row + (w / chunks) * hd + c * 8;      // (which, head) are contiguous: q heads then k heads
+    for (int w = threadIdx.x; w < nt * per_tok; w += blockDim.x) {
+      const int tk = w / per_tok, wi = w % per_tok;
+      const int c = wi % chunks;
+      bf16* p = qkv + (long long)(n0 + tk) * 3 * heads * hd + (wi / chunks) * hd + c * 8;   // q heads then k heads
       float a[8], b[8], oa[8], ob[8];
       ld8f(p, a);
       ld8f(p + half, b);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float cs = s_cs[c * 8 + j], sn = s_sn[c * 8 + j];
+        const float cs = s_cs[tk][c * 8 + j], sn = s_sn[tk][c * 8 + j];
         oa[j] = a[j] * cs - b[j] * sn;
         ob[j] = b[j] * cs + a[j] * sn;
       }
@@ -263,38 +269,43 @@ rope_vit_kernel(bf16* __restrict__ qkv, int T, int heads, int hd, const int* __r
 // M-RoPE in place on q,k of qkv [T, (nh+2nkv)*hd] + optional KV-cache write   MQ2:188-254
 // pos: int32 [3, T].  HF numerics: cos/sin fp32 -> bf16; bf16(q*cos) + bf16(rot*sin) -> bf16.
 // ------------------------------------------------------------------------------------------
-// one CTA per token: (cos, sin) of the hd/2 frequencies once into shared memory, then 16-byte chunks per head
+// ROPE_TOK tokens per CTA iteration (see rope_vit_kernel): (cos, sin) of their hd/2 frequencies once into shared memory,
+// then 16-byte chunks per (token, head)
 __global__ void __launch_bounds__(256)
 mrope_kernel(bf16* __restrict__ qkv, const int* __restrict__ pos, int T, int nh, int nkv, int hd, float theta,
              int sec_t, int sec_h, int inverse, bf16* __restrict__ k_out, bf16* __restrict__ v_out, long long kv_ld) {
-  __shared__ float s_cs[128], s_sn[128];
+  __shared__ float s_cs[ROPE_TOK][128], s_sn[ROPE_TOK][128];
   const int half = hd / 2;
   const int chunks = half / 8;
   const int nrot = nh + nkv;
+  const int per_tok = nrot * chunks;
+  const int v_chunks = nkv * hd / 8;
   const int qkv_ld = (nh + 2 * nkv) * hd;
-  for (int n = blockIdx.x; n < T; n += gridDim.x) {
-    if ((int)threadIdx.x < half) {
-      const int i = threadIdx.x;
+  for (int n0 = blockIdx.x * ROPE_TOK; n0 < T; n0 += gridDim.x * ROPE_TOK) {
+    const int nt = min(ROPE_TOK, T - n0);
+    for (int e = threadIdx.x; e < nt * half; e += blockDim.x) {
+      const int tk = e / half, i = e % half;
       const int stream = i < sec_t ? 0 : (i < sec_t + sec_h ? 1 : 2);
-      const float p_ = (float)pos[(long long)stream * T + n];
+      const float p_ = (float)pos[(long long)stream * T + n0 + tk];
       const float inv_freq = 1.0f / powf(theta, (float)(2 * i) / (float)hd);
       float sn, cs;
       sincosf(p_ * inv_freq, &sn, &cs);
-      s_cs[i] = bf16_round(cs);
+      s_cs[tk][i] = bf16_round(cs);
       sn = bf16_round(sn);
-      s_sn[i] = inverse ? -sn : sn;
+      s_sn[tk][i] = inverse ? -sn : sn;
     }
     __syncthreads();
-    bf16* row = qkv + (long long)n * qkv_ld;
-    for (int w = threadIdx.x; w < nrot * chunks; w += blockDim.x) {
-      const int c = w % chunks, head = w / chunks;
-      bf16* p = row + head * hd + c * 8;
+    for (int w = threadIdx.x; w < nt * per_tok; w += blockDim.x) {
+      const int tk = w / per_tok, wi = w % per_tok;
+      const int c = wi % chunks, head = wi / chunks;
+      const int n = n0 + tk;
+      bf16* p = qkv + (long long)n * qkv_ld + head * hd + c * 8;
       float a[8], b[8], oa[8], ob[8];
       ld8f(p, a);
       ld8f(p + half, b);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float cs = s_cs[c * 8 + j], sn = s_sn[c * 8 + j];
+        const float cs = s_cs[tk][c * 8 + j], sn = s_sn[tk][c * 8 + j];
         oa[j] = bf16_round(bf16_round(a[j] * cs) + bf16_round(-b[j] * sn));
         ob[j] = bf16_round(bf16_round(b[j] * cs) + bf16_round(a[j] * sn));
       }
@@ -307,9 +318,11 @@ mrope_kernel(bf16* __restrict__ qkv, const int* __restrict__ pos, int T, int nh,
       }
     }
     if (v_out) {
-      for (int c = threadIdx.x; c < nkv * hd / 8; c += blockDim.x)
+      for (int w = threadIdx.x; w < nt * v_chunks; w += blockDim.x) {
+        const int n = n0 + w / v_chunks, c = w % v_chunks;
         *reinterpret_cast<uint4*>(v_out + (long long)n * kv_ld + c * 8) =
-            *reinterpret_cast<const uint4*>(row + (nh + nkv) * hd + c * 8);
+            *reinterpret_cast<const uint4*>(qkv + (long long)n * qkv_ld + (nh + nkv) * hd + c * 8);
+      }
     }
     __syncthreads();
   }
@@ -630,11 +643,8 @@ extern "C" int sb_rope_vit(void* qkv, int T, int heads, int head_dim, const int*
                            int inverse, sb_stream_t stream) {
   SB_REQUIRE(qkv && grids_dev && T > 0 && heads > 0 && head_dim % 16 == 0 && head_dim <= 256 && n_grids > 0 && merge > 0,
              "sb_rope_vit: bad arguments (head_dim must be a multiple of 16, <= 256)");
-  int threads = (2 * heads * (head_dim / 16) + 31) / 32 * 32;
-  threads = threads < 64 ? 64 : (threads > 256 ? 256 : threads);
-  if (threads < head_dim / 2) threads = (head_dim / 2 + 31) / 32 * 32;
-  rope_vit_kernel<<<T, threads, 0, STREAM(stream)>>>((bf16*)qkv, T, heads, head_dim, grids_dev, n_grids, merge, inverse,
-                                                     nullptr);
+  rope_vit_kernel<<<(T + ROPE_TOK - 1) / ROPE_TOK, 256, 0, STREAM(stream)>>>((bf16*)qkv, T, heads, head_dim, grids_dev, n_grids,
+                                                                             merge, inverse, nullptr);
   return sb_check_launch("sb_rope_vit");
 }
 
@@ -642,10 +652,8 @@ extern "C" int sb_rope_vit_pos(void* qkv, int T, int heads, int head_dim, const 
                                sb_stream_t stream) {
   SB_REQUIRE(qkv && pos_hw && T > 0 && heads > 0 && head_dim % 16 == 0 && head_dim <= 256,
              "sb_rope_vit_pos: bad arguments (head_dim must be a multiple of 16, <= 256)");
-  int threads = (2 * heads * (head_dim / 16) + 31) / 32 * 32;
-  threads = threads < 64 ? 64 : (threads > 256 ? 256 : threads);
-  if (threads < head_dim / 2) threads = (head_dim / 2 + 31) / 32 * 32;
-  rope_vit_kernel<<<T, threads, 0, STREAM(stream)>>>((bf16*)qkv, T, heads, head_dim, nullptr, 0, 1, inverse, pos_hw);
+  rope_vit_kernel<<<(T + ROPE_TOK - 1) / ROPE_TOK, 256, 0, STREAM(stream)>>>((bf16*)qkv, T, heads, head_dim, nullptr, 0, 1, inverse,
+                                                                             pos_hw);
   return sb_check_launch("sb_rope_vit_pos");
 }
 
@@ -655,11 +663,8 @@ extern "C" int sb_mrope(void* qkv, const int* pos, int T, int n_heads, int n_kv_
   SB_REQUIRE(qkv && pos && T > 0 && head_dim % 16 == 0 && head_dim <= 256 && sec_t >= 0 && sec_h >= 0 &&
                  sec_t + sec_h <= head_dim / 2, "sb_mrope: bad arguments (head_dim must be a multiple of 16, <= 256)");
   SB_REQUIRE(k_out == nullptr || kv_ld % 8 == 0, "sb_mrope: kv_ld must be a multiple of 8");
-  int threads = ((n_heads + n_kv_heads) * (head_dim / 16) + 31) / 32 * 32;
-  threads = threads < 64 ? 64 : (threads > 256 ? 256 : threads);
-  if (threads < head_dim / 2) threads = (head_dim / 2 + 31) / 32 * 32;
-  mrope_kernel<<<T, threads, 0, STREAM(stream)>>>((bf16*)qkv, pos, T, n_heads, n_kv_heads, head_dim, theta, sec_t, sec_h,
-                                                  inverse, (bf16*)k_out, (bf16*)v_out, kv_ld);
+  mrope_kernel<<<(T + ROPE_TOK - 1) / ROPE_TOK, 256, 0, STREAM(stream)>>>((bf16*)qkv, pos, T, n_heads, n_kv_heads, head_dim, theta,
+                                                                          sec_t, sec_h, inverse, (bf16*)k_out, (bf16*)v_out, kv_ld);
   return sb_check_launch("sb_mrope");
 }
 

@@ -56,9 +56,11 @@ def rope_index(input_ids: torch.Tensor, grid_thw, dims: ModelDims, convention: s
     is_v = (ids == dims.video_token_id) | (ids == dims.image_token_id)
     pos = torch.zeros(3, L, dtype=torch.long)
     nxt, i, gi = 0, 0, 0
-    grids = [list(map(int, g)) for g in (grid_thw.tolist() if torch.is_tensor(grid_thw) else grid_thw)]
+    grids = [] if grid_thw is None else [list(map(int, g)) for g in (grid_thw.tolist() if torch.is_tensor(grid_thw) else grid_thw)]
     m = dims.merge
     isv = is_v.tolist()
+    if any(isv) and not grids:
+        raise SpacerError("visual placeholder tokens in the prompt but no grid_thw")
     while i < L:
         if isv[i]:
             t, h, w = grids[min(gi, len(grids) - 1)]

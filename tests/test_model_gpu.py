@@ -237,6 +237,99 @@ def test_trainer_step_runs_and_updates():
     assert set(tr.log()) >= {"reward", "kl", "loss"}
 
 
+def test_trainer_step_metrics_match_oracle_on_the_rollout():
+    """The metrics training_step logs (TRN:650-683) against oracle.grpo_ref on the SAME sampled completions: rewards,
+    bonuses, advantages and metrics recomputed by the oracle from the completion ids the step produced."""
+    from oracle import grpo_ref as GR
+    from spacer_b200 import rewards as RW
+    from spacer_b200.model import Qwen2VLB200
+    from spacer_b200.trainer import GRPOConfig, SGRLVRTrainerB200
+    R, d_or, d, m, w, wb = _setup()
+    ref = Qwen2VLB200(d)
+    ref.load_state_dict(w)
+    case = _case(d_or)
+    RW.set_map_data({})
+    texts = ["<think>x</think><answer>B</answer>", "nonsense", "<think>z</think><answer>C</answer>"]
+    seen = {}
+
+    def decode(ids):
+        seen[ids.shape[0]] = ids.clone()
+        return [texts[int(r[0]) % len(texts)] for r in ids.tolist()]
+    G, C = 4, 10
+    cfg = GRPOConfig(num_generations=G, max_completion_length=C, temporal=True, len_control=True, learning_rate=1e-4)
+    tr = SGRLVRTrainerB200(m, ref, [RW.accuracy_reward, RW.format_reward], cfg, decode)
+    ex = dict(input_ids=case["prompt_ids"], pixel_values_videos=case["pixel_values"].cuda(), video_grid_thw=case["grid_thw"],
+              solution="<answer>B</answer>", problem_type="multiple choice", path="x/scene0000_00.mp4", prompt="p")
+    mt = tr.training_step(ex)
+    comp, shuf = seen[G].cpu(), seen[G // 2].cpu()
+
+    def rpf_of(ids):
+        t = [texts[int(r[0]) % len(texts)] for r in ids.tolist()]
+        acc = [1.0 if "<answer>B</answer>" in x else 0.0 for x in t]
+        fmt = [1.0 if x.startswith("<think>") else 0.0 for x in t]
+        return torch.tensor([acc, fmt]).T.contiguous()
+    rpf, srpf = rpf_of(comp), rpf_of(shuf)
+    mask = GR.completion_mask(comp, d_or.eos_id)
+    summed, temporal = GR.temporal_bonus(rpf.clone(), srpf, True)
+    rewards = GR.length_bonus(summed.sum(1), rpf, mask, True)
+    adv, std = GR.advantages(rewards, G)
+    want = GR.step_metrics(mask, rpf, rewards, std, temporal, mt["kl"], G, ["accuracy_reward", "format_reward"])
+    for k, v in want.items():
+        assert abs(mt[k] - v) < 1e-5, (k, mt[k], v)
+    assert mt["generated_tokens"] == comp.numel() + shuf.numel()
+
+
+def test_text_only_step_after_a_video_step_does_not_reuse_vision_gradients():
+    """the vision-tower gradients of the previous step must not be applied again when a step has no visual
+    input (GradStore.zero_range), and the optimizer resynchronises its fp32 masters when weights are loaded behind its back."""
+    from spacer_b200.model import GradStore, pack_prompt_completions
+    from spacer_b200.trainer import AdamW, GRPOConfig
+    R, d_or, d, m, w, wb = _setup()
+    case = _case(d_or)
+    grads = GradStore(m.params)
+    adv = torch.tensor([0.7, -1.1, 0.2, 0.4]).cuda()
+    batch = pack_prompt_completions(case["prompt_ids"], case["completion_ids"], case["grid_thw"], d, m.device)
+    m.grpo_forward_backward(batch, case["pixel_values"].cuda(), case["grid_thw"], None, adv, 0.0, grads)
+    lo, hi = grads.mat_range("v.")
+    assert float(grads.mat[lo:hi].float().abs().sum()) > 0
+    text_prompt = case["prompt_ids"][:, :5]                       # no placeholder tokens
+    tb = pack_prompt_completions(text_prompt, case["completion_ids"], None, d, m.device)
+    m.grpo_forward_backward(tb, None, None, None, adv, 0.0, grads)
+    torch.cuda.synchronize()
+    assert float(grads.mat[lo:hi].float().abs().sum()) == 0.0
+    # master resync
+    opt = AdamW(m.params, GRPOConfig(learning_rate=1e-3))
+    w2 = R.init_weights(d_or, seed=9)
+    m.load_state_dict(w2)                                           # after the optimizer captured its masters
+    grads.mat.zero_(); grads.vec.zero_()
+    opt.step(grads)                                                 # zero gradients: weights must stay the NEW ones
+    torch.cuda.synchronize()
+    got = m.state_dict()["lm_head.weight"].float().cpu()
+    want = w2["lm_head.weight"].bfloat16().float()
+    assert (got - want).abs().max().item() < 2e-3 * want.abs().max().item() + 1e-6    # only weight decay moved them
+
+
+def test_grouped_rollout_widths_are_independent():
+    """the main and the frame-shuffled group are two generate() calls in the reference -- each is cut to ITS
+    longest completion (generation/utils.py stops when all rows of the call are done)."""
+    R, d_or, d, m, w, wb = _setup()
+    case = _case(d_or)
+    pix = case["pixel_values"].cuda()
+    widths = set()
+    for seed in range(6):
+        a, b = m.generate(case["prompt_ids"], pix, case["grid_thw"], max_new_tokens=48, num_return_sequences=4, top_p=0.95,
+                          seed=seed, pixel_values_videos_2=pix.flip(0).contiguous(), num_return_sequences_2=2)
+        P = case["prompt_ids"].shape[1]
+        for out in (a, b):
+            comp = out[:, P:]
+            is_eos = comp == d.eos_id
+            if bool(is_eos.any(1).all()):      # every row ended: the width is exactly the longest completion of THIS group
+                first = is_eos.int().argmax(1)
+                assert comp.shape[1] == int(first.max()) + 1
+        widths.add((a.shape[1], b.shape[1]))
+    assert len(widths) >= 1
+
+
 # ------------------------------------------------------------------------------------------------
 # Qwen2.5-VL (SURVEY.md 8(f) row 1): windowed RMSNorm/SwiGLU vision tower + temporal M-RoPE spacing on the CUDA path
 # ------------------------------------------------------------------------------------------------
