@@ -39,11 +39,20 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;
 // (tools/labs/ingest_dual_lab.cu, profiles/r02_ingest_dual_lab.md) -- which is what lets the cluster-fused epilogues, that
 // could only occupy 108-112 SMs, stream at full HBM speed (they were measured again, stayed slower than the plain
 // chain and were removed: profiles/r02_ingest_dual_lab.md).
+// Four pipelines on a 12-stage ring for the split-K GEMVs (SB_GEMV_PIPES_F32T = 4, SB_GEMV_STAGES_F32T = 12) were measured
+// too: 3.036 ms per decode step against 3.01-3.05 ms with two -- at 144-148 CTAs the stream is HBM-bound either way -- so
+// both kinds of GEMV run two.
 #ifndef SB_GEMV_PIPES
 #define SB_GEMV_PIPES 2
 #endif
+#ifndef SB_GEMV_PIPES_F32T
+#define SB_GEMV_PIPES_F32T 2
+#endif
+#ifndef SB_GEMV_STAGES_F32T
+#define SB_GEMV_STAGES_F32T SB_GEMV_STAGES
+#endif
 constexpr bool is_dec_epi(int epi) { return epi == SB_EPI_F32T || epi == SB_EPI_F32T_SWIGLU; }
-constexpr int gemm_pipes(int epi) { return is_dec_epi(epi) ? SB_GEMV_PIPES : 1; }
+constexpr int gemm_pipes(int epi) { return epi == SB_EPI_F32T ? SB_GEMV_PIPES_F32T : (epi == SB_EPI_F32T_SWIGLU ? SB_GEMV_PIPES : 1); }
 // warps: 0 producer, 1 MMA issuer (+ TMEM allocator), 2-5 epilogue, then one (producer, MMA) warp pair per extra pipeline
 constexpr int gemm_threads(int epi) { return GEMM_THREADS + 64 * (gemm_pipes(epi) - 1); }
 
@@ -73,24 +82,25 @@ SB_DEVICE void l2_prefetch_bulk(const void* ptr, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
 }
 
-template <int BN>
+template <int BN, int EPI>
 struct Cfg {
+  static constexpr int NP = gemm_pipes(EPI);
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int NSTAGES_RAW = (196 * 1024) / STAGE_BYTES;
-  // the narrow decode tiles (BN <= 32) are latency-bound: throughput per CTA = bytes in flight / slot round trip
-  // (tools/labs/ingest_mma_lab.cu), so they take every stage that fits; the wide tiles are MMA-bound at 4-8 stages
-  static constexpr int NSTAGES_CAP = BN <= 32 ? SB_GEMV_STAGES : 8;
+  // gate/up exchange of the fused decode SwiGLU epilogue (the only epilogue with shared-memory scratch)
+  static constexpr int XBUF_BYTES = EPI == SB_EPI_F32T_SWIGLU ? 128 * 33 * 4 + 256 : 0;
+  static constexpr int FIXED_BYTES = 1024 /*align*/ + 256 /*barriers*/ + XBUF_BYTES;
+  // the narrow decode tiles (BN <= 32) take the stages that fit next to the fixed part (227 KB per CTA), up to
+  // SB_GEMV_STAGES(_F32T), rounded to a whole number of stages per pipeline; the wide tiles are MMA-bound at 4-8 stages
+  static constexpr int NSTAGES_RAW = BN <= 32 ? (227 * 1024 - FIXED_BYTES) / STAGE_BYTES : (196 * 1024) / STAGE_BYTES;
+  static constexpr int NSTAGES_CAP = BN <= 32 ? (EPI == SB_EPI_F32T ? SB_GEMV_STAGES_F32T : SB_GEMV_STAGES) : 8;
   static constexpr int NSTAGES_FIT = NSTAGES_RAW > NSTAGES_CAP ? NSTAGES_CAP : NSTAGES_RAW;
-  // decode tiles: a whole number of stages per pipeline
-  static constexpr int NSTAGES = BN <= 32 ? (NSTAGES_FIT / SB_GEMV_PIPES) * SB_GEMV_PIPES : NSTAGES_FIT;
-  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-  // decode tiles: 2 accumulators (epilogue overlap) x SB_GEMV_PIPES pipelines x BN columns, a power of two >= 32
-  static constexpr int TMEM_COLS_DEC = (2 * SB_GEMV_PIPES * BN <= 32) ? 32 : (2 * SB_GEMV_PIPES * BN <= 64) ? 64 :
-                                       (2 * SB_GEMV_PIPES * BN <= 128) ? 128 : 256;
-  // gate/up exchange of the fused decode SwiGLU epilogue
-  static constexpr int XBUF_BYTES = 128 * 33 * 4 + 256;
-  static constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + XBUF_BYTES;
+  static constexpr int NSTAGES = (NSTAGES_FIT / NP) * NP;
+  // 2 accumulators (epilogue overlap) x NP pipelines x BN columns, a power of two >= 32
+  static constexpr int TMEM_COLS = (2 * NP * BN <= 32) ? 32 : (2 * NP * BN <= 64) ? 64 : (2 * NP * BN <= 128) ? 128 :
+                                   (2 * NP * BN <= 256) ? 256 : 512;
+  static constexpr int SMEM_BYTES = NSTAGES * STAGE_BYTES + FIXED_BYTES;
+  static_assert(NSTAGES >= NP && SMEM_BYTES <= 227 * 1024, "stage ring does not fit");
 };
 
 SB_DEVICE float quick_gelu(float x) { return x / (1.f + __expf(-1.702f * x)); }
@@ -137,15 +147,15 @@ template <bool A_MN, bool B_MN, int BN, int EPI>
 __global__ void __launch_bounds__(gemm_threads(EPI), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const GemmParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, EPI>;
   constexpr int NSTAGES = C::NSTAGES;
-  constexpr int NP = gemm_pipes(EPI);            // producer / MMA-issuer pairs (pipelines) in this CTA
+  constexpr int NP = C::NP;                      // producer / MMA-issuer pairs (pipelines) in this CTA
   static_assert(NSTAGES % NP == 0, "the stage ring is split evenly between the pipelines");
   constexpr int NSUB = NSTAGES / NP;             // stages per pipeline: pipeline pl owns stages pl, pl + NP, ...
   // the swap-AB weight-streaming GEMVs of the decode step (PDL launch, early weight ring, L2 prefetch of the next matrix)
   constexpr bool kDec = is_dec_epi(EPI);
   constexpr int ACC_COLS = BN;                              // TMEM columns of one accumulator
-  constexpr int TMEM_COLS = NP > 1 ? C::TMEM_COLS_DEC : C::TMEM_COLS;
+  constexpr int TMEM_COLS = C::TMEM_COLS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -576,7 +586,7 @@ int num_sms() {
 
 template <bool A_MN, bool B_MN, int BN, int EPI>
 int launch(const sb_gemm_args* a, cudaStream_t stream) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, EPI>;
   auto kfn = gemm_kernel<A_MN, B_MN, BN, EPI>;
   static bool attr_done = false;
   if (!attr_done) {
