@@ -19,6 +19,7 @@
 #include "spacer_b200.h"
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <cstdlib>
 #include <cstring>
 
 namespace {
@@ -75,6 +76,7 @@ struct GemmParams {
   long long prefetch_bytes;
   const uint8_t* prefetch2;      // second range (the matrix after next)
   long long prefetch2_bytes;
+  int a_3d, b_3d;                // MN-major operand described by ONE 3-D tensor map (all 64-wide chunks of a stage in one TMA)
 };
 
 // 16 KB per instruction: cp.async.bulk.prefetch.L2 only warms L2, nothing is written to shared memory
@@ -243,6 +245,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             mbar_expect_tx(fb, C::STAGE_BYTES);
             if (!A_MN) {
               tma_load_2d(sa, &tmA, fb, kb * BK, mt * BM);
+            } else if (p.a_3d) {     // [BM/64] chunk tiles of [BK][64] in one instruction
+              tma_load_3d(sa, &tmA, fb, 0, kb * BK, mt * (BM / 64));
             } else {
 #pragma unroll
               for (int j = 0; j < BM / 64; ++j)
@@ -251,6 +255,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           if (!B_MN) {
             tma_load_2d(sb, &tmB, fb, kb * BK, nt * BN);
+          } else if (p.b_3d) {
+            tma_load_3d(sb, &tmB, fb, 0, kb * BK, nt * (BN / 64));
           } else {
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j)
@@ -573,6 +579,25 @@ int make_tmap(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, u
   return 0;
 }
 
+// 3-D bf16 tensor map over an MN-major operand stored [k_rows][ld] with `mn` (a multiple of 64) contiguous elements per
+// row: dims (64 within a chunk, k, chunk) so that ONE box [64][box_k][box_chunks] lands in shared memory as box_chunks
+// consecutive 128B-swizzled [box_k][64] tiles -- the layout the UMMA MN-major descriptor walks (LBO = 8192).  The 2-D form
+// needs one TMA per 64-wide chunk (6 issues per stage for the weight-gradient GEMMs, which made their single producer
+// thread the bottleneck: 73 % tensor pipe against 82-86 % for the K-major forward GEMMs).  Returns 1 (no error set) when
+// the driver rejects the descriptor; the caller then falls back to the 2-D form.
+int make_tmap_mn3(CUtensorMap* m, const void* ptr, uint64_t mn, uint64_t k_rows, uint64_t ld, uint32_t box_k,
+                  uint32_t box_chunks) {
+  if (get_encode()) return 1;
+  cuuint64_t dims[3] = {64, k_rows, mn / 64};
+  cuuint64_t strides[2] = {ld * 2, 128};
+  cuuint32_t box[3] = {64, box_k, box_chunks};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 1;
+}
+
 int g_num_sms = 0;
 int num_sms() {
   if (g_num_sms == 0) {
@@ -594,17 +619,21 @@ int launch(const sb_gemm_args* a, cudaStream_t stream) {
     attr_done = true;
   }
   CUtensorMap tmA, tmB;
+  GemmParams p;
+  p.a_3d = p.b_3d = 0;
+  static const bool mn3 = getenv("SB_GEMM_NO_TMA3D") == nullptr;
   if (!A_MN) {
     if (make_tmap(&tmA, a->A, a->K, a->M, a->lda, BK, BM)) return 1;
   } else {
-    if (make_tmap(&tmA, a->A, a->M, a->K, a->lda, 64, BK)) return 1;
+    if (mn3 && a->M % 64 == 0 && make_tmap_mn3(&tmA, a->A, a->M, a->K, a->lda, BK, BM / 64) == 0) p.a_3d = 1;
+    else if (make_tmap(&tmA, a->A, a->M, a->K, a->lda, 64, BK)) return 1;
   }
   if (!B_MN) {
     if (make_tmap(&tmB, a->B, a->K, a->N, a->ldb, BK, BN)) return 1;
   } else {
-    if (make_tmap(&tmB, a->B, a->N, a->K, a->ldb, 64, BK)) return 1;
+    if (mn3 && BN >= 64 && a->N % 64 == 0 && make_tmap_mn3(&tmB, a->B, a->N, a->K, a->ldb, BK, BN / 64) == 0) p.b_3d = 1;
+    else if (make_tmap(&tmB, a->B, a->N, a->K, a->ldb, 64, BK)) return 1;
   }
-  GemmParams p;
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.m_tiles = (a->M + BM - 1) / BM;
   p.n_tiles = (a->N + BN - 1) / BN;
