@@ -248,3 +248,62 @@ def test_processor_to_generate_end_to_end(tmp_path_factory):
     completions = proc.batch_decode(out[:, P:], skip_special_tokens=True)
     assert len(completions) == G and all(isinstance(c, str) for c in completions)
     assert all("<|im_end|>" not in c and "<|endoftext|>" not in c for c in completions)
+
+
+def test_from_pretrained_with_the_reference_kwargs_and_generation_config(tmp_path):
+    """TRN:163-190: `from_pretrained(model_id, attn_implementation=..., torch_dtype=..., use_cache=...)` on a local HF
+    directory; generation_config.json supplies the eos list and the evaluation defaults; wrong class / dtype / kwargs raise."""
+    import json
+    from spacer_b200.hf_api import Qwen2_5_VLForConditionalGenerationB200, Qwen2VLForConditionalGenerationB200
+    from spacer_b200.ops import SpacerError
+    R, d_or, d, model, wb, case = _setup()
+    path = str(tmp_path / "Qwen2-VL-tiny")
+    model.engine.generation_config = dict(do_sample=True, repetition_penalty=1.05, temperature=0.1, top_k=1, top_p=0.001,
+                                          eos_token_id=[d.eos_id, d.pad_id], pad_token_id=d.pad_id)
+    model.save_pretrained(path)
+    assert json.load(open(os.path.join(path, "generation_config.json")))["eos_token_id"] == [d.eos_id, d.pad_id]
+    m2 = Qwen2VLForConditionalGenerationB200.from_pretrained(path, attn_implementation="flash_attention_2",
+                                                             torch_dtype=torch.bfloat16, use_cache=False)
+    assert m2.config._name_or_path == path and isinstance(m2.warnings_issued, dict)
+    assert m2.engine.dims.eos_ids == (d.eos_id, d.pad_id) and m2.generation_config.repetition_penalty == 1.05
+    sd, sd2 = model.state_dict(), m2.state_dict()
+    assert set(sd) == set(sd2) and all(torch.equal(sd[k], sd2[k]) for k in sd)
+    assert sum(p.numel() for p in m2.parameters()) == model.engine.params.sizes["mat"] + model.engine.params.sizes["vec"]
+    ids = case["input_ids"].cuda()
+    G = ids.shape[0]
+    kw = dict(pixel_values_videos=case["pixel_values"].cuda().repeat(G, 1), video_grid_thw=case["grid_thw"].repeat(G, 1))
+    with torch.no_grad():
+        assert torch.equal(model.per_token_logps(ids, **kw), m2.per_token_logps(ids, **kw))
+    with pytest.raises(SpacerError):
+        Qwen2_5_VLForConditionalGenerationB200.from_pretrained(path)                       # a qwen2_vl checkpoint
+    with pytest.raises(SpacerError):
+        Qwen2VLForConditionalGenerationB200.from_pretrained(path, torch_dtype=torch.float16)
+    with pytest.raises(TypeError):
+        Qwen2VLForConditionalGenerationB200.from_pretrained(path, load_in_8bit=True)
+
+
+def test_qwen25_wrapper_scores_like_the_engine():
+    """The class run_SpaceR_SG_RLVR.sh actually trains (Qwen2.5-VL): wrapper scoring == engine scoring, second_per_grid_ts is
+    accepted by generate() and ignored by the scoring call like the reference's `del` (TRN:519-520)."""
+    from oracle import qwen25vl_ref as R25
+    from oracle.make_golden import tiny_case25
+    from spacer_b200 import config
+    from spacer_b200.hf_api import Qwen2_5_VLForConditionalGenerationB200
+    from spacer_b200.model import pack_prompt_completions
+    d_or, d = R25.dims25_tiny(), config.tiny25()
+    model = Qwen2_5_VLForConditionalGenerationB200.from_dims(d, "cuda")
+    model.load_state_dict(R25.init_weights(d_or, seed=0))
+    case = tiny_case25(d_or)
+    ids = case["input_ids"].cuda()
+    G, P = ids.shape[0], case["prompt_ids"].shape[1]
+    pix = case["pixel_values"].cuda()
+    kw = dict(pixel_values_videos=pix.repeat(G, 1), video_grid_thw=case["grid_thw"].repeat(G, 1))
+    with torch.no_grad():
+        lp = model.per_token_logps(ids, second_per_grid_ts=[1.5] * G, **kw)[:, P - 1:]
+        batch = pack_prompt_completions(case["prompt_ids"], case["completion_ids"], case["grid_thw"], d, model.engine.device)
+        want = model.engine.per_token_logps(batch, pix, case["grid_thw"])
+    assert torch.equal(lp, want)
+    out = model.generate(input_ids=case["prompt_ids"].cuda(), attention_mask=torch.ones_like(case["prompt_ids"]).cuda(),
+                         pixel_values_videos=pix, video_grid_thw=case["grid_thw"], second_per_grid_ts=[1.5],
+                         max_new_tokens=5, do_sample=False)
+    assert out.shape == (1, P + 5) or (out.shape[0] == 1 and out.shape[1] <= P + 5)
