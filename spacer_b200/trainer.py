@@ -312,13 +312,13 @@ class SGRLVRTrainerB200:
     def compute_rewards(self, completions_text, example, G):
         prompts = [example.get("prompt")] * G
         completions = [[{"role": "assistant", "content": s}] for s in completions_text]
-        per_func = torch.zeros(G, len(self.reward_funcs), device=self.model.device)
+        per_func = torch.zeros(G, len(self.reward_funcs))
         extra = {k: [example[k]] * G for k in example
                  if k not in ("prompt", "completion", "input_ids", "pixel_values_videos", "video_grid_thw", "path",
                               "video_frames")}
         for i, fn in enumerate(self.reward_funcs):
             out = fn(prompts=prompts, completions=completions, path=[example.get("path", "")] * G, **extra)  # TRN:592
-            per_func[:, i] = torch.tensor([float(x) for x in out], device=self.model.device)
+            per_func[:, i] = torch.tensor([float(x) for x in out])
         return per_func
 
     def rollout_seed(self) -> int:
@@ -343,21 +343,26 @@ class SGRLVRTrainerB200:
         mark("rollout")
         P = prompt_ids.reshape(-1).numel()
         completion_ids = main[:, P:]
+        # the sampled ids go to the host NOW (the GPU is idle after the rollout anyway): everything the CPU does with them
+        # -- decoding, reward functions, bonuses, advantages -- then runs while the GPU works on the reference scoring,
+        # instead of stalling behind it and leaving the GPU idle before the policy forward
+        comp_host = completion_ids.cpu()
+        shuf_host = shuf[:, P:].cpu() if shuf is not None else None
         pix, grid = example["pixel_values_videos"], example["video_grid_thw"]
-        batch = pack_prompt_completions(prompt_ids, completion_ids, grid, m.dims, m.device, m.rope_convention)
-        # reference-policy log-probs (TRN:534-547); beta = 0 skips it
+        batch = pack_prompt_completions(prompt_ids, comp_host, grid, m.dims, m.device, m.rope_convention)
+        # reference-policy log-probs (TRN:534-547); beta = 0 skips it.  Enqueued, not waited for.
         ref_lp = None
         if self.ref_model is not None and c.beta != 0.0:
             ref_lp = self.ref_model.per_token_logps(batch, pix, grid)
-        mark("ref_scoring")
-        # rewards on decoded text (TRN:555-593)
-        rewards_per_func = self.compute_rewards(self.decode_completions(completion_ids), example, G)
+        # rewards on decoded text (TRN:555-593), on the host
+        rewards_per_func = self.compute_rewards(self.decode_completions(comp_host), example, G)
         shuf_rpf = None
-        if c.temporal and shuf is not None:
-            shuf_rpf = self.compute_rewards(self.decode_completions(shuf[:, P:]), example, G // 2)
+        if c.temporal and shuf_host is not None:
+            shuf_rpf = self.compute_rewards(self.decode_completions(shuf_host), example, G // 2)
         # completion lengths are needed for the length bonus before the loss kernel runs (TRN:489-494, 620-629)
-        lengths = completion_lengths(completion_ids, m.dims.eos_id)
+        lengths = completion_lengths(comp_host, m.dims.eos_id)
         rewards, adv, std, temporal_rewards = reward_tail(rewards_per_func, shuf_rpf, lengths, G, c.temporal, c.len_control)
+        mark("ref_scoring")
         mark("rewards")
         if self.reducer is not None:
             self.reducer.begin_step()
@@ -374,14 +379,15 @@ class SGRLVRTrainerB200:
         mark("adamw")
         self.global_step += 1
         # metrics (TRN:650-683): the reference gathers nine quantities one by one; here one packed vector per rank
-        allp = self._gather(pack_step_stats(lengths, rewards_per_func, rewards, std, out["mean_kl"], temporal_rewards))
+        allp = self._gather(pack_step_stats(lengths.to(m.device), rewards_per_func.to(m.device), rewards.to(m.device),
+                                            std.to(m.device), out["mean_kl"], temporal_rewards))
         mt = step_metrics(allp, G, [fn.__name__ for fn in self.reward_funcs], c.temporal)
         mt["loss"] = out["loss"].item()
         mt["learning_rate"] = lr
         for k, v in mt.items():
             self._metrics[k].append(v)
         self.last_phase_ms = {marks[i][0]: marks[i - 1][1].elapsed_time(marks[i][1]) for i in range(1, len(marks))}
-        mt["generated_tokens"] = int(completion_ids.numel() + (shuf[:, P:].numel() if shuf is not None else 0))
+        mt["generated_tokens"] = int(comp_host.numel() + (shuf_host.numel() if shuf_host is not None else 0))
         return mt
 
     def log(self):
