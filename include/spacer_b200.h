@@ -27,7 +27,7 @@ extern "C" {
 
 typedef struct CUstream_st* sb_stream_t;
 
-#define SB_ABI_VERSION 3
+#define SB_ABI_VERSION 4
 
 const char* sb_last_error(void);
 int sb_abi_version(void);
@@ -39,10 +39,17 @@ int sb_launch_counter(long long* count_host, int reset);
 /* decode-step kernels are launched with programmatic dependent launch (next kernel's prologue and weight prefetch
  * overlap the current kernel's tail); 0 turns it off (debugging / A-B timing).  Default on unless SB_NO_PDL is set. */
 int sb_set_pdl(int enable);
+/* decode GEMVs tag their weight stream evict_first (createpolicy cache hint): a weight is read once per step, so it
+ * should not push out what is reused (activations, split-K partials, KV, lines prefetched by sb_dec_l2_prefetch);
+ * 0 turns the hint off (A-B timing).  Default on unless SB_NO_L2_HINTS is set. */
+int sb_set_dec_l2_hints(int enable);
 /* profiling aid: with a device buffer of 1 + 4*capacity uint64 installed (buf[0] = 0), every decode-step kernel
  * appends {kind, t_entry, t_ready (dependencies satisfied), t_end} of its block 0 in globaltimer ns; buf[0] counts
  * records.  (NULL, 0) disables.  Not for production runs. */
 int sb_trace_enable(unsigned long long* buf_dev, int capacity);
+/* profiling aid: per-CTA timeline of the decode GEMVs.  buf: n_sms lists of 1 + 3*capacity_per_cta uint64, zeroed; CTA b
+ * appends {M ^ (K << 32), t_ready, t_end} to list b (element 0 = count).  (NULL, 0) disables. */
+int sb_trace_enable_gemv_ctas(unsigned long long* buf_dev, int capacity_per_cta);
 
 /* ------------------------------------------------------------------------------------------------
  * GEMM  D[M,N] = epi(A[M,K] * B[N,K]^T)   (tcgen05 + TMEM + TMA)
@@ -78,10 +85,6 @@ typedef struct sb_gemm_args {
   float* tgt_logit;                       /* [M] LMHEAD out                                         */
   const float* lse;                       /* [M] DLOGITS in                                         */
   const float* coef;                      /* [M] DLOGITS in: dLoss/dlogprob                         */
-  const void* prefetch;                   /* F32T only, optional: device bytes to warm into L2 after this   */
-  long long prefetch_bytes;               /*   kernel's own loads (the NEXT weight matrix of the decode step) */
-  const void* prefetch2;                  /* second L2-prefetch range (the matrix after next), 16-byte aligned */
-  long long prefetch2_bytes;
 } sb_gemm_args;
 
 int sb_gemm(const sb_gemm_args* args, sb_stream_t stream);
@@ -219,6 +222,16 @@ int sb_dec_attn(const void* q, const void* kp0, const void* vp0, const void* kp1
                 long long workspace_floats, void* out, int R, sb_stream_t stream);
 int sb_dec_swiglu(const float* parts, int S, long long stride_s, long long stride_r, void* act, int R, int I,
                   sb_stream_t stream);
+/* asks L2 (cp.async.bulk.prefetch.L2, evict_last) for weights a later GEMV of the decode step will stream: `chunks` runs of
+ * chunk_bytes each, stride_bytes apart (chunks <= 1: one run) -- e.g. the first rows of every 128-row tile of gate|up.
+ * A bulk prefetch holds its issuing CTA until the memory system has taken it, so this is its own small kernel, meant for
+ * a side stream / parallel graph branch: nothing on the layer's dependency chain waits for it.  ctas (0 = one per SM)
+ * bounds the request rate: every issuing SM adds ~0.15 TB/s, and a request stream faster than HBM drains fills the
+ * memory system's queues, which the latency-bound small kernels of the layer then wait behind.
+ * pace_ns >= 0 selects the load/store-path form instead: one prefetch.global.L2::evict_last per 128-byte line from
+ * `ctas` CTAs of 128 threads, each thread sleeping pace_ns between two requests (no TMA queue involved). */
+int sb_dec_l2_prefetch(const void* base, long long chunk_bytes, long long stride_bytes, int chunks, int ctas, int pace_ns,
+                       sb_stream_t stream);
 /* top-p sampling of one token per row from fp32 logits [R][ld]; TopPLogitsWarper + multinomial semantics
  * (logits_process.py:521-533, generation/utils.py:2789-2797).  out_ids[r][*step_ptr] = token (optional).
  * seed_dev (optional device scalar) overrides `seed`, so that a captured CUDA graph can be replayed with new seeds */

@@ -27,8 +27,6 @@ class GemmArgs(C.Structure):
         ("aux", C.c_void_p), ("ldaux", C.c_longlong),
         ("targets", C.c_void_p), ("lse_part", C.c_void_p), ("tgt_logit", C.c_void_p),
         ("lse", C.c_void_p), ("coef", C.c_void_p),
-        ("prefetch", C.c_void_p), ("prefetch_bytes", C.c_longlong),
-        ("prefetch2", C.c_void_p), ("prefetch2_bytes", C.c_longlong),
     ]
 
 

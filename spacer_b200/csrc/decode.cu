@@ -25,16 +25,19 @@ __global__ void dec_embed_kernel(const int* __restrict__ tokens, const bf16* __r
 }
 
 // x[r] += bf16(sum_s parts[s][r][:]) (if parts);  xn[r] = w * bf16(x * rstd)
-// one CTA of 1024 threads per row, 4 consecutive elements per thread per pass (float4 partial loads)
-constexpr int RN_THREADS = 1024;
-__global__ void __launch_bounds__(RN_THREADS)
+// one CTA of 512 threads per row, 4 consecutive elements per thread per pass (float4 partial loads).  512 threads x <= 64
+// registers leave half of the SM's register file free: a CTA of 1024 threads took all of it, so the 12 SMs that ran this
+// kernel could not host the next GEMV's CTA early (PDL) -- those CTAs missed the pre-wait weight prefetch, became ready
+// 0.5-0.8 us after the others and were the last to finish (tools/decode_lab.py --exp skew).
+constexpr int RN_THREADS = 512;
+__global__ void __launch_bounds__(RN_THREADS, 2)
 dec_residual_rmsnorm_kernel(bf16* __restrict__ x, const float* __restrict__ parts, int S, long long part_stride_s,
                             long long part_stride_r, const bf16* __restrict__ w, bf16* __restrict__ xn, int H,
                             float eps) {
   pdl_launch_dependents();
   const bool tr_on = blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
   const int tr = tr_on ? sb_trace_begin(SB_TR_RMSNORM) : -1;
-  constexpr int MAXV = 4;                      // up to 4 passes of 4096 elements (H <= 16384)
+  constexpr int MAXV = 4;                      // up to 4 passes of 2048 elements (H <= 8192)
   constexpr int MAXS = 8;                      // split-K partials gathered in one round trip (more: extra rounds)
   // the norm weight does not depend on the preceding kernels: fetch it before the dependency wait
   uint2 wreg[MAXV];
@@ -187,6 +190,38 @@ __global__ void dec_swiglu_kernel(const float* __restrict__ parts, int S, long l
   sb_trace_mark(tr, 2);
 }
 
+// L2 prefetch of weights a later GEMV will stream (see sb_dec_l2_prefetch in the header): one warp per CTA, 8 KB per
+// instruction, evict_last so that the weight streams passing through L2 in between (tagged evict_first) do not push
+// the lines out before they are read.  tools/labs/l2_hint_lab.cu measures what that buys.
+__global__ void __launch_bounds__(32)
+dec_l2_prefetch_kernel(const uint8_t* __restrict__ base, long long chunk_bytes, long long stride_bytes, int chunks) {
+  constexpr long long PIECE = 8192;
+  const uint64_t pol = l2_policy_evict_last();
+  const long long per = (chunk_bytes + PIECE - 1) / PIECE, n = per * chunks;
+  for (long long c = (long long)blockIdx.x * 32 + threadIdx.x; c < n; c += (long long)gridDim.x * 32) {
+    const long long off = (c % per) * PIECE;
+    const long long len = min(PIECE, chunk_bytes - off) & ~15LL;
+    if (len > 0)
+      asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(base + (c / per) * stride_bytes + off),
+                   "r"((uint32_t)len), "l"(pol) : "memory");
+  }
+}
+
+// the same request through the load/store path: one prefetch.global.L2::evict_last per 128-byte line, paced with
+// nanosleep.  Unlike the bulk form it does not queue in the SM's TMA unit -- where a backlog of bulk prefetches holds up the
+// weight-ring requests of the GEMV CTA that shares the SM -- and its rate can be set below what HBM drains, so that the
+// latency-bound small kernels of the layer do not wait behind a saturated memory system.
+__global__ void __launch_bounds__(128)
+dec_l2_prefetch_lsu_kernel(const uint8_t* __restrict__ base, long long chunk_bytes, long long stride_bytes, int chunks,
+                           int sleep_ns) {
+  const long long per = chunk_bytes / 128, n = per * chunks;
+  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
+    const uint8_t* ptr = base + (c / per) * stride_bytes + (c % per) * 128;
+    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(ptr) : "memory");
+    if (sleep_ns > 0) __nanosleep(sleep_ns);
+  }
+}
+
 }  // namespace
 
 SB_DEFINE_TRACE_SETTER(sb_trace_set_decode)
@@ -203,8 +238,8 @@ extern "C" int sb_dec_embed(const int* tokens, const void* embed, void* x, int R
 
 extern "C" int sb_dec_residual_rmsnorm(void* x, const float* parts, int S, long long stride_s, long long stride_r,
                                        const void* w, void* xn, int R, int H, float eps, sb_stream_t stream) {
-  SB_REQUIRE(x && R > 0 && H > 0 && H % 4 == 0 && H <= 16384 && (xn == nullptr || w != nullptr),
-             "sb_dec_residual_rmsnorm: bad arguments (H must be a multiple of 4, <= 16384)");
+  SB_REQUIRE(x && R > 0 && H > 0 && H % 4 == 0 && H <= 8192 && (xn == nullptr || w != nullptr),
+             "sb_dec_residual_rmsnorm: bad arguments (H must be a multiple of 4, <= 8192)");
   SB_REQUIRE(parts == nullptr || (stride_s % 4 == 0 && stride_r % 4 == 0), "sb_dec_residual_rmsnorm: partial strides must be multiples of 4");
   SB_CUDA(sb_launch(dec_residual_rmsnorm_kernel, dim3(R), dim3(RN_THREADS), 0, STREAM(stream), sb_pdl_enabled(), (bf16*)x,
                     parts, S, stride_s, stride_r, (const bf16*)w, (bf16*)xn, H, eps));
@@ -229,4 +264,24 @@ extern "C" int sb_dec_swiglu(const float* parts, int S, long long stride_s, long
   SB_CUDA(sb_launch(dec_swiglu_kernel, dim3((I + 255) / 256, R), dim3(256), 0, STREAM(stream), sb_pdl_enabled(), parts, S,
                     stride_s, stride_r, (bf16*)act, I));
   return sb_check_launch("sb_dec_swiglu");
+}
+
+extern "C" int sb_dec_l2_prefetch(const void* base, long long chunk_bytes, long long stride_bytes, int chunks, int ctas,
+                                  int pace_ns, sb_stream_t stream) {
+  SB_REQUIRE(base && (reinterpret_cast<uintptr_t>(base) & 15) == 0 && chunk_bytes > 0 && chunks >= 1 &&
+                 (chunks == 1 || (stride_bytes >= chunk_bytes && stride_bytes % 16 == 0)),
+             "sb_dec_l2_prefetch: bad arguments (16-byte aligned base, chunk_bytes > 0, stride >= chunk)");
+  int dev = 0, sms = 0;
+  SB_CUDA(cudaGetDevice(&dev));
+  SB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (sms <= 0) sms = 148;
+  if (pace_ns >= 0) {
+    SB_REQUIRE(chunk_bytes % 128 == 0, "sb_dec_l2_prefetch: chunk_bytes must be a multiple of 128 for the paced form");
+    SB_CUDA(sb_launch(dec_l2_prefetch_lsu_kernel, dim3(ctas > 0 ? ctas : sms), dim3(128), 0, STREAM(stream), false,
+                      (const uint8_t*)base, chunk_bytes, stride_bytes, chunks, pace_ns));
+    return sb_check_launch("sb_dec_l2_prefetch");
+  }
+  SB_CUDA(sb_launch(dec_l2_prefetch_kernel, dim3(ctas > 0 && ctas < sms ? ctas : sms), dim3(32), 0, STREAM(stream), false,
+                    (const uint8_t*)base, chunk_bytes, stride_bytes, chunks));
+  return sb_check_launch("sb_dec_l2_prefetch");
 }

@@ -72,17 +72,15 @@ struct GemmParams {
   float* tgt_logit;
   const float* lse;
   const float* coef;
-  const uint8_t* prefetch;       // optional: bytes to pull into L2 once this kernel's own loads are issued
-  long long prefetch_bytes;
-  const uint8_t* prefetch2;      // second range (the matrix after next)
-  long long prefetch2_bytes;
+  int l2_hints;                  // decode GEMVs: the weight stream is tagged evict_first (sb_set_dec_l2_hints)
   int a_3d, b_3d;                // MN-major operand described by ONE 3-D tensor map (all 64-wide chunks of a stage in one TMA)
 };
 
-// 16 KB per instruction: cp.async.bulk.prefetch.L2 only warms L2, nothing is written to shared memory
-SB_DEVICE void l2_prefetch_bulk(const void* ptr, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
-}
+// per-CTA timeline of the decode GEMVs (sb_trace_enable_gemv_ctas): CTA b appends {M ^ (K << 32), t_ready, t_end} to its
+// own list buf[b * (1 + 3 * cap)] (element 0 = count).  Shows the spread of the CTAs' finishing times (the kernel-level
+// trace only sees block 0).
+static __device__ unsigned long long* sb_gemv_cta_trace = nullptr;
+static __device__ int sb_gemv_cta_cap = 0;
 
 template <int BN, int EPI>
 struct Cfg {
@@ -154,7 +152,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   constexpr int NP = C::NP;                      // producer / MMA-issuer pairs (pipelines) in this CTA
   static_assert(NSTAGES % NP == 0, "the stage ring is split evenly between the pipelines");
   constexpr int NSUB = NSTAGES / NP;             // stages per pipeline: pipeline pl owns stages pl, pl + NP, ...
-  // the swap-AB weight-streaming GEMVs of the decode step (PDL launch, early weight ring, L2 prefetch of the next matrix)
+  // the swap-AB weight-streaming GEMVs of the decode step (PDL launch, early weight ring, evict_first weight stream)
   constexpr bool kDec = is_dec_epi(EPI);
   constexpr int ACC_COLS = BN;                              // TMEM columns of one accumulator
   constexpr int TMEM_COLS = C::TMEM_COLS;
@@ -168,6 +166,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t tempty0 = smem_u32(bars + 2 * NSTAGES + 2);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGES + 4);
   float* xbuf = reinterpret_cast<float*>(smem + NSTAGES * C::STAGE_BYTES + 256);
+  unsigned long long* xtime = reinterpret_cast<unsigned long long*>(tmem_slot + 2);   // t_ready of the per-CTA trace
   const uint32_t smem_base = smem_u32(smem);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -209,7 +208,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // the small kernel that produces the activations (B operand) is still running.
       int pre = 0;
       int tr = -1;
+      uint64_t pol_stream = 0;
       if constexpr (kDec) {
+        if (p.l2_hints) pol_stream = l2_policy_evict_first();
         if (blockIdx.x == 0 && pl == 0) { tr = sb_trace_begin(SB_TR_GEMV); *reinterpret_cast<volatile int*>(tmem_slot + 1) = tr; }
         for (int t = t_begin; t < total_tiles && pre < NSUB; t += t_step) {
           const int mt = t % p.m_tiles;
@@ -220,12 +221,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int st = pl + NP * pre;
             const uint32_t fb = full0 + 8 * st;
             mbar_expect_tx(fb, C::STAGE_BYTES);
-            tma_load_2d(smem_base + st * C::STAGE_BYTES, &tmA, fb, kb * BK, mt * BM);
+            if (p.l2_hints) tma_load_2d_hint(smem_base + st * C::STAGE_BYTES, &tmA, fb, kb * BK, mt * BM, pol_stream);
+            else tma_load_2d(smem_base + st * C::STAGE_BYTES, &tmA, fb, kb * BK, mt * BM);
           }
         }
       }
       pdl_wait();
       sb_trace_mark(tr, 1);
+      if constexpr (kDec) {
+        if (pl == 0 && sb_gemv_cta_trace != nullptr) *reinterpret_cast<volatile unsigned long long*>(xtime) = sb_gtime();
+      }
       int si = 0;                 // position in this pipeline's sub-ring; stage = pl + NP * si
       uint32_t phase = 0;
       int issued = 0;
@@ -244,7 +249,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             mbar_wait(empty0 + 8 * stage, phase ^ 1);
             mbar_expect_tx(fb, C::STAGE_BYTES);
             if (!A_MN) {
-              tma_load_2d(sa, &tmA, fb, kb * BK, mt * BM);
+              if (kDec && p.l2_hints) tma_load_2d_hint(sa, &tmA, fb, kb * BK, mt * BM, pol_stream);
+              else tma_load_2d(sa, &tmA, fb, kb * BK, mt * BM);
             } else if (p.a_3d) {     // [BM/64] chunk tiles of [BK][64] in one instruction
               tma_load_3d(sa, &tmA, fb, 0, kb * BK, mt * (BM / 64));
             } else {
@@ -263,22 +269,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               tma_load_2d(sb + j * 8192, &tmB, fb, nt * BN + j * 64, kb * BK);
           }
           if (++si == NSUB) { si = 0; phase ^= 1; }
-        }
-      }
-      if (kDec && pl == 0) {
-        // Weight streaming never pauses: while the small kernels between two GEMVs run (HBM otherwise idle), the
-        // next weight matrix is already on its way into L2.  Each CTA prefetches its 1/gridDim slice.
-        constexpr long long CH = 16384;
-#pragma unroll 1
-        for (int which = 0; which < 2; ++which) {
-          const uint8_t* base = which ? p.prefetch2 : p.prefetch;
-          const long long bytes = which ? p.prefetch2_bytes : p.prefetch_bytes;
-          const long long n_ch = (bytes + CH - 1) / CH;
-          for (long long c = blockIdx.x; c < n_ch; c += gridDim.x) {
-            const long long off = c * CH;
-            const long long len = min(CH, bytes - off);
-            l2_prefetch_bulk(base + off, (uint32_t)(len & ~15LL));
-          }
         }
       }
     }
@@ -536,6 +526,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   if constexpr (kDec) {
     if (blockIdx.x == 0 && threadIdx.x == 0) sb_trace_mark(*reinterpret_cast<volatile int*>(tmem_slot + 1), 2);
+    if (threadIdx.x == 0 && sb_gemv_cta_trace != nullptr) {
+      unsigned long long* mine = sb_gemv_cta_trace + (long long)blockIdx.x * (1 + 3 * sb_gemv_cta_cap);
+      const unsigned long long k = mine[0];
+      if (k < (unsigned long long)sb_gemv_cta_cap) {
+        mine[1 + 3 * k] = (unsigned long long)p.M ^ ((unsigned long long)p.K << 32);
+        mine[2 + 3 * k] = *reinterpret_cast<volatile unsigned long long*>(xtime);
+        mine[3 + 3 * k] = sb_gtime();
+        mine[0] = k + 1;
+      }
+    }
   }
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
@@ -598,6 +598,9 @@ int make_tmap_mn3(CUtensorMap* m, const void* ptr, uint64_t mn, uint64_t k_rows,
   return r == CUDA_SUCCESS ? 0 : 1;
 }
 
+// decode GEMVs: L2 eviction-priority hints (sb_set_dec_l2_hints; SB_NO_L2_HINTS in the environment turns them off)
+int g_l2_hints = getenv("SB_NO_L2_HINTS") == nullptr ? 1 : 0;
+
 int g_num_sms = 0;
 int num_sms() {
   if (g_num_sms == 0) {
@@ -650,10 +653,7 @@ int launch(const sb_gemm_args* a, cudaStream_t stream) {
   p.lse_part = reinterpret_cast<float2*>(a->lse_part);
   p.tgt_logit = a->tgt_logit;
   p.lse = a->lse; p.coef = a->coef;
-  p.prefetch = reinterpret_cast<const uint8_t*>(a->prefetch);
-  p.prefetch_bytes = a->prefetch ? a->prefetch_bytes : 0;
-  p.prefetch2 = reinterpret_cast<const uint8_t*>(a->prefetch2);
-  p.prefetch2_bytes = a->prefetch2 ? a->prefetch2_bytes : 0;
+  p.l2_hints = g_l2_hints;
   const int total = p.m_tiles * p.n_tiles * p.k_splits;
   const int grid = total < num_sms() ? total : num_sms();
   const bool pdl = (EPI == SB_EPI_F32T || EPI == SB_EPI_F32T_SWIGLU) && sb_pdl_enabled();
@@ -668,6 +668,18 @@ int launch(const sb_gemm_args* a, cudaStream_t stream) {
 }  // namespace
 
 SB_DEFINE_TRACE_SETTER(sb_trace_set_gemm)
+
+extern "C" int sb_trace_enable_gemv_ctas(unsigned long long* buf_dev, int capacity_per_cta) {
+  SB_REQUIRE((buf_dev == nullptr) == (capacity_per_cta == 0), "sb_trace_enable_gemv_ctas: pass (NULL, 0) to disable");
+  SB_CUDA(cudaMemcpyToSymbol(sb_gemv_cta_trace, &buf_dev, sizeof(buf_dev)));
+  SB_CUDA(cudaMemcpyToSymbol(sb_gemv_cta_cap, &capacity_per_cta, sizeof(capacity_per_cta)));
+  return 0;
+}
+
+extern "C" int sb_set_dec_l2_hints(int enable) {
+  g_l2_hints = enable ? 1 : 0;
+  return 0;
+}
 
 extern "C" int sb_gemm_effective_splits(int K, int k_splits) {
   int k_iters = (K + BK - 1) / BK;
@@ -692,8 +704,6 @@ extern "C" int sb_gemm(const sb_gemm_args* a, sb_stream_t stream_) {
     SB_REQUIRE(!amn && !bmn, "sb_gemm: F32T epilogue needs K-major operands");
     SB_REQUIRE(a->N <= 32, "sb_gemm: F32T epilogue is for N<=32 (decode rows), got %d", a->N);
     SB_REQUIRE(a->ldd >= a->M, "sb_gemm: F32T ldd (%lld) < M (%d)", a->ldd, a->M);
-    SB_REQUIRE(a->prefetch == nullptr || ((reinterpret_cast<uintptr_t>(a->prefetch) & 15) == 0 && a->prefetch_bytes >= 0),
-               "sb_gemm: prefetch pointer must be 16-byte aligned");
     if (a->N <= 16) return launch<false, false, 16, SB_EPI_F32T>(a, stream);
     return launch<false, false, 32, SB_EPI_F32T>(a, stream);
   }
@@ -703,8 +713,6 @@ extern "C" int sb_gemm(const sb_gemm_args* a, sb_stream_t stream_) {
     SB_REQUIRE(a->M % 128 == 0, "sb_gemm: F32T_SWIGLU needs M %% 128 == 0 (interleaved gate/up rows), got %d", a->M);
     SB_REQUIRE(a->k_splits <= 1, "sb_gemm: F32T_SWIGLU cannot be split along K");
     SB_REQUIRE(a->ldd >= a->M / 2, "sb_gemm: F32T_SWIGLU ldd (%lld) < M/2 (%d)", a->ldd, a->M / 2);
-    SB_REQUIRE(a->prefetch == nullptr || (reinterpret_cast<uintptr_t>(a->prefetch) & 15) == 0,
-               "sb_gemm: prefetch pointer must be 16-byte aligned");
     if (a->N <= 16) return launch<false, false, 16, SB_EPI_F32T_SWIGLU>(a, stream);
     return launch<false, false, 32, SB_EPI_F32T_SWIGLU>(a, stream);
   }

@@ -1013,24 +1013,42 @@ class Qwen2VLB200:
         return dict(gbs=byts / (ms * 1e-3) / 1e9, bytes_per_launch=byts / launches, avg_us=ms * 1e3 / launches,
                     launches=launches, ms_per_sweep=ms)
 
-    # L2 prefetch plan of the decode step: behind its own loads every GEMV asks L2 for the head of the matrices that
-    # come next, sized to the HBM-idle window that follows it (the small kernels + dependency gaps, see
-    # profiles/r01_decode_trace.txt): after qkv comes the ~24 us attention window -> all of o_w plus the head of gate|up.
-    L2_PREFETCH_BYTES = 16 << 20          # default window after a GEMV (o, gate|up, down, lm_head)
-    L2_PREFETCH_ATTN_BYTES = 48 << 20     # head of gate|up requested behind the qkv GEMV
+    # L2 plan of the decode step (profiles/r02_l2_hint_lab.md).  Every weight stream of the decode GEMVs is tagged
+    # evict_first (a weight is read once per step).  During the attention window of a layer -- the longest stretch in which
+    # HBM would idle -- a small kernel on a side stream (a parallel branch of the step's CUDA graph, so that nothing on the
+    # layer's dependency chain waits for it) asks L2 for the first PF_GU_ROWS rows of EVERY 128-row tile of gate|up, tagged
+    # evict_last so that they survive the ~70 MB that pass through L2 before the gate|up GEMV reads them.  A row subset of
+    # every tile (instead of the head of the matrix) makes every TMA box of that GEMV part L2 hit, part HBM: all CTAs gain
+    # alike and HBM stays saturated beside the hits.  PF_AFTER names the kernel whose completion releases the requests.
+    # The requests go through the load/store path (one prefetch.global.L2::evict_last per line), paced so that they are
+    # spread over the window at ~3 TB/s: a burst -- or the bulk/TMA form -- saturates the memory system, and the
+    # latency-bound attention / norm kernels then wait behind it (tools/decode_lab.py --exp step: 2.96 ms per step without,
+    # 2.87 with; 3.1-3.3 when the requests come as a burst or overrun into the gate|up GEMV).
+    PF_GU_ROWS = 24
+    PF_AFTER = "qkv_post"      # "qkv" | "qkv_post" | "combine"
+    PF_CTAS = 0                # CTAs that issue the requests (0 = one per SM)
+    PF_PACE_NS = 750           # >= 0: per-line requests, each of the CTAs' 128 threads pausing this long; -1: bulk (TMA) form
 
-    def _gemv(self, w, x16, out_parts, splits, next_w=None, swiglu=False, next2_w=None, next_bytes=None, next2_bytes=0):
+    def _gemv(self, w, x16, out_parts, splits, swiglu=False):
         """parts[s][r][n] = x16[r] . w[n] over K split s   (swap-AB tcgen05 GEMM, weights streamed once).
-        next_w / next2_w: weight matrices the decode step reads next; their heads are prefetched into L2 behind this
-        GEMV.  swiglu: w is the interleaved gate|up matrix and out_parts the bf16 activation [rows, I] (fused epilogue)."""
-        cap = self.L2_PREFETCH_BYTES if next_bytes is None else next_bytes
-        nb = 0 if next_w is None else min(next_w.numel() * 2, cap)
-        nb2 = 0 if next2_w is None else min(next2_w.numel() * 2, next2_bytes)
-        kw = dict(prefetch=next_w if nb else None, prefetch_bytes=nb, prefetch2=next2_w if nb2 else None, prefetch2_bytes=nb2)
+        swiglu: w is the interleaved gate|up matrix and out_parts the bf16 activation [rows, I] (fused epilogue)."""
         if swiglu:
-            ops.gemm(w, x16, out=out_parts, epilogue=ops.EPI_F32T_SWIGLU, **kw)
+            ops.gemm(w, x16, out=out_parts, epilogue=ops.EPI_F32T_SWIGLU)
         else:
-            ops.gemm(w, x16, out=out_parts, epilogue=EPI_F32T, k_splits=splits, **kw)
+            ops.gemm(w, x16, out=out_parts, epilogue=EPI_F32T, k_splits=splits)
+
+    def _prefetch_tile_rows(self, st, w, rows):
+        """Fork: the side stream waits for what the main stream has enqueued so far, then requests the first `rows` rows of
+        every 128-row tile of `w`.  Joined once, at the end of the step."""
+        n_rows, k = w.shape
+        main = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        side = st["side"]
+        side.wait_event(ev)
+        with torch.cuda.stream(side):
+            ops.call("sb_dec_l2_prefetch", w, min(int(rows), 128) * k * 2, 128 * k * 2, n_rows // 128, int(self.PF_CTAS), int(self.PF_PACE_NS))
+        st["forked"] = True
 
     def _splits_for(self, n_out, k):
         m_tiles = (n_out + 127) // 128
@@ -1068,7 +1086,7 @@ class Qwen2VLB200:
             out_ids=torch.zeros((R, c_max), device=dev, dtype=I32),
             seed=torch.zeros(1, device=dev, dtype=torch.int64),
             seen=torch.zeros((RP, (d.vocab + 31) // 32), device=dev, dtype=I32),   # token bitmap (repetition penalty)
-            graphs={},
+            graphs={}, side=torch.cuda.Stream(device=dev), forked=False,
         )
         st["attn_ws"] = None      # sized on first use (depends on the group split)
         return st
@@ -1113,34 +1131,42 @@ class Qwen2VLB200:
         ws = self._attn_workspace(st, rows_group0)
         ops.call("sb_dec_embed", st["tokens"], W["embed"], st["x"], R, H)
         parts, sp = None, 0
+        pf_rows = int(self.PF_GU_ROWS)
+        st["forked"] = False
         for i in range(d.layers):
             p = f"l.{i}."
             ops.call("sb_dec_residual_rmsnorm", st["x"], parts, sp, RP * H, H, W[p + "ln1_w"], st["xn"], R, H, d.rms_eps)
-            self._gemv(W[p + "qkv_w"], st["xn"], st["p_qkv"], S["qkv"], next_w=W[p + "o_w"], next_bytes=1 << 30,
-                       next2_w=W[p + "gu_w"], next2_bytes=self.L2_PREFETCH_ATTN_BYTES)
+            self._gemv(W[p + "qkv_w"], st["xn"], st["p_qkv"], S["qkv"])
+            if pf_rows and self.PF_AFTER == "qkv":
+                self._prefetch_tile_rows(st, W[p + "gu_w"], pf_rows)
             ops.call("sb_dec_qkv_post", st["p_qkv"], S["qkv"], RP * d.qkv_dim, d.qkv_dim, W[p + "qkv_b"], st["step"],
                      rope_base, float(d.rope_theta), nh, nkv, hd, st["q"], st["kc"][i], st["vc"][i],
                      st["c_max"] * nkv * hd, st["c_max"], R)
+            if pf_rows and self.PF_AFTER == "qkv_post":
+                self._prefetch_tile_rows(st, W[p + "gu_w"], pf_rows)
             kp1 = st["kp"][1][i] if len(st["kp"]) > 1 else None
             vp1 = st["vp"][1][i] if len(st["vp"]) > 1 else None
             ops.call("sb_dec_attn", st["q"], st["kp"][0][i], st["vp"][0][i], kp1, vp1, rows_group0, P, st["kc"][i],
                      st["vc"][i], st["c_max"] * nkv * hd, st["c_max"], st["step"], nh, nkv, hd, hd ** -0.5, ws,
                      ws.numel(), st["attn"], R)
-            self._gemv(W[p + "o_w"], st["attn"], st["p_o"], S["o"], next_w=W[p + "gu_w"])
+            if pf_rows and self.PF_AFTER == "combine":
+                self._prefetch_tile_rows(st, W[p + "gu_w"], pf_rows)
+            self._gemv(W[p + "o_w"], st["attn"], st["p_o"], S["o"])
             ops.call("sb_dec_residual_rmsnorm", st["x"], st["p_o"], S["o"], RP * H, H, W[p + "ln2_w"], st["xn"], R, H,
                      d.rms_eps)
             if S["gu"] == 1:     # SwiGLU fused into the GEMV epilogue (no fp32 partials, one kernel less)
-                self._gemv(W[p + "gu_w"], st["xn"], st["act"], 1, next_w=W[p + "down_w"], swiglu=True)
+                self._gemv(W[p + "gu_w"], st["xn"], st["act"], 1, swiglu=True)
             else:
-                self._gemv(W[p + "gu_w"], st["xn"], st["p_gu"], S["gu"], next_w=W[p + "down_w"])
+                self._gemv(W[p + "gu_w"], st["xn"], st["p_gu"], S["gu"])
                 ops.call("sb_dec_swiglu", st["p_gu"], S["gu"], RP * 2 * I, 2 * I, st["act"], R, I)
-            self._gemv(W[p + "down_w"], st["act"], st["p_down"], S["down"],
-                       next_w=W[f"l.{i + 1}.qkv_w"] if i + 1 < d.layers else W["lm_head"])
+            self._gemv(W[p + "down_w"], st["act"], st["p_down"], S["down"])
             parts, sp = st["p_down"], S["down"]
         ops.call("sb_dec_residual_rmsnorm", st["x"], parts, sp, RP * H, H, W["norm_w"], st["xn"], R, H, d.rms_eps)
-        self._gemv(W["lm_head"], st["xn"], st["logits"], 1, next_w=W["l.0.qkv_w"])   # warms L2 for the next step
+        self._gemv(W["lm_head"], st["xn"], st["logits"], 1)
         ops.call("sb_step_advance", st["step"])
         self._sample(st, samp, suppress_eos)
+        if st["forked"]:     # join the prefetch branch (long finished): a capture must end with every fork joined
+            torch.cuda.current_stream().wait_stream(st["side"])
 
     def _decode_graph(self, st, rope_base, rows_group0, sp, suppress_eos):
         """Capture one decode step into a CUDA graph (cached per decode state and step arguments).  Captured with the

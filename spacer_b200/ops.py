@@ -61,8 +61,7 @@ def _req(t: torch.Tensor, dtype, name: str):
 
 def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn=False, b_mn=False, out=None, epilogue=EPI_STORE,
          bias=None, residual=None, aux=None, k_splits=1, bn=0, targets=None, lse_part=None,
-         tgt_logit=None, lse=None, coef=None, M=None, N=None, K=None, prefetch=None, prefetch_bytes=0,
-         prefetch2=None, prefetch2_bytes=0):
+         tgt_logit=None, lse=None, coef=None, M=None, N=None, K=None):
     """D[M,N] = epi(A * B^T).  a: [M,K] (or [K,M] if a_mn); b: [N,K] (or [K,N] if b_mn)."""
     lib = _lib.load()
     _req(a, torch.bfloat16, "a")
@@ -102,10 +101,6 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn=False, b_mn=False, out=None, 
                     ("lse", lse), ("coef", coef)):
         if t is not None:
             setattr(g, name, t.data_ptr())
-    if prefetch is not None:
-        g.prefetch, g.prefetch_bytes = prefetch.data_ptr(), int(prefetch_bytes)
-    if prefetch2 is not None:
-        g.prefetch2, g.prefetch2_bytes = prefetch2.data_ptr(), int(prefetch2_bytes)
     check(lib.sb_gemm(C.byref(g), _stream()), "sb_gemm")
     return out
 

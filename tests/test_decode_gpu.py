@@ -420,3 +420,21 @@ def test_adamw_matches_torch(grad_f32, mom_bf16):
     tol = 2e-3 if mom_bf16 else 1e-5
     assert (master - ref_p.data).abs().max().item() < tol
     assert torch.equal(p, master.bfloat16())
+
+
+def test_l2_prefetch_kernel_forms():
+    """sb_dec_l2_prefetch only warms L2: both forms (bulk/TMA and paced per-line) run over a strided row subset and over one
+    linear run without touching the data; bad arguments are rejected."""
+    from spacer_b200 import ops
+    w = torch.randn((1024, 512), device="cuda").bfloat16()
+    ref = w.clone()
+    k = w.shape[1]
+    for pace in (-1, 0, 300):
+        ops.call("sb_dec_l2_prefetch", w, 24 * k * 2, 128 * k * 2, w.shape[0] // 128, 0, pace)
+        ops.call("sb_dec_l2_prefetch", w, w.numel() * 2, 0, 1, 16, pace)
+    torch.cuda.synchronize()
+    assert torch.equal(w, ref)
+    with pytest.raises(Exception):
+        ops.call("sb_dec_l2_prefetch", w, 0, 0, 1, 0, -1)
+    with pytest.raises(Exception):
+        ops.call("sb_dec_l2_prefetch", w, 200, 128 * k * 2, 4, 0, 100)      # paced form needs whole 128-byte lines

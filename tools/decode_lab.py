@@ -32,6 +32,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="c3")
     ap.add_argument("--exp", default="step,gemv")
+    ap.add_argument("--plans", default="", help="hints,gu_rows,after;... (overrides the built-in sweep)")
     a = ap.parse_args()
     cfg = bench.CONFIGS[a.config]
     dims = mcfg.PRESETS[cfg["preset"]]()
@@ -72,31 +73,38 @@ def main():
     wbytes = m.decode_weight_bytes()
     flush = torch.empty(512 << 20, device=dev, dtype=torch.uint8)
 
-    if "step" in a.exp:
-        for pdl, pf, pfa in ((1, 16, 48), (1, 0, 0), (1, 16, 72), (1, 16, 96), (1, 16, 120), (1, 32, 96), (1, 48, 96), (1, 0, 96), (1, 16, 48)):
-            if True:
-                pf <<= 20
-                lib.sb_set_pdl(pdl)
-                m.L2_PREFETCH_BYTES = pf
-                m.L2_PREFETCH_ATTN_BYTES = pfa << 20
-                st["graphs"].clear()
-                st["step"].fill_(200)
-                graph, nodes = m._decode_graph(st, nxt, G, SP, True)
-                st["step"].fill_(200)
-                for _ in range(5):
-                    graph.replay()
-                st["step"].fill_(200)
-                ms = timed(graph.replay, 100)
-                kv = 2 * dims.layers * dims.kv_heads * dims.head_dim * 2
-                byts = wbytes + 2 * ids.numel() * kv + (G + G // 2) * 250 * kv
-                print(json.dumps({"exp": "decode_step_graph", "pdl": pdl, "l2_prefetch_mb": pf >> 20, "l2_prefetch_attn_mb": pfa, "ms": round(ms, 4),
-                                  "gbs": round(byts / ms / 1e6, 1), "nodes": nodes}), flush=True)
-        lib.sb_set_pdl(1)
-        m.L2_PREFETCH_BYTES = 16 << 20
-        m.L2_PREFETCH_ATTN_BYTES = 48 << 20
+    def set_plan(hints, gu_rows, after, ctas, pace=-1):
+        lib.sb_set_dec_l2_hints(hints)
+        m.PF_GU_ROWS, m.PF_AFTER, m.PF_CTAS, m.PF_PACE_NS = gu_rows, after, ctas, pace
 
-    for trace_cfg in ([(16, 48), (0, 0)] if "trace" in a.exp else []):
-        m.L2_PREFETCH_BYTES, m.L2_PREFETCH_ATTN_BYTES = trace_cfg[0] << 20, trace_cfg[1] << 20
+    default_plan = (1, m.PF_GU_ROWS, m.PF_AFTER, m.PF_CTAS, m.PF_PACE_NS)
+    if "step" in a.exp:
+        plans = [default_plan, (1, 0, "attn", 0, -1), (1, 24, "combine", 0, -1)]
+        for after in ("combine", "qkv_post"):
+            for pace in (0, 200, 500, 1000):
+                for rows in (24, 32):
+                    plans.append((1, rows, after, 0, pace))
+        plans += [(1, 32, "qkv_post", 74, 500), (1, 32, "qkv_post", 37, 200), (1, 40, "qkv_post", 0, 500), (1, 0, "attn", 0, -1), default_plan]
+        if a.plans:
+            plans = [(int(pl.split(",")[0]), int(pl.split(",")[1]), pl.split(",")[2], int(pl.split(",")[3]), int(pl.split(",")[4])) for pl in a.plans.split(";")]
+        for plan in plans:
+            set_plan(*plan)
+            st["graphs"].clear()
+            st["step"].fill_(200)
+            graph, nodes = m._decode_graph(st, nxt, G, SP, True)
+            st["step"].fill_(200)
+            for _ in range(5):
+                graph.replay()
+            st["step"].fill_(200)
+            ms = timed(graph.replay, 100)
+            kv = 2 * dims.layers * dims.kv_heads * dims.head_dim * 2
+            byts = wbytes + 2 * ids.numel() * kv + (G + G // 2) * 250 * kv
+            print(json.dumps({"exp": "decode_step_graph", "l2_hints": plan[0], "pf_gu_rows": plan[1], "pf_after": plan[2], "pf_ctas": plan[3], "pf_pace_ns": plan[4], "ms": round(ms, 4),
+                              "gbs": round(byts / ms / 1e6, 1), "nodes": nodes}), flush=True)
+        set_plan(*default_plan)
+
+    for trace_cfg in ([default_plan, (1, 0, "attn", 0, -1)] if "trace" in a.exp else []):
+        set_plan(*trace_cfg)
         KINDS = {1: "gemv", 2: "embed", 3: "rmsnorm", 4: "qkv_post", 5: "attn", 6: "combine", 7: "swiglu", 8: "sample", 9: "advance"}
         cap = 4096
         buf = torch.zeros(1 + 4 * cap, device=dev, dtype=torch.int64)
@@ -120,7 +128,7 @@ def main():
         one = recs[idx[0] + 1: idx[1] + 1] if len(idx) >= 2 else recs
         t0 = one[0][1]
         tag = "r02"
-        out_path = os.path.join(ROOT, "gpurun_out", f"decode_trace_{tag}_pf{trace_cfg[0]}_{trace_cfg[1]}.txt")
+        out_path = os.path.join(ROOT, "gpurun_out", f"decode_trace_{tag}_plan{'_'.join(str(v) for v in trace_cfg)}.txt")
         os.makedirs(os.path.dirname(out_path), exist_ok=True)
         agg = {}
         with open(out_path, "w") as f:
@@ -138,6 +146,72 @@ def main():
                           "per_kind": {k: {"n": v[0], "wait_us": round(v[1] / v[0], 2), "exec_us": round(v[2] / v[0], 2),
                                            "gap_after_prev_end_us": round(v[3] / v[0], 2), "exec_total_us": round(v[2], 1),
                                            "gap_total_us": round(v[3], 1)} for k, v in agg.items()}}), flush=True)
+
+    if "skew" in a.exp:
+        # spread of the finishing times of the CTAs of every decode GEMV (the kernel-level trace only sees block 0)
+        import statistics
+        if a.plans:
+            pl = a.plans.split(";")[0].split(",")
+            set_plan(int(pl[0]), int(pl[1]), pl[2], int(pl[3]), int(pl[4]))
+        cap = 260
+        n_sms = 148
+        buf = torch.zeros(n_sms * (1 + 3 * cap), device=dev, dtype=torch.int64)
+        st["graphs"].clear()
+        st["step"].fill_(200)
+        graph, nodes = m._decode_graph(st, nxt, G, SP, True)
+        for _ in range(3):
+            graph.replay()
+        torch.cuda.synchronize()
+        lib.sb_trace_enable_gemv_ctas(ctypes.c_void_p(buf.data_ptr()), cap)
+        graph.replay()
+        torch.cuda.synchronize()
+        lib.sb_trace_enable_gemv_ctas(None, 0)
+        h = buf.cpu().view(n_sms, 1 + 3 * cap).tolist()
+        names = {4608 ^ (3584 << 32): "qkv", 3584 ^ (3584 << 32): "o", 37888 ^ (3584 << 32): "gu", 3584 ^ (18944 << 32): "down",
+                 152064 ^ (3584 << 32): "lm_head"}
+        per = {}           # (name, occurrence) -> list of (block, ready, end)
+        for b in range(n_sms):
+            seen = {}
+            for k in range(int(h[b][0])):
+                tag, tr_, te = h[b][1 + 3 * k], h[b][2 + 3 * k], h[b][3 + 3 * k]
+                nm = names.get(tag, hex(tag))
+                occ = seen.get(nm, 0)
+                seen[nm] = occ + 1
+                per.setdefault((nm, occ), []).append((b, tr_, te))
+        agg = {}
+        for (nm, occ), lst in per.items():
+            ends = sorted(e for _, _, e in lst)
+            readies = sorted(r for _, r, _ in lst)
+            e_b0 = [e for b, _, e in lst if b == 0]
+            d = agg.setdefault(nm, {"n": 0, "ctas": len(lst), "dur_first_ready_to_last_end": [], "end_max_minus_median": [], "end_max_minus_min": [],
+                                    "end_max_minus_block0": [], "ready_spread": []})
+            d["n"] += 1
+            d["dur_first_ready_to_last_end"].append((ends[-1] - readies[0]) / 1e3)
+            d["end_max_minus_median"].append((ends[-1] - ends[len(ends) // 2]) / 1e3)
+            d["end_max_minus_min"].append((ends[-1] - ends[0]) / 1e3)
+            d["ready_spread"].append((readies[-1] - readies[0]) / 1e3)
+            if e_b0:
+                d["end_max_minus_block0"].append((ends[-1] - e_b0[0]) / 1e3)
+        for nm, d in agg.items():
+            out = {"exp": "gemv_cta_skew", "gemv": nm, "instances": d["n"], "ctas": d["ctas"]}
+            for k in ("dur_first_ready_to_last_end", "end_max_minus_median", "end_max_minus_min", "end_max_minus_block0", "ready_spread"):
+                out[k + "_us"] = round(statistics.median(d[k]), 2) if d[k] else None
+            print(json.dumps(out), flush=True)
+        for nm in ("gu", "qkv", "down", "o"):
+            lst = sorted(per.get((nm, 5), []))
+            if lst:
+                t0 = min(r for _, r, _ in lst)
+                late = [[b, round((r - t0) / 1e3, 2), round((e - t0) / 1e3, 2)] for b, r, e in lst if r - t0 > 300]
+                print(json.dumps({"exp": "gemv_cta_skew", "gemv": nm, "layer": 5, "late_blocks_ready_end_us": late,
+                                  "median_end_us": round(statistics.median(e - t0 for _, _, e in lst) / 1e3, 2)}), flush=True)
+        # which SMs finish last in the gate|up GEMV (stable across layers = a property of the SM, not of the data)
+        late = {}
+        for (nm, occ), lst in per.items():
+            if nm != "gu":
+                continue
+            for b, _, e in sorted(lst, key=lambda x: -x[2])[:15]:
+                late[b] = late.get(b, 0) + 1
+        print(json.dumps({"exp": "gemv_cta_skew", "gu_blocks_among_15_latest": sorted(late.items(), key=lambda kv: -kv[1])[:20]}), flush=True)
 
     if "gemv" in a.exp:
         W = m.params
