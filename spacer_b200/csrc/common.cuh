@@ -46,6 +46,14 @@ int sb_check_launch(const char* what);
 // ----------------------------------------------------------------------------------------------
 SB_DEVICE void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 SB_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// 8-byte read-only load that stays where it is written relative to pdl_wait(): a plain C++ load of data the preceding
+// kernels do not write may be sunk below the wait by the compiler (it was, in the decode RMSNorm: the norm weights, cold in
+// HBM every step, were fetched AFTER the dependency resolved -- 2-3 us on the layer's critical path, twice per layer)
+SB_DEVICE uint2 ldg_nc_u2_ordered(const void* p) {
+  uint2 v;
+  asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t sb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,

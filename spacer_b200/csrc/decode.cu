@@ -44,7 +44,10 @@ dec_residual_rmsnorm_kernel(bf16* __restrict__ x, const float* __restrict__ part
 #pragma unroll
   for (int np = 0; np < MAXV; ++np) {
     const int i = (np * RN_THREADS + threadIdx.x) * 4;
-    wreg[np] = (xn && i < H) ? *reinterpret_cast<const uint2*>(w + i) : make_uint2(0u, 0u);
+    wreg[np] = (xn && i < H) ? ldg_nc_u2_ordered(w + i) : make_uint2(0u, 0u);
+    // ptxas still sinks the load itself below the wait (it only has to be complete where the value is used); a prefetch
+    // has no result to wait for and stays here, so the load after the wait is an L2 hit instead of a cold HBM read
+    if (xn && i < H && (threadIdx.x & 15) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(w + i) : "memory");
   }
   pdl_wait();
   sb_trace_mark(tr, 1);
@@ -230,7 +233,10 @@ SB_DEFINE_TRACE_SETTER(sb_trace_set_decode)
 
 extern "C" int sb_dec_embed(const int* tokens, const void* embed, void* x, int R, int H, sb_stream_t stream) {
   SB_REQUIRE(tokens && embed && x && R > 0 && H % 8 == 0, "sb_dec_embed: bad arguments");
-  SB_CUDA(sb_launch(dec_embed_kernel, dim3(R), dim3(256), 0, STREAM(stream), sb_pdl_enabled(), tokens, (const bf16*)embed,
+  // The first kernel of a decode step is launched WITHOUT programmatic dependent launch: a full dependency on whatever
+  // precedes it (the previous step's sampler when steps are enqueued back to back outside a graph) ends the PDL cascade at
+  // the step boundary, which is what lets later kernels read the step counter and older cache rows before their own wait.
+  SB_CUDA(sb_launch(dec_embed_kernel, dim3(R), dim3(256), 0, STREAM(stream), false, tokens, (const bf16*)embed,
                     (bf16*)x, H));
   return sb_check_launch("sb_dec_embed");
 }

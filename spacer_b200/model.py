@@ -1025,7 +1025,7 @@ class Qwen2VLB200:
     # latency-bound attention / norm kernels then wait behind it (tools/decode_lab.py --exp step: 2.96 ms per step without,
     # 2.87 with; 3.1-3.3 when the requests come as a burst or overrun into the gate|up GEMV).
     PF_GU_ROWS = 24
-    PF_AFTER = "qkv_post"      # "qkv" | "qkv_post" | "combine"
+    PF_AFTER = "qkv"           # "qkv" | "qkv_post" | "combine"
     PF_CTAS = 0                # CTAs that issue the requests (0 = one per SM)
     PF_PACE_NS = 750           # >= 0: per-line requests, each of the CTAs' 128 threads pausing this long; -1: bulk (TMA) form
 

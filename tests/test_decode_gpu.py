@@ -106,8 +106,23 @@ def test_dec_qkv_post_and_attention():
     (24, 16, 12, 2, 832, 1024, 700),    # G=16 (+8): two 64-query blocks per (group, kv head), 8 completion splits
     (3, 3, 4, 4, 70, 40, 5),            # one group, rep 1, ragged prompt tile
     (5, 0, 8, 2, 130, 64, 63),          # every row in the second group
+    (32, 16, 28, 4, 2304, 512, 500),    # 32 rows leave room for ONE completion split: 8 key tiles per own item (the
+                                        # current token's row sits in a tile that is loaded inside the loop)
+    (32, 16, 28, 4, 2304, 512, 100),    # same plan, current token in the second pre-loaded tile
 ])
-def test_dec_attention_shapes(R, g0, nh, nkv, P, Cmax, step):
+@pytest.mark.parametrize("impl", [1, 0])    # 1 = tcgen05 (the default), 0 = mma.sync
+def test_dec_attention_shapes(R, g0, nh, nkv, P, Cmax, step, impl):
+    import ctypes
+    from spacer_b200 import ops
+    lib = ops._lib.load()
+    assert lib.sb_set_dec_attn_impl(impl) == 0
+    try:
+        _dec_attention_case(R, g0, nh, nkv, P, Cmax, step)
+    finally:
+        lib.sb_set_dec_attn_impl(1)
+
+
+def _dec_attention_case(R, g0, nh, nkv, P, Cmax, step):
     import ctypes
     from spacer_b200 import ops
     hd = 128

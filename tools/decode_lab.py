@@ -32,6 +32,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="c3")
     ap.add_argument("--exp", default="step,gemv")
+    ap.add_argument("--attn-impl", type=int, default=1)
     ap.add_argument("--plans", default="", help="hints,gu_rows,after;... (overrides the built-in sweep)")
     a = ap.parse_args()
     cfg = bench.CONFIGS[a.config]
@@ -45,6 +46,7 @@ def main():
     G, C = cfg["G"], cfg["C"]
     pix2 = pix.flip(0).contiguous()
     lib = ops._lib.load()
+    lib.sb_set_dec_attn_impl(a.attn_impl)
     SP = SamplingParams(top_p=0.95, top_k=50, eos_ids=(dims.eos_id,), pad_id=dims.pad_id)   # the trainer's rollout options
     if "ab" in a.exp:
         # the decode step as bench.py runs it (graph replay at step 200) + the 113 GEMVs alone
@@ -106,7 +108,7 @@ def main():
     for trace_cfg in ([default_plan, (1, 0, "attn", 0, -1)] if "trace" in a.exp else []):
         set_plan(*trace_cfg)
         KINDS = {1: "gemv", 2: "embed", 3: "rmsnorm", 4: "qkv_post", 5: "attn", 6: "combine", 7: "swiglu", 8: "sample", 9: "advance"}
-        cap = 4096
+        cap = 8192
         buf = torch.zeros(1 + 4 * cap, device=dev, dtype=torch.int64)
         st["graphs"].clear()
         st["step"].fill_(200)
