@@ -88,7 +88,7 @@ def main():
                     plans.append((1, rows, after, 0, pace))
         plans += [(1, 32, "qkv_post", 74, 500), (1, 32, "qkv_post", 37, 200), (1, 40, "qkv_post", 0, 500), (1, 0, "attn", 0, -1), default_plan]
         if a.plans:
-            plans = [(int(pl.split(",")[0]), int(pl.split(",")[1]), pl.split(",")[2], int(pl.split(",")[3]), int(pl.split(",")[4])) for pl in a.plans.split(";")]
+            plans = [tuple(int(v) if i != 2 else v for i, v in enumerate(pl.split(","))) for pl in a.plans.split(";")]
         for plan in plans:
             set_plan(*plan)
             st["graphs"].clear()
