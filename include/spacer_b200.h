@@ -215,8 +215,6 @@ int sb_dec_qkv_post(const float* parts, int S, long long stride_s, long long str
  * row also attends to its own completion cache [c_max][nkv*hd] slots 0..*step_ptr.  The shared prompt K/V is read once
  * per group (queries of all its rows batched on tensor cores).  workspace: fp32 scratch of at least
  * sb_dec_attn_workspace() floats.  out bf16 [R][n_heads*hd] */
-/* decode attention engine: 1 = tcgen05 + TMEM + TMA (default), 0 = mma.sync (A-B timing; SB_DEC_ATTN_IMPL overrides) */
-int sb_set_dec_attn_impl(int impl);
 int sb_dec_attn_workspace(int R, int rows_group0, int P, int c_max, int n_heads, int n_kv_heads, long long* floats_out);
 int sb_dec_attn(const void* q, const void* kp0, const void* vp0, const void* kp1, const void* vp1, int rows_group0,
                 int P, const void* k_cache, const void* v_cache, long long cache_stride_r, int c_max,

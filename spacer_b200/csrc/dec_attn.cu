@@ -5,12 +5,14 @@
 //
 // The context of row r is [shared prompt of r's group | r's own completion so far].  Work is cut into independent
 // items, one CTA each, all in ONE launch:
-//   prefix items (group, q-block, kv head, key split): the <= 64 query vectors (rows of the group x the q heads of the
+//   prefix items (group, q-block, kv head, key split): the <= 128 query vectors (rows of the group x the q heads of the
 //                kv head) against a slice of the SHARED prompt K/V -> the prompt cache is read once per group per
-//                step, not once per row, and the products run on tensor cores (mma.sync m16n8k16, M = rows x heads);
+//                step, not once per row, and the products run on tcgen05 tensor cores (M = rows x heads);
 //   own items    (row, kv head, key split): the row's q heads against a slice of its own completion cache.
 // Every item writes a normalised partial (O, log2-sum-exp) for its (row, head) pairs; a combine kernel merges them.
 // The step is read from device memory so that one captured CUDA graph replays for every step.
+// (Rounds 1-2 ran these items on mma.sync m16n8k16 -- the last legacy-tensor-path kernel of the decode step; the tcgen05
+// version measured the same step time and replaced it.)
 #include "common.cuh"
 #include "spacer_b200.h"
 #include <cuda.h>
@@ -19,12 +21,6 @@
 namespace {
 
 constexpr int HD = 128;
-constexpr int LD = HD + 8;       // padded smem row (elements): conflict-free ldmatrix
-constexpr int TQ = 64;           // query vectors per item (4 warps x 16)
-constexpr int TK = 64;           // keys per pipeline stage
-constexpr int THREADS = 128;
-constexpr int TILE = 64 * LD;    // elements of one [64][LD] tile
-
 SB_DEVICE void cp_async16(uint32_t dst, const void* src, bool pred) {
   const int sz = pred ? 16 : 0;
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
@@ -32,20 +28,6 @@ SB_DEVICE void cp_async16(uint32_t dst, const void* src, bool pred) {
 SB_DEVICE void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 SB_DEVICE void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-SB_DEVICE void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-SB_DEVICE void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-SB_DEVICE void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
 
 struct Plan {
   int rep;            // q heads per kv head
@@ -57,7 +39,8 @@ struct Plan {
   int n_prefix_items, n_items;
 };
 
-Plan make_plan(int R, int rows_group0, int P, int c_max, int nh, int nkv, int sms, int tq) {
+Plan make_plan(int R, int rows_group0, int P, int c_max, int nh, int nkv, int sms) {
+  constexpr int tq = 128, TK = 64;     // query vectors per item (TMEM lanes), keys per tile
   Plan pl;
   pl.rep = nh / nkv;
   pl.n_rows[0] = rows_group0 < R ? rows_group0 : R;
@@ -99,216 +82,6 @@ struct DecAttnParams {
   float* o_part;                       // [R][nh][NS][HD]
   float* lse_part;                     // [R][nh][NS]   (log2 domain; -inf = empty)
 };
-
-__global__ void __launch_bounds__(THREADS)
-dec_attn_kernel(const DecAttnParams p) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  bf16* sQ = reinterpret_cast<bf16*>(smem_raw);
-  bf16* sK = sQ + TILE;        // 2 stages
-  bf16* sV = sK + 2 * TILE;    // 2 stages
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int g = lane >> 2, t4 = lane & 3;
-  const Plan& pl = p.pl;
-  const int rep = pl.rep;
-
-  pdl_launch_dependents();
-  const int tr = (blockIdx.x == 0 && tid == 0) ? sb_trace_begin(SB_TR_ATTN) : -1;
-  // ---- decode the item
-  int item = blockIdx.x;
-  const bf16 *kbase, *vbase;
-  int j_lo, j_hi, slot, kvh, row0, n_q;   // query vector m -> (row0 + m / rep, head kvh*rep + m % rep), m < n_q
-  int m0 = 0;                             // first query vector of this q-block
-  int j_new = -1;                         // own items: the key written by the preceding kernel (loaded after the wait)
-  if (item < pl.n_prefix_items) {
-    const int per_group0 = pl.n_qb[0] * p.nkv * pl.n_psplit;
-    int grp = 0;
-    if (item >= per_group0) { grp = 1; item -= per_group0; }
-    const int s = item % pl.n_psplit;
-    kvh = (item / pl.n_psplit) % p.nkv;
-    const int qb = item / (pl.n_psplit * p.nkv);
-    row0 = grp == 0 ? 0 : pl.n_rows[0];
-    m0 = qb * pl.rows_qb * rep;
-    n_q = min(pl.rows_qb, pl.n_rows[grp] - qb * pl.rows_qb) * rep;
-    kbase = p.kp[grp] + (long long)kvh * HD;
-    vbase = p.vp[grp] + (long long)kvh * HD;
-    j_lo = s * pl.p_chunk;
-    j_hi = min(j_lo + pl.p_chunk, p.P);
-    slot = s;
-  } else {
-    // Own items.  *step_ptr was written by the PREVIOUS step's advance kernel and the completion cache rows below the
-    // current slot by previous steps' qkv_post kernels: with a PDL chain a kernel's pre-wait code can run while several of
-    // its predecessors are still in flight, but never across the sampler that ends the previous step (a graph launch
-    // boundary), so both are stable here.  Only the row of the CURRENT token (slot *step_ptr, written by the qkv_post
-    // kernel right before this one) has to wait.
-    item -= pl.n_prefix_items;
-    const int s = item % pl.n_csplit;
-    kvh = (item / pl.n_csplit) % p.nkv;
-    row0 = item / (pl.n_csplit * p.nkv);
-    n_q = rep;
-    kbase = p.kc + row0 * p.cache_stride_r + (long long)kvh * HD;
-    vbase = p.vc + row0 * p.cache_stride_r + (long long)kvh * HD;
-    const int n_ctx = *p.step_ptr + 1;
-    int per = (n_ctx + pl.n_csplit - 1) / pl.n_csplit;
-    per = (per + TK - 1) / TK * TK;
-    j_lo = s * per;
-    j_hi = min(j_lo + per, n_ctx);
-    slot = pl.n_psplit + s;
-    j_new = n_ctx - 1;
-  }
-  const bool is_prefix = blockIdx.x < pl.n_prefix_items;
-  const long long kv_ld = (long long)p.nkv * HD;
-  const int n_tiles = j_hi > j_lo ? (j_hi - j_lo + TK - 1) / TK : 0;
-
-  // rows of tile t -> stage buf; `skip` (a key index or -1) is left out, `only` >= 0 loads nothing but that key
-  auto load_kv = [&](int t, int buf, int skip, int only) {
-    const int k0 = j_lo + t * TK;
-    for (int i = tid; i < TK * (HD / 8); i += THREADS) {
-      const int r = i / (HD / 8), c = i % (HD / 8);
-      if (k0 + r == skip || (only >= 0 && k0 + r != only)) continue;
-      const bool ok = (k0 + r) < j_hi;
-      const long long off = (long long)(ok ? (k0 + r) : j_lo) * kv_ld + c * 8;
-      cp_async16(smem_u32(sK + buf * TILE + r * LD + c * 8), kbase + off, ok);
-      cp_async16(smem_u32(sV + buf * TILE + r * LD + c * 8), vbase + off, ok);
-    }
-  };
-
-  // ---- the first TWO K/V tiles (both stages) are requested before waiting for the kernels that produce q: the prompt
-  // cache is constant during decode and the completion cache only changes in the current token's row.  After the wait
-  // only L2 hits are left on the critical path: the gathered query vectors and, for own items, that one row.
-  if (n_tiles > 0) load_kv(0, 0, j_new, -1);
-  if (n_tiles > 1) load_kv(1, 1, j_new, -1);
-  cp_async_commit();
-  pdl_wait();
-  sb_trace_mark(tr, 1);
-  for (int i = tid; i < TQ * (HD / 8); i += THREADS) {
-    const int m = i / (HD / 8), c = i % (HD / 8);
-    const bool ok = m < n_q;
-    const int mm = ok ? (m0 + m) : m0;
-    const bf16* src = p.q + (long long)(row0 + mm / rep) * p.nh * HD + (long long)(kvh * rep + mm % rep) * HD + c * 8;
-    cp_async16(smem_u32(sQ + m * LD + c * 8), src, ok);
-  }
-  if (j_new >= j_lo && j_new < j_hi) {
-    const int t_new = (j_new - j_lo) / TK;
-    if (t_new < 2) load_kv(t_new, t_new, -1, j_new);   // later tiles are loaded whole, after the wait, inside the loop
-  }
-  cp_async_commit();
-
-  const bool active = warp * 16 < n_q;   // warp-uniform: this warp owns at least one real query vector
-  uint32_t qf[HD / 16][4];
-  float o_acc[HD / 8][4];
-#pragma unroll
-  for (int i = 0; i < HD / 8; ++i) { o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f; }
-  float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
-
-  for (int t = 0; t < n_tiles; ++t) {
-    const int buf = t & 1;
-    // tiles 0 and 1 and the q tile were requested above (two groups); tile t + 2 is requested at the end of iteration t
-    // (one group per iteration, possibly empty), so that at most the newest group may still be in flight here
-    if (t == 0) cp_async_wait<0>(); else cp_async_wait<1>();
-    __syncthreads();
-    if (active) {
-      if (t == 0) {
-#pragma unroll
-        for (int ks = 0; ks < HD / 16; ++ks)
-          ldsm_x4(smem_u32(sQ + (warp * 16 + (lane & 15)) * LD + ks * 16 + (lane >> 4) * 8), qf[ks][0], qf[ks][1],
-                  qf[ks][2], qf[ks][3]);
-      }
-      const bf16* cK = sK + buf * TILE;
-      const bf16* cV = sV + buf * TILE;
-      float s[8][4];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
-#pragma unroll
-      for (int ks = 0; ks < HD / 16; ++ks) {
-#pragma unroll
-        for (int np = 0; np < 4; ++np) {
-          uint32_t b0, b1, b2, b3;
-          ldsm_x4(smem_u32(cK + (np * 16 + (lane & 7) + (lane >> 4) * 8) * LD + ks * 16 + ((lane >> 3) & 1) * 8), b0, b1,
-                  b2, b3);
-          mma16816(s[np * 2], qf[ks], b0, b1);
-          mma16816(s[np * 2 + 1], qf[ks], b2, b3);
-        }
-      }
-      const int k0 = j_lo + t * TK;
-      const bool full = k0 + TK <= j_hi;
-      float mx_lo = -INFINITY, mx_hi = -INFINITY;
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float v = s[nt][e] * p.scale_log2;
-          if (!full && (k0 + nt * 8 + t4 * 2 + (e & 1)) >= j_hi) v = -INFINITY;
-          s[nt][e] = v;
-          if (e < 2) mx_lo = fmaxf(mx_lo, v); else mx_hi = fmaxf(mx_hi, v);
-        }
-      }
-      mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1));
-      mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
-      mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1));
-      mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
-      const float nm_lo = fmaxf(m_lo, mx_lo), nm_hi = fmaxf(m_hi, mx_hi);   // finite: every tile has >= 1 valid key
-      const float cr_lo = exp2f(m_lo - nm_lo), cr_hi = exp2f(m_hi - nm_hi);
-      m_lo = nm_lo; m_hi = nm_hi;
-      float rs_lo = 0.f, rs_hi = 0.f;
-      uint32_t pf[4][4];
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const float p0 = exp2f(s[nt][0] - nm_lo), p1 = exp2f(s[nt][1] - nm_lo);
-        const float p2 = exp2f(s[nt][2] - nm_hi), p3 = exp2f(s[nt][3] - nm_hi);
-        rs_lo += p0 + p1; rs_hi += p2 + p3;
-        pf[nt >> 1][(nt & 1) * 2] = pack_bf16(p0, p1);
-        pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p2, p3);
-      }
-      l_lo = l_lo * cr_lo + rs_lo;
-      l_hi = l_hi * cr_hi + rs_hi;
-#pragma unroll
-      for (int i = 0; i < HD / 8; ++i) {
-        o_acc[i][0] *= cr_lo; o_acc[i][1] *= cr_lo; o_acc[i][2] *= cr_hi; o_acc[i][3] *= cr_hi;
-      }
-#pragma unroll
-      for (int kk = 0; kk < TK / 16; ++kk) {
-#pragma unroll
-        for (int dp = 0; dp < HD / 16; ++dp) {
-          uint32_t b0, b1, b2, b3;
-          ldsm_x4_t(smem_u32(cV + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + dp * 16 + (lane >> 4) * 8), b0, b1,
-                    b2, b3);
-          mma16816(o_acc[dp * 2], pf[kk], b0, b1);
-          mma16816(o_acc[dp * 2 + 1], pf[kk], b2, b3);
-        }
-      }
-    }
-    __syncthreads();
-    if (t + 2 < n_tiles) load_kv(t + 2, buf, -1, -1);
-    cp_async_commit();
-  }
-  cp_async_wait<0>();
-  if (!active) return;
-
-  l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1);
-  l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
-  l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1);
-  l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    const int m = warp * 16 + g + half * 8;
-    if (m >= n_q) continue;
-    const int mm = m0 + m;
-    const int row = row0 + mm / rep, head = kvh * rep + mm % rep;
-    const float l = half ? l_hi : l_lo, mxv = half ? m_hi : m_lo;
-    const float inv = l > 0.f ? 1.f / l : 0.f;
-    const long long pbase = ((long long)row * p.nh + head) * pl.NS + slot;
-    float* op = p.o_part + pbase * HD;
-#pragma unroll
-    for (int i = 0; i < HD / 8; ++i) {
-      const float2 v = half ? make_float2(o_acc[i][2] * inv, o_acc[i][3] * inv)
-                            : make_float2(o_acc[i][0] * inv, o_acc[i][1] * inv);
-      *reinterpret_cast<float2*>(op + i * 8 + t4 * 2) = v;
-    }
-    if (t4 == 0) p.lse_part[pbase] = l > 0.f ? mxv + log2f(l) : -INFINITY;
-  }
-  sb_trace_mark(tr, 2);
-}
-
 
 // ---------------------------------------------------------------------------------------------------------------------
 // The same items on the 5th-generation tensor cores (tcgen05 + TMEM + TMA) -- the engine of attention_tc.cu's forward
@@ -752,29 +525,17 @@ int sm_count() {
   return g_sms;
 }
 
-constexpr int DEC_ATTN_SMEM = 5 * TILE * 2;
-// 1 = tcgen05 (default), 0 = mma.sync (sb_set_dec_attn_impl; SB_DEC_ATTN_IMPL in the environment)
-int g_dec_attn_impl = getenv("SB_DEC_ATTN_IMPL") ? atoi(getenv("SB_DEC_ATTN_IMPL")) : 1;
-int plan_tq() { return g_dec_attn_impl == 1 ? tc::TQ : TQ; }
+
 
 }  // namespace
 
 SB_DEFINE_TRACE_SETTER(sb_trace_set_dec_attn)
 
-extern "C" int sb_set_dec_attn_impl(int impl) {
-  SB_REQUIRE(impl == 0 || impl == 1, "sb_set_dec_attn_impl: 0 = mma.sync, 1 = tcgen05");
-  g_dec_attn_impl = impl;
-  return 0;
-}
-
 extern "C" int sb_dec_attn_workspace(int R, int rows_group0, int P, int c_max, int n_heads, int n_kv_heads,
                                      long long* floats_out) {
   SB_REQUIRE(floats_out && R > 0 && P >= 0 && c_max > 0 && n_heads > 0 && n_kv_heads > 0 && n_heads % n_kv_heads == 0,
              "sb_dec_attn_workspace: bad arguments");
-  // sized for either implementation (the two plans can differ in the number of key splits)
-  const Plan pl0 = make_plan(R, rows_group0, P, c_max, n_heads, n_kv_heads, sm_count(), TQ);
-  const Plan pl1 = make_plan(R, rows_group0, P, c_max, n_heads, n_kv_heads, sm_count(), tc::TQ);
-  const Plan& pl = pl0.NS >= pl1.NS ? pl0 : pl1;
+  const Plan pl = make_plan(R, rows_group0, P, c_max, n_heads, n_kv_heads, sm_count());
   *floats_out = (long long)R * n_heads * pl.NS * (HD + 1);
   return 0;
 }
@@ -787,7 +548,7 @@ extern "C" int sb_dec_attn(const void* q, const void* kp0, const void* vp0, cons
   SB_REQUIRE(P == 0 || (kp0 && vp0), "sb_dec_attn: prompt cache missing");
   SB_REQUIRE(head_dim == HD, "sb_dec_attn: head_dim must be 128, got %d", head_dim);
   SB_REQUIRE(R > 0 && R <= 32 && c_max > 0 && n_heads % n_kv_heads == 0, "sb_dec_attn: bad sizes");
-  SB_REQUIRE(n_heads / n_kv_heads <= 16, "sb_dec_attn: at most 16 q heads per kv head");
+  SB_REQUIRE(n_heads / n_kv_heads <= 128, "sb_dec_attn: at most 128 q heads per kv head");
   SB_REQUIRE(rows_group0 >= R || (kp1 && vp1), "sb_dec_attn: second prompt cache missing for rows >= rows_group0");
   DecAttnParams p;
   p.q = (const bf16*)q;
@@ -796,44 +557,35 @@ extern "C" int sb_dec_attn(const void* q, const void* kp0, const void* vp0, cons
   p.kc = (const bf16*)k_cache; p.vc = (const bf16*)v_cache; p.cache_stride_r = cache_stride_r;
   p.step_ptr = step_ptr; p.R = R; p.P = P; p.nh = n_heads; p.nkv = n_kv_heads;
   p.scale_log2 = scale * 1.4426950408889634f;
-  p.pl = make_plan(R, rows_group0, P, c_max, n_heads, n_kv_heads, sm_count(), plan_tq());
+  p.pl = make_plan(R, rows_group0, P, c_max, n_heads, n_kv_heads, sm_count());
   const long long need = (long long)R * n_heads * p.pl.NS * (HD + 1);
   SB_REQUIRE(workspace_floats >= need, "sb_dec_attn: workspace too small (%lld floats, need %lld; see sb_dec_attn_workspace)",
              workspace_floats, need);
   p.o_part = workspace;
   p.lse_part = workspace + (long long)R * n_heads * p.pl.NS * HD;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (g_dec_attn_impl == 1) {
-    static bool done_tc = false;
-    if (!done_tc) {
-      SB_CUDA(cudaFuncSetAttribute(tc::dec_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM));
-      done_tc = true;
-    }
-    SB_REQUIRE(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k_cache) | reinterpret_cast<uintptr_t>(v_cache) |
-                 reinterpret_cast<uintptr_t>(kp0) | reinterpret_cast<uintptr_t>(vp0) | reinterpret_cast<uintptr_t>(kp1) |
-                 reinterpret_cast<uintptr_t>(vp1)) & 15) == 0, "sb_dec_attn: q and the caches must be 16-byte aligned");
-    SB_REQUIRE(cache_stride_r == (long long)c_max * n_kv_heads * HD,
-               "sb_dec_attn: the completion cache must be contiguous [R][c_max][n_kv_heads*head_dim]");
-    tc::Maps maps;
-    const uint64_t cols = (uint64_t)n_kv_heads * HD;
-    if (tc::make_map(&maps.kc, p.kc, cols, (uint64_t)R * c_max) || tc::make_map(&maps.vc, p.vc, cols, (uint64_t)R * c_max)) return 1;
-    for (int g = 0; g < 2; ++g) {
-      if (P > 0) {
-        if (tc::make_map(&maps.kp[g], p.kp[g], cols, (uint64_t)P) || tc::make_map(&maps.vp[g], p.vp[g], cols, (uint64_t)P)) return 1;
-      } else {
-        maps.kp[g] = maps.kc; maps.vp[g] = maps.vc;   // no prefix items: never dereferenced
-      }
-    }
-    SB_CUDA(sb_launch(tc::dec_attn_tc_kernel, dim3(p.pl.n_items), dim3(tc::THREADS), (size_t)tc::SMEM, st, sb_pdl_enabled(), maps, p,
-                      c_max));
-  } else {
-    static bool done = false;
-    if (!done) {
-      SB_CUDA(cudaFuncSetAttribute(dec_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_ATTN_SMEM));
-      done = true;
-    }
-    SB_CUDA(sb_launch(dec_attn_kernel, dim3(p.pl.n_items), dim3(THREADS), (size_t)DEC_ATTN_SMEM, st, sb_pdl_enabled(), p));
+  static bool done_tc = false;
+  if (!done_tc) {
+    SB_CUDA(cudaFuncSetAttribute(tc::dec_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM));
+    done_tc = true;
   }
+  SB_REQUIRE(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k_cache) | reinterpret_cast<uintptr_t>(v_cache) |
+               reinterpret_cast<uintptr_t>(kp0) | reinterpret_cast<uintptr_t>(vp0) | reinterpret_cast<uintptr_t>(kp1) |
+               reinterpret_cast<uintptr_t>(vp1)) & 15) == 0, "sb_dec_attn: q and the caches must be 16-byte aligned");
+  SB_REQUIRE(cache_stride_r == (long long)c_max * n_kv_heads * HD,
+             "sb_dec_attn: the completion cache must be contiguous [R][c_max][n_kv_heads*head_dim]");
+  tc::Maps maps;
+  const uint64_t cols = (uint64_t)n_kv_heads * HD;
+  if (tc::make_map(&maps.kc, p.kc, cols, (uint64_t)R * c_max) || tc::make_map(&maps.vc, p.vc, cols, (uint64_t)R * c_max)) return 1;
+  for (int g = 0; g < 2; ++g) {
+    if (P > 0) {
+      if (tc::make_map(&maps.kp[g], p.kp[g], cols, (uint64_t)P) || tc::make_map(&maps.vp[g], p.vp[g], cols, (uint64_t)P)) return 1;
+    } else {
+      maps.kp[g] = maps.kc; maps.vp[g] = maps.vc;   // no prefix items: never dereferenced
+    }
+  }
+  SB_CUDA(sb_launch(tc::dec_attn_tc_kernel, dim3(p.pl.n_items), dim3(tc::THREADS), (size_t)tc::SMEM, st, sb_pdl_enabled(), maps, p,
+                    c_max));
   if (sb_check_launch("sb_dec_attn")) return 1;
   const int n_pairs = R * n_heads;
   SB_CUDA(sb_launch(dec_attn_combine_kernel, dim3((n_pairs + 3) / 4), dim3(128), 0, st, sb_pdl_enabled(),

@@ -110,19 +110,7 @@ def test_dec_qkv_post_and_attention():
                                         # current token's row sits in a tile that is loaded inside the loop)
     (32, 16, 28, 4, 2304, 512, 100),    # same plan, current token in the second pre-loaded tile
 ])
-@pytest.mark.parametrize("impl", [1, 0])    # 1 = tcgen05 (the default), 0 = mma.sync
-def test_dec_attention_shapes(R, g0, nh, nkv, P, Cmax, step, impl):
-    import ctypes
-    from spacer_b200 import ops
-    lib = ops._lib.load()
-    assert lib.sb_set_dec_attn_impl(impl) == 0
-    try:
-        _dec_attention_case(R, g0, nh, nkv, P, Cmax, step)
-    finally:
-        lib.sb_set_dec_attn_impl(1)
-
-
-def _dec_attention_case(R, g0, nh, nkv, P, Cmax, step):
+def test_dec_attention_shapes(R, g0, nh, nkv, P, Cmax, step):
     import ctypes
     from spacer_b200 import ops
     hd = 128

@@ -32,7 +32,6 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="c3")
     ap.add_argument("--exp", default="step,gemv")
-    ap.add_argument("--attn-impl", type=int, default=1)
     ap.add_argument("--plans", default="", help="hints,gu_rows,after;... (overrides the built-in sweep)")
     a = ap.parse_args()
     cfg = bench.CONFIGS[a.config]
@@ -46,7 +45,6 @@ def main():
     G, C = cfg["G"], cfg["C"]
     pix2 = pix.flip(0).contiguous()
     lib = ops._lib.load()
-    lib.sb_set_dec_attn_impl(a.attn_impl)
     SP = SamplingParams(top_p=0.95, top_k=50, eos_ids=(dims.eos_id,), pad_id=dims.pad_id)   # the trainer's rollout options
     if "ab" in a.exp:
         # the decode step as bench.py runs it (graph replay at step 200) + the 113 GEMVs alone
