@@ -185,39 +185,23 @@ SB_DEVICE bool kept_token(uint32_t k, uint32_t kstar, int& tie_rank, int n_drop)
   return keep;
 }
 
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(ST)
-sample_kernel(const SampleParams p) {
-  pdl_launch_dependents();
-  const int tr = (blockIdx.x == 0 && threadIdx.x == 0) ? sb_trace_begin(SB_TR_SAMPLE) : -1;
-  pdl_wait();
-  sb_trace_mark(tr, 1);
+// Everything after the slice is in shared memory: cluster max, exact top-k by count, nucleus cut by mass, draw.  CLUSTER:
+// the 8 CTAs of a row work on their slices and exchange histograms through distributed shared memory; !CLUSTER: one CTA
+// alone on a short list (the compacted top-k candidates, `gidx` = their token ids), same code, same semantics.
+template <bool CLUSTER>
+SB_DEVICE void sample_core(const SampleParams& p, Shared* sh, float* wh_m, int* wh_c, float* sl, int n, int i0,
+                           const int* gidx, int row, float mx, float* red) {
   cg::cluster_group cluster = cg::this_cluster();
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  Shared* sh = reinterpret_cast<Shared*>(smem_raw);
-  float* wh_m = reinterpret_cast<float*>(smem_raw + ((sizeof(Shared) + 15) & ~15));  // [NW][256] per-warp mass
-  int* wh_c = reinterpret_cast<int*>(wh_m + NW * 256);                               // [NW][256] per-warp counts
-  float* sl = reinterpret_cast<float*>(wh_c + NW * 256);                             // this CTA's logits slice
-  __shared__ float red[32];
-
+  constexpr int NR = CLUSTER ? CL : 1;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int rank = cluster.block_rank();
-  const int row = blockIdx.x / CL;
-  const int i0 = rank * p.slice;
-  const int n = max(0, min(p.slice, p.V - i0));
-  const float* lg = p.logits + (long long)row * p.ld;
-
-  // ---- phase A: load slice (bf16-rounded), cluster max
-  float mx = -INFINITY;
-  for (int i = tid; i < n; i += ST) {
-    const float v = load_logit(p, lg, row, i0 + i);
-    sl[i] = v;
-    mx = fmaxf(mx, v);
-  }
+  const int rank = CLUSTER ? (int)cluster.block_rank() : 0;
+  auto csync = [&]() { if constexpr (CLUSTER) cluster.sync(); else __syncthreads(); };
+  auto peer = [&](int c) -> Shared* { if constexpr (CLUSTER) return cluster.map_shared_rank(sh, c); else return sh; };
   mx = block_max(mx, red);
   if (tid == 0) sh->part_f[0] = mx;
-  cluster.sync();
+  csync();
   float m = -INFINITY;
-  for (int c = 0; c < CL; ++c) m = fmaxf(m, cluster.map_shared_rank(sh, c)->part_f[0]);
+  for (int c = 0; c < NR; ++c) m = fmaxf(m, peer(c)->part_f[0]);
 
   // ---- phase A2 (top_k > 0): two-level radix select of the k-th largest key by COUNT; everything strictly below it
   // is removed (-inf) before the nucleus cut, ties at the k-th value stay (TopKLogitsWarper)
@@ -240,16 +224,16 @@ sample_kernel(const SampleParams p) {
         for (int w = 0; w < NW; ++w) c += wh_c[w * 256 + tid];
         sh->hist_c[tid] = c;
       }
-      cluster.sync();
+      csync();
       if (tid < 256) {
         int c = 0;
-        for (int q = 0; q < CL; ++q) c += cluster.map_shared_rank(sh, q)->hist_c[tid];
+        for (int q = 0; q < NR; ++q) c += peer(q)->hist_c[tid];
         sh->g_cnt[tid] = c;
       }
       __syncthreads();
       find_bin_top(sh, want, &sh->kb, &sh->kabove);
       const int b = sh->kb, above = sh->kabove;
-      cluster.sync();   // remote reads of hist_c are done before the next level overwrites it
+      csync();   // remote reads of hist_c are done before the next level overwrites it
       if (b < 0) { kth_key = 0; break; }          // fewer than k candidates: keep all (CTA- and cluster-uniform)
       if (level == 0) { hi_bin = b; want -= above; }
       else kth_key = ((uint32_t)hi_bin << 8) | (uint32_t)b;
@@ -280,20 +264,20 @@ sample_kernel(const SampleParams p) {
     sh->hist_m[tid] = s;
   }
   if (tid == 0) sh->part_f[1] = z;
-  cluster.sync();
+  csync();
   float Z = 0.f;
-  for (int c = 0; c < CL; ++c) Z += cluster.map_shared_rank(sh, c)->part_f[1];
+  for (int c = 0; c < NR; ++c) Z += peer(c)->part_f[1];
   const float thr = (1.f - p.top_p) * Z;   // unnormalised mass that may be removed (cum <= thr)
   if (tid < 256) {
     float s = 0.f;
-    for (int c = 0; c < CL; ++c) s += cluster.map_shared_rank(sh, c)->hist_m[tid];
+    for (int c = 0; c < NR; ++c) s += peer(c)->hist_m[tid];
     sh->g_hist[tid] = s;
   }
   __syncthreads();
   find_bin(sh, 0.f, thr, &sh->b1, &sh->below);
   const int b1 = sh->b1;
   const float below1 = sh->below;
-  cluster.sync();  // all remote reads of hist_m are done before it is overwritten
+  csync();  // all remote reads of hist_m are done before it is overwritten
 
   // ---- phase C: level-2 histogram (low 8 key bits) inside bin b1: mass and counts
   for (int i = tid; i < NW * 256; i += ST) { wh_m[i] = 0.f; wh_c[i] = 0; }
@@ -315,10 +299,10 @@ sample_kernel(const SampleParams p) {
     sh->hist_m[tid] = s;
     sh->hist_c[tid] = c;
   }
-  cluster.sync();
+  csync();
   if (tid < 256) {
     float s = 0.f;
-    for (int c = 0; c < CL; ++c) s += cluster.map_shared_rank(sh, c)->hist_m[tid];
+    for (int c = 0; c < NR; ++c) s += peer(c)->hist_m[tid];
     sh->g_hist[tid] = s;
   }
   __syncthreads();
@@ -328,8 +312,8 @@ sample_kernel(const SampleParams p) {
   const uint32_t kstar = ((uint32_t)b1 << 8) | (uint32_t)b2;
   // ties at the threshold key share one probability; `n_drop` of them (lowest indices first) are removed
   int tie_total = 0, tie_before = 0;
-  for (int c = 0; c < CL; ++c) {
-    const int tc = cluster.map_shared_rank(sh, c)->hist_c[b2];
+  for (int c = 0; c < NR; ++c) {
+    const int tc = peer(c)->hist_c[b2];
     tie_total += tc;
     if (c < rank) tie_before += tc;
   }
@@ -357,11 +341,11 @@ sample_kernel(const SampleParams p) {
   float my_kept;
   const float pre = excl_scan_f(kept, sh->wtot_f, my_kept);
   if (tid == 0) { sh->part_f[2] = my_kept; sh->sel = -1; sh->last = -1; }
-  cluster.sync();
+  csync();
   float kept_total = 0.f, kept_before = 0.f;
   bool later_mass = false;
-  for (int c = 0; c < CL; ++c) {
-    const float kc = cluster.map_shared_rank(sh, c)->part_f[2];
+  for (int c = 0; c < NR; ++c) {
+    const float kc = peer(c)->part_f[2];
     if (c < rank) kept_before += kc;
     if (c > rank && kc > 0.f) later_mass = true;
     kept_total += kc;
@@ -399,10 +383,119 @@ sample_kernel(const SampleParams p) {
         run += e;
       }
       if (chosen < 0) { chosen = last_kept; chosen_e = last_e; }
-      emit_token(p, row, step, i0 + chosen);
+      emit_token(p, row, step, gidx ? gidx[chosen] : i0 + chosen);
       if (p.out_logprob) p.out_logprob[row] = logf(chosen_e / kept_total);
     }
   }
+}
+
+constexpr int KCAP = 128;       // top-k fast path: candidates one CTA may contribute (local top-k incl. ties)
+constexpr int KMAX = 64;        // ... for top_k up to this
+
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(ST)
+sample_kernel(const SampleParams p) {
+  pdl_launch_dependents();
+  const int tr = (blockIdx.x == 0 && threadIdx.x == 0) ? sb_trace_begin(SB_TR_SAMPLE) : -1;
+  pdl_wait();
+  sb_trace_mark(tr, 1);
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  Shared* sh = reinterpret_cast<Shared*>(smem_raw);
+  float* wh_m = reinterpret_cast<float*>(smem_raw + ((sizeof(Shared) + 15) & ~15));  // [NW][256] per-warp mass
+  int* wh_c = reinterpret_cast<int*>(wh_m + NW * 256);                               // [NW][256] per-warp counts
+  float* sl = reinterpret_cast<float*>(wh_c + NW * 256);                             // this CTA's logits slice
+  __shared__ float red[32];
+  __shared__ float c_val[CL * KCAP];      // rank 0: the row's compacted top-k candidates, ascending token id
+  __shared__ int c_idx[CL * KCAP];
+  __shared__ int c_cnt;                   // candidates of this CTA (<= KCAP, or KCAP + 1 = overflow)
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int rank = cluster.block_rank();
+  const int row = blockIdx.x / CL;
+  const int i0 = rank * p.slice;
+  const int n = max(0, min(p.slice, p.V - i0));
+  const float* lg = p.logits + (long long)row * p.ld;
+
+  // ---- phase A: load slice (bf16-rounded)
+  float mx = -INFINITY;
+  for (int i = tid; i < n; i += ST) {
+    const float v = load_logit(p, lg, row, i0 + i);
+    sl[i] = v;
+    mx = fmaxf(mx, v);
+  }
+
+  // ---- top-k fast path (0 < top_k <= KMAX, the rollout's configuration): the row's top-k set is contained in the union
+  // of the slices' LOCAL top-k sets (ties at a local k-th value included), so every CTA selects its own <= KCAP
+  // candidates without talking to the others, the candidates are gathered in rank 0's shared memory in ascending token
+  // order (two cluster barriers), and rank 0 alone finishes on that short list.  The generic path below needs ten cluster
+  // barriers and seven passes over the slices; it still runs when a slice has more than KCAP candidates (ties).
+  if (p.top_k > 0 && p.top_k <= KMAX) {
+    __syncthreads();
+    // local k-th largest key by count (two-level radix select on this CTA's histogram only)
+    uint32_t kth_key = 0;
+    int want = p.top_k, hi_bin = -1;
+    for (int level = 0; level < 2; ++level) {
+      for (int i = tid; i < NW * 256; i += ST) wh_c[i] = 0;
+      __syncthreads();
+      for (int i = tid; i < n; i += ST) {
+        const float v = sl[i];
+        if (v == -INFINITY) continue;
+        const uint32_t k = key16(v);
+        if (level == 0) atomicAdd(&wh_c[warp * 256 + (k >> 8)], 1);
+        else if ((int)(k >> 8) == hi_bin) atomicAdd(&wh_c[warp * 256 + (k & 255)], 1);
+      }
+      __syncthreads();
+      if (tid < 256) {
+        int c = 0;
+        for (int w = 0; w < NW; ++w) c += wh_c[w * 256 + tid];
+        sh->g_cnt[tid] = c;
+      }
+      __syncthreads();
+      find_bin_top(sh, want, &sh->kb, &sh->kabove);
+      const int b = sh->kb, above = sh->kabove;
+      __syncthreads();
+      if (b < 0) { kth_key = 0; break; }          // fewer than k finite entries in this slice: all of them are candidates
+      if (level == 0) { hi_bin = b; want -= above; }
+      else kth_key = ((uint32_t)hi_bin << 8) | (uint32_t)b;
+    }
+    // compaction in index order: each thread owns a contiguous chunk
+    const int per = (n + ST - 1) / ST;
+    const int a0 = min(tid * per, n), a1 = min(a0 + per, n);
+    int mine = 0;
+    for (int i = a0; i < a1; ++i) mine += (sl[i] != -INFINITY && key16(sl[i]) >= kth_key) ? 1 : 0;
+    int total;
+    const int pos0 = excl_scan_i(mine, sh->wtot_i, total);
+    if (tid == 0) c_cnt = total <= KCAP ? total : KCAP + 1;
+    cluster.sync();
+    int before = 0;
+    bool overflow = false;
+    for (int c = 0; c < CL; ++c) {
+      const int cc = *cluster.map_shared_rank(&c_cnt, c);
+      overflow |= cc > KCAP;
+      if (c < rank) before += cc;
+    }
+    if (!overflow) {     // cluster-uniform
+      float* dv = cluster.map_shared_rank(c_val, 0);
+      int* di = cluster.map_shared_rank(c_idx, 0);
+      int pos = before + pos0;
+      for (int i = a0; i < a1; ++i) {
+        const float v = sl[i];
+        if (v != -INFINITY && key16(v) >= kth_key) { dv[pos] = v; di[pos] = i0 + i; ++pos; }
+      }
+      int n_all = 0;
+      for (int c = 0; c < CL; ++c) n_all += *cluster.map_shared_rank(&c_cnt, c);
+      cluster.sync();    // candidates are in rank 0's shared memory; nobody reads remote memory after this point
+      if (rank != 0) return;
+      float m2 = -INFINITY;
+      for (int i = tid; i < n_all; i += ST) m2 = fmaxf(m2, c_val[i]);
+      sample_core<false>(p, sh, wh_m, wh_c, c_val, n_all, 0, c_idx, row, m2, red);
+      sb_trace_mark(tr, 2);
+      return;
+    }
+    __syncthreads();
+  }
+
+  sample_core<true>(p, sh, wh_m, wh_c, sl, n, i0, nullptr, row, mx, red);
   cluster.sync();  // keep every CTA's shared memory alive until all remote reads are done
   sb_trace_mark(tr, 2);
 }
