@@ -505,8 +505,8 @@ def main():
     ach = stats.get("decode_gbs") or 0.0
     # DRAM bytes of one decode step measured under ncu (--cache-control none), committed with the profile it came from
     traffic, traffic_src = None, None
-    tpath = next((q for q in (os.path.join(ROOT, "profiles", f"r0{r}_decode_traffic_{args.config}.json") for r in (2, 1))
-                  if os.path.exists(q)), "")
+    tpath = next((q for q in (os.path.join(ROOT, "profiles", f"r0{r}_decode_traffic_{args.config}{sfx}.json")
+                              for r, sfx in ((2, "_final"), (2, ""), (1, ""))) if os.path.exists(q)), "")
     if tpath:
         with open(tpath) as f:
             tj = json.load(f)

@@ -323,6 +323,25 @@ def test_sampler_matches_hf_processor_chain(V, rep_pen, temperature, top_k, top_
             assert (int(seen[r, last >> 5].item()) >> (last & 31)) & 1
 
 
+def test_sampler_topk_tie_overflow_takes_generic_path():
+    """300 tokens tie at the k-th value inside ONE cluster slice: more candidates than the top-k fast path gathers per CTA
+    (KCAP = 128), so the kernel falls back to the generic path; TopKLogitsWarper keeps the whole tie group either way."""
+    V, R, n_draws = 4096, 2, 4000
+    logits = rnd((R, V), 77, 1.0, torch.float32)
+    logits[0, 100:400] = 9.0
+    context = torch.zeros((R, 1), dtype=torch.long)
+    ids = _draw(logits, n_draws, top_p=1.0, top_k=50, temperature=1.0, repetition_penalty=1.0)
+    exact = _hf_chain(logits.bfloat16().float().cpu(), context, 1.0, 1.0, 50, 1.0, reround=True)
+    assert int((exact[0] > 0).sum()) == 300
+    for r in range(R):
+        kept = set(torch.nonzero(exact[r] > 0).flatten().tolist())
+        assert set(ids[r].tolist()) <= kept
+        got = torch.bincount(ids[r], minlength=V).float() / n_draws
+        tv = 0.5 * (got - exact[r]).abs().sum().item()
+        assert tv < 3 * math.sqrt(len(kept) / (2 * math.pi * n_draws)) + 0.02, (r, tv)
+    assert len(set(ids[0].tolist())) > 200       # the tie group is really sampled from, not truncated to 128
+
+
 def test_sampler_greedy_with_repetition_penalty_and_eos_list():
     """Evaluation decoding (checkpoint generation_config: repetition_penalty 1.05, top_k 1; vsibench.py:174): argmax of
     the penalised logits; ANY id of the eos list finishes a row."""
