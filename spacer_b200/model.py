@@ -1041,13 +1041,16 @@ class Qwen2VLB200:
         """Fork: the side stream waits for what the main stream has enqueued so far, then requests the first `rows` rows of
         every 128-row tile of `w`.  Joined once, at the end of the step."""
         n_rows, k = w.shape
+        chunk = min(int(rows), 128) * k * 2
+        if n_rows < 128 or chunk % 128:          # nothing sensible to request for toy shapes
+            return
         main = torch.cuda.current_stream()
         ev = torch.cuda.Event()
         ev.record(main)
         side = st["side"]
         side.wait_event(ev)
         with torch.cuda.stream(side):
-            ops.call("sb_dec_l2_prefetch", w, min(int(rows), 128) * k * 2, 128 * k * 2, n_rows // 128, int(self.PF_CTAS), int(self.PF_PACE_NS))
+            ops.call("sb_dec_l2_prefetch", w, chunk, 128 * k * 2, n_rows // 128, int(self.PF_CTAS), int(self.PF_PACE_NS))
         st["forked"] = True
 
     def _splits_for(self, n_out, k):

@@ -202,6 +202,33 @@ def test_generate_semantics_and_decode_parity():
     assert err < 3e-2 * ref_b.abs().max().item() + 5e-3, err
 
 
+def test_l2_plan_of_the_decode_step_does_not_change_the_tokens():
+    """The L2 plan of the decode step (evict_first weight streams, paced evict_last prefetch of gate|up row subsets on a side
+    stream / parallel graph branch) only moves cache lines: rollouts are bit-identical with it on, off, and with any of its
+    variants (bulk / paced requests, released by different kernels), graph or eager."""
+    from spacer_b200 import ops
+    R, d_or, d, m, w, wb = _setup()
+    case = _case(d_or)
+    grid, prompt, pix = case["grid_thw"], case["prompt_ids"], case["pixel_values"].cuda()
+    lib = ops._lib.load()
+    kw = dict(max_new_tokens=7, num_return_sequences=4, top_p=0.95, seed=9, min_new_tokens=7)
+    saved = (m.PF_GU_ROWS, m.PF_AFTER, m.PF_CTAS, m.PF_PACE_NS)
+    try:
+        ref = m.generate(prompt, pix, grid, **kw)
+        for hints, rows, after, ctas, pace, graph in ((0, 0, "qkv", 0, 750, True), (1, 0, "qkv", 0, 750, True),
+                                                      (1, 24, "qkv_post", 0, 0, True), (1, 32, "combine", 16, -1, True),
+                                                      (1, 24, "qkv", 0, 750, False)):
+            lib.sb_set_dec_l2_hints(hints)
+            m.PF_GU_ROWS, m.PF_AFTER, m.PF_CTAS, m.PF_PACE_NS = rows, after, ctas, pace
+            m._dec = None                                   # new decode state: the captured graphs belong to the old plan
+            out = m.generate(prompt, pix, grid, use_graph=graph, **kw)
+            assert torch.equal(out, ref), (hints, rows, after, ctas, pace, graph)
+    finally:
+        lib.sb_set_dec_l2_hints(1)
+        m.PF_GU_ROWS, m.PF_AFTER, m.PF_CTAS, m.PF_PACE_NS = saved
+        m._dec = None
+
+
 def test_trainer_step_runs_and_updates():
     from spacer_b200 import rewards as RW
     from spacer_b200.model import Qwen2VLB200
