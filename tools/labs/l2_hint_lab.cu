@@ -186,7 +186,23 @@ int main() {
   // interference of ~70 MB = 76 tiles; 0 = none
   const Trial trials[] = {
       //                         mode k_lo k_hi stride(ks) tpc tiles pfpol strpol interf ipol spin
+      // --- how fast does an L2-resident matrix stream (mode -2: `tiles` m-tiles x `stride` K splits, read 4 times)
+      {"hot_37x4",                 -2, 0, 0, 4, 0, 37,  0, 0, 0, 0, 0},
+      {"hot_74x2",                 -2, 0, 0, 2, 0, 74,  0, 0, 0, 0, 0},
+      {"hot_111x1",                -2, 0, 0, 1, 0, 111, 0, 0, 0, 0, 0},
+      {"hot_148x1",                -2, 0, 0, 1, 0, 148, 0, 0, 0, 0, 0},
+      // --- nothing prefetched
       {"baseline",                 -1, 0, 0, 1, 0, 0,   0, 0, 76, 0, 0},
+      {"baseline_evict_first",     -1, 0, 0, 1, 0, 0,   0, 1, 76, 1, 0},
+      // --- contiguous head of the matrix (the layout rounds 1-2 tried), every 4th K block of every tile
+      {"head53tiles",               2, 0, 0, 1, 0, 53,  0, 0, 76, 0, 0},
+      {"head53tiles_nointerf",      2, 0, 0, 1, 0, 53,  0, 0, 0, 0, 12},
+      {"head53tiles_pol",           2, 0, 0, 1, 0, 53,  2, 1, 76, 1, 0},
+      {"inter4_both_nointerf",      1, 10, 0, 4, 2, 0,  0, 0, 0, 0, 12},
+      {"inter4_both",               1, 10, 0, 4, 2, 0,  0, 0, 76, 0, 0},
+      {"inter4_both_pol",           1, 10, 0, 4, 2, 0,  2, 1, 76, 1, 0},
+      {"inter8_both_pol",           1, 10, 0, 8, 2, 0,  2, 1, 76, 1, 0},
+      // --- the first rows of every 128-row tile
       {"rows32_both_nointerf",      3, 0, 32, 1, 2, 0,  0, 0, 0, 0, 14},
       {"rows32_both",               3, 0, 32, 1, 2, 0,  0, 0, 76, 0, 0},
       {"rows32_both_pol",           3, 0, 32, 1, 2, 0,  2, 1, 76, 1, 0},
