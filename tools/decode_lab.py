@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""A/B timing of the decode step on one B200 (cfg3 shapes): PDL on/off, L2 weight prefetch size, per-GEMV cold/warm/hot.
+"""A/B timing of the decode step on one B200 (cfg3 shapes): L2 plan (hints, paced prefetch variants), kernel timeline trace,
+per-CTA GEMV timeline (--exp skew), per-GEMV cold/warm/hot.
 Prints one JSON line per experiment.   python tools/decode_lab.py [--config c3]"""
 import argparse
 import ctypes
@@ -217,8 +218,8 @@ def main():
         W = m.params
         S = st["S"]
         shapes = [("qkv", W["l.5.qkv_w"], st["xn"], st["p_qkv"], S["qkv"]), ("o", W["l.5.o_w"], st["attn"], st["p_o"], S["o"]),
-                  ("gu", W["l.5.gu_w"], st["xn"], st["p_gu"], S["gu"]), ("down", W["l.5.down_w"], st["act"], st["p_down"], S["down"])]
-        dummy_w = W["l.20.o_w"]
+                  ("gu", W["l.5.gu_w"], st["xn"], st["act"] if S["gu"] == 1 else st["p_gu"], S["gu"]),
+                  ("down", W["l.5.down_w"], st["act"], st["p_down"], S["down"])]
         for name, w, x, out, s in shapes:
             nbytes = w.numel() * 2
             res = {"exp": "gemv", "name": name, "mb": round(nbytes / 1e6, 1), "splits": s}
@@ -229,16 +230,16 @@ def main():
                 n = 10
                 for _ in range(n):
                     flush.fill_(1)                       # evict L2
-                    if mode == "warm":                    # a carrier GEMV prefetches w into L2, a small kernel gives it time
-                        m._gemv(dummy_w, st["attn"], st["p_o"], S["o"], next_w=w)
+                    if mode == "warm":                    # the paced prefetch kernel warms 24 rows per tile of w, then a pause
+                        ops.call("sb_dec_l2_prefetch", w, 24 * w.shape[1] * 2, 128 * w.shape[1] * 2, w.shape[0] // 128, 0, 750)
                         for _ in range(4):
                             ops.call("sb_dec_swiglu", st["p_gu"], S["gu"], st["RP"] * 2 * dims.inter, 2 * dims.inter, st["act"], st["R"], dims.inter)
                     elif mode == "hot":
-                        m._gemv(w, x, out, s)
+                        m._gemv(w, x, out, s, swiglu=(name == "gu" and s == 1))
                     elif mode == "cold_after_small":
                         ops.call("sb_dec_swiglu", st["p_gu"], S["gu"], st["RP"] * 2 * dims.inter, 2 * dims.inter, st["act"], st["R"], dims.inter)
                     e0.record()
-                    m._gemv(w, x, out, s)
+                    m._gemv(w, x, out, s, swiglu=(name == "gu" and s == 1))
                     e1.record()
                     torch.cuda.synchronize()
                     tot += e0.elapsed_time(e1)
