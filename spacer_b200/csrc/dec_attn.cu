@@ -341,7 +341,8 @@ dec_attn_tc_kernel(const __grid_constant__ Maps maps, const DecAttnParams p, int
       if (it > 0) {
         mbar_wait(pv_done, (it - 1) & 1);
         tc_fence_after();
-        if (__any_sync(0xffffffffu, factor != 1.f)) {
+        // (lanes beyond n_q hold whatever their never-written Q row produced: they must not trigger the rescale)
+        if (__any_sync(0xffffffffu, r < n_q && factor != 1.f)) {
 #pragma unroll 1
           for (int c = 0; c < HD / 32; ++c) {
             uint32_t v[32];
